@@ -1,0 +1,151 @@
+"""TEST INFRASTRUCTURE ONLY -- generate the golden fixtures under tests/golden/ by executing the
+UNMODIFIED reference (``/root/reference``, build container only; it cannot travel to the GPU box).
+
+    python -m oracle.make_golden            # writes tests/golden/*.npz, *.json
+
+Fixtures:
+  full_<cfg>_n<N>_s<a>_<b>.npz   every output of hit.tracks + device.calculate_device_hit for a small N
+  digest_<cfg>_n<N>_s<a>_<b>.json  sha256 of every output array for N=1e5 (too large to commit verbatim)
+  helpers.json                   known-answer values of the reference's helper functions (hex floats)
+
+Seeds: ``a`` seeds the interpreter's numpy RNG, ``b`` Numba's MT19937 (two independent streams,
+SURVEY.md H1).
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import reference_shim  # noqa: E402
+from pytestbeam_b200 import config as cfg  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+TRACK_NAMES = ("energy", "anglex", "angley", "x", "y", "z", "time_stamp")
+
+FULL_CASES = [("c1", 1000, 11, 22), ("c3", 1000, 33, 44), ("c4", 1000, 55, 66)]
+DIGEST_CASES = [("c1", 100_000, 1, 2), ("c3", 100_000, 3, 4), ("c4", 100_000, 5, 6)]
+
+
+def sha(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def run_case(name, n, s_interp, s_numba):
+    setup = getattr(cfg, name)(n)
+    beam, devices, materials, names = cfg.flatten(setup)
+    tracks, eloss, hits = reference_shim.run_reference(beam, devices, materials, names, s_interp, s_numba)
+    return names, tracks, eloss, hits
+
+
+def helper_kats():
+    hit, device, _, _ = reference_shim.load()
+    out = {"highland": [], "cloud_sigma_terms": [], "pixel_index": [], "pixel_centre": [], "gauss": [],
+           "moyal_pdf": [], "noise_sigma": []}
+    for thick, x0, e in [(50, 93650, 5000.0), (300, 93650, 4999.7), (1000, 5612, 100.0), (50, 93650, 0.6),
+                         (100, 93650, 99.2)]:
+        out["highland"].append([thick, x0, float(e).hex(), float(hit.highlander_fast_electrons(thick, x0, e)).hex()])
+    # calc_cluster_radius draws a normal; pin it through a seeded stream: |sigma * z| with known z
+    from numba import njit
+
+    @njit
+    def radius_with_seed(seed, energy):
+        np.random.seed(seed)
+        return device.calc_cluster_radius(energy)
+
+    for e in [0.0, 0.0137, 0.083, 0.5, 0.03286]:
+        z = np.random.RandomState(7).standard_normal()
+        r = radius_with_seed(7, e)
+        out["cloud_sigma_terms"].append([float(e).hex(), float(z).hex(), float(r).hex()])
+    for x, delta, pitch, number in [(0.0, 0, 18.4, 1152), (-10.0, 100, 18.4, 1152), (5298.0, 100, 18.4, 1152),
+                                    (-10700.0, 0, 18.4, 1152), (-10600.1, 0, 18.4, 576), (9999.99, -2500, 50, 400),
+                                    (-30000.0, 0, 40000, 1), (19999.0, 0, 40000, 1), (20001.0, 0, 40000, 1),
+                                    (-59999.0, 0, 40000, 1), (1234.5678, 6000, 33.04, 512)]:
+        out["pixel_index"].append([float(x).hex(), delta, pitch, number,
+                                   int(device._row_col_from_hit(x, delta, pitch, number))])
+    for idx, delta, pitch, number in [(1, 0, 18.4, 1152), (577, 100, 18.4, 1152), (1152, -2500, 18.4, 1152),
+                                      (0, 0, 50, 400), (-3, 6000, 50, 384), (1, 0, 40000, 1), (300, 0, 33.04, 512)]:
+        out["pixel_centre"].append([idx, delta, pitch, number,
+                                    float(device._hit_from_row_col(idx, delta, pitch, number)).hex()])
+    for x, s in [(0.0, 20.4), (9.2, 3.3), (-18.4, 0.3989422804014327), (55.0, 41.0), (1e-3, 1.0)]:
+        out["gauss"].append([float(x).hex(), float(s).hex(), float(device.gauss(x, 0, s)).hex()])
+    for delta in [0.0, 0.0315, 0.0752, 0.2, 0.5]:
+        for args in [(50 * 10 ** (-4), -1, 14, 24, 5000.0, 2.33, 1), (300 * 10 ** (-4), -1, 14, 24, 4999.8, 2.33, 1),
+                     (1000 * 10 ** (-4), -1, 82, 207, 99.9, 11.35, 1)]:
+            v = hit.landau_approx(np.array([delta]), *args)[0]
+            out["moyal_pdf"].append([float(delta).hex(), [float(a).hex() for a in args], float(v).hex()])
+
+    @njit
+    def noise_with_seed(seed, rp, cp, th):
+        np.random.seed(seed)
+        return device.draw_noise_charge(300, rp, cp, th)
+
+    for rp, cp, th in [(18.4, 18.4, 50), (50, 50, 300), (40000, 40000, 1000), (33.04, 33.04, 100)]:
+        z = np.random.RandomState(9).standard_normal()
+        out["noise_sigma"].append([rp, cp, th, float(z).hex(), float(noise_with_seed(9, rp, cp, th)).hex()])
+    # whole clusters with their f8 charges (the /Hits table only keeps f4): seeded Numba stream,
+    # device.py:139-155 call sequence for a single particle
+    @njit
+    def cluster_with_seed(seed, pc, nc, dx, x, pr, nr, dy, y, thr, th, e):
+        np.random.seed(seed)
+        rx = device.calc_cluster_radius(e)
+        ry = device.calc_cluster_radius(e)
+        c, r, q = device.calc_cluster_hits(pc, nc, dx, x, pr, nr, dy, y, rx, ry, thr * 1e-3, th, e)
+        return rx, ry, np.array(c), np.array(r), np.array(q)
+
+    out["clusters"] = []
+    rs = np.random.RandomState(2024)
+    geos = [(18.4, 1152, 100, 18.4, 576, 0, 100, 50), (50, 400, 0, 50, 384, 0, 1000, 300),
+            (33.04, 512, -2500, 33.04, 512, 6000, 200, 100), (40000, 1, 0, 40000, 1, 0, 1e9, 1000),
+            (18.4, 1152, 0, 18.4, 576, 0, 0, 50)]
+    for i in range(60):
+        pc, nc, dx, pr, nr, dy, thr, th = geos[i % len(geos)]
+        x = float(rs.uniform(-0.55, 0.55) * pc * nc)
+        y = float(rs.uniform(-0.55, 0.55) * pr * nr)
+        e = float([0.0, 0.0137, 0.0329, 0.083, 0.31][i % 5] * rs.uniform(0.5, 1.5))
+        seed = 1000 + i
+        rx, ry, c, r, q = cluster_with_seed(seed, pc, nc, dx, x, pr, nr, dy, y, thr, th, e)
+        out["clusters"].append({"seed": seed, "geo": [pc, nc, dx, pr, nr, dy, thr, th], "x": x.hex(), "y": y.hex(),
+                                "e": e.hex(), "rx": float(rx).hex(), "ry": float(ry).hex(),
+                                "col": [int(v) for v in c], "row": [int(v) for v in r],
+                                "q": [float(v).hex() for v in q]})
+    return out
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    for name, n, a, b in FULL_CASES:
+        names, tracks, eloss, hits = run_case(name, n, a, b)
+        blob = {"names": np.array(names), "eloss": eloss}
+        for nm, arr in zip(TRACK_NAMES, tracks):
+            blob[nm] = np.asarray(arr)
+        for dn in names:
+            blob["hits_" + dn] = hits[dn]
+        path = os.path.join(GOLD, f"full_{name}_n{n}_s{a}_{b}.npz")
+        np.savez_compressed(path, **blob)
+        print("wrote", path, os.path.getsize(path))
+    for name, n, a, b in DIGEST_CASES:
+        names, tracks, eloss, hits = run_case(name, n, a, b)
+        dig = {"config": name, "n": n, "seed_interp": a, "seed_numba": b, "names": names,
+               "eloss": sha(eloss), "tracks": {nm: sha(np.asarray(arr)) for nm, arr in zip(TRACK_NAMES, tracks)},
+               "track_dtypes": {nm: str(np.asarray(arr).dtype) for nm, arr in zip(TRACK_NAMES, tracks)},
+               "hits": {dn: {"n": int(len(hits[dn])), "sha256": sha(hits[dn]),
+                             "sum_charge": float(hits[dn]["charge"].astype(np.float64).sum())} for dn in names}}
+        path = os.path.join(GOLD, f"digest_{name}_n{n}_s{a}_{b}.json")
+        with open(path, "w") as f:
+            json.dump(dig, f, indent=1)
+        print("wrote", path)
+    with open(os.path.join(GOLD, "helpers.json"), "w") as f:
+        json.dump(helper_kats(), f, indent=1)
+    print("wrote helpers.json")
+
+
+if __name__ == "__main__":
+    main()
