@@ -1,0 +1,172 @@
+/*
+ * ptb.h -- C ABI of libptb_b200: the per-particle Monte Carlo hot path of pytestbeam as sm_100a CUDA
+ * kernels.  Plain pointers and sizes only; no torch, no C++ types.  Every entry point is
+ * stream-ordered and non-blocking; the caller owns all device buffers (hit slabs, track tables,
+ * injected variates, workspace); the library owns only the handle (host memory).
+ *
+ * What each entry point replaces in the reference (rpartzsch/pytestbeam has no FFI layer; the boundary
+ * is two Python calls and the two Numba kernels behind them -- SURVEY.md section 8b):
+ *
+ *   ptb_create      the flattening of setup.yml / material.yml into per-plane scalar lists:
+ *                   pytestbeam/main/hit.py:24-61 and pytestbeam/main/device.py:30-53
+ *   ptb_prefix      the two running counters the sequential loops carry across particles: the accepted-
+ *                   event counter (main/device.py:134,164-165) and the cumulative time stamp
+ *                   (main/hit.py:73,239); needed up front only when particles are sharded
+ *   ptb_simulate    generate_tracks (main/hit.py:141-241, called at :107), the Landau table it consumes
+ *                   (main/hit.py:84-102 with sample_dist_fast :327-368), the trigger mask
+ *                   (main/device.py:56) and calc_position (main/device.py:91-168, called at :68) for
+ *                   every plane, fused; with PTB_TRACKS_FROM_TABLE it is calc_position alone, fed from
+ *                   the hit_tables tuple exactly as main/device.py:132-138 reads it
+ *   PtbTrackTable   the 8-tuple returned by hit.tracks (main/hit.py:138)
+ *   PtbHitSlab      the per-device hit table (main/device.py:20-28,66,156-163), as structure of arrays
+ *   ptb_pack_hits   the structured-array rows handed to create_hit_file (main/device.py:317-327)
+ *
+ * Error convention: 0 on success, negative PTB_E_* otherwise; nothing is thrown across the ABI.
+ * Conditions detected on the device (staging or slab overflow) are reported in PtbTotals.error, which
+ * the caller reads after synchronising the stream.
+ * One handle per GPU; a handle is not thread-safe, distinct handles are independent.
+ */
+#ifndef PTB_H_
+#define PTB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTB_MAX_PLANES 32
+
+/* return codes */
+#define PTB_OK 0
+#define PTB_E_INVALID (-1)   /* bad argument / unsupported geometry (see ptb_last_error) */
+#define PTB_E_CUDA (-2)      /* a CUDA runtime call failed */
+#define PTB_E_NOMEM (-3)
+
+/* bits of PtbTotals.error (device-detected) */
+#define PTB_DEV_STAGE_OVERFLOW 1u /* one 32-particle group produced more hits on one plane than stage_hits */
+#define PTB_DEV_SLAB_OVERFLOW 2u  /* a hit slab's capacity was exceeded; totals still hold the exact counts */
+#define PTB_DEV_BOX_TOO_LARGE 4u  /* a cluster bounding box exceeded 2^20 pixels */
+
+/* flags of PtbRun.flags */
+#define PTB_DIGITISE 1u          /* run the cluster digitisation and fill the hit slabs */
+#define PTB_TRACKS_FROM_TABLE 2u /* do not generate tracks: read x, y, eloss from PtbRun.tracks (calc_position alone) */
+#define PTB_WRITE_TRACKS 4u      /* store the per-plane track records into PtbRun.tracks */
+#define PTB_KEEP_CHARGE64 8u     /* also store the f8 charge of every hit (PtbHitSlab.charge64) */
+
+/* beam block of setup.yml; lengths um, angles rad, energy MeV, rate Hz */
+typedef struct PtbBeam {
+    double energy, sigma_x, sigma_y, loc_x, loc_y, disp_x, disp_y, angle_x, angle_y, particle_rate;
+} PtbBeam;
+
+/* one device of setup.yml with its material.yml entry, in beam order */
+typedef struct PtbDevice {
+    int32_t ncol, nrow;
+    double  pitch_c, pitch_r, thickness, z, delta_x, delta_y;
+    double  threshold_e;  /* electrons, as written in setup.yml */
+    int32_t triggered;    /* trigger: "triggered" -> 1 */
+    int32_t _pad;
+    double  rad_length, Z, A, rho;
+} PtbDevice;
+
+typedef struct PtbOptions {
+    int32_t stage_hits;   /* hits one 32-particle group may produce on one plane; 0 = choose from the geometry */
+    int32_t fast_math;    /* 0: IEEE operation order of the reference, no FMA contraction; 1: contracted build */
+    double  trigger_accept; /* main/device.py:56 hard-codes 0.7; 0 = use that */
+} PtbOptions;
+
+/*
+ * Deterministic mode: every random variate of particles [first, first+n) pre-drawn by the caller
+ * (device pointers, indexed by k - first).  Layout = oracle/cpu_oracle.py:Variates.
+ */
+typedef struct PtbInjected {
+    const double  *zstart;   /* [n][4]  standard normals for (angle_x, angle_y, x, y) at the source */
+    const int64_t *gap;      /* [n]     Poisson gap to the previous particle, ns */
+    const double  *zkick;    /* [n][D-1][2] standard normals of the scattering kicks at planes 1..D-1 */
+    const double  *eloss;    /* [D][n]  Landau energy loss per plane before the acceptance zeroing */
+    const uint8_t *accepted; /* [n]     trigger mask */
+    const double  *dig_z;    /* digitisation normals, concatenated */
+    const int64_t *dig_off;  /* [D][n+1] offsets into dig_z: (radius_x, radius_y, seed noise, pixel noise ...) */
+    double         eloss0_prev; /* eloss[0][first-1]; ignored when first == 0 */
+} PtbInjected;
+
+/* the reference's hit_tables tuple (main/hit.py:138) for particles [first, first+n), particle-major */
+typedef struct PtbTrackTable {
+    double  *energy, *angle_x, *angle_y, *x, *y, *z; /* [n*D] */
+    int64_t *time_stamp;                              /* [n*D] */
+    double  *eloss;                                   /* [D][n] after the acceptance zeroing */
+    uint8_t *accepted;                                /* [n] trigger mask (input with PTB_TRACKS_FROM_TABLE) */
+} PtbTrackTable;
+
+/* hit table of one plane as structure of arrays; rows in particle order, then column-major in the cluster */
+typedef struct PtbHitSlab {
+    int64_t  *event;    /* event_number */
+    uint16_t *col;      /* column, 1-based */
+    uint16_t *row;      /* row, 1-based */
+    float    *charge;   /* ke */
+    double   *charge64; /* optional (PTB_KEEP_CHARGE64) */
+    uint64_t  capacity; /* rows */
+} PtbHitSlab;
+
+/* running prefixes carried from one particle range to the next (device memory) */
+typedef struct PtbBases {
+    int64_t  event;            /* accepted particles before `first` */
+    int64_t  time;             /* time stamp of particle first-1 (0 when first == 0) */
+    uint64_t hits[PTB_MAX_PLANES]; /* rows already in each slab (row offset at which this range starts) */
+} PtbBases;
+
+/* per-call results (device memory) */
+typedef struct PtbTotals {
+    uint64_t hits[PTB_MAX_PLANES]; /* rows produced per plane by this call */
+    uint64_t accepted;
+    int64_t  time_sum;
+    uint64_t pairs, inside, pixels; /* census: digitised (particle,plane) pairs, seed-in-matrix pairs, pixel evaluations */
+    uint32_t error, _pad;
+} PtbTotals;
+
+typedef struct PtbRun {
+    uint64_t first, n;   /* global particle index range */
+    uint64_t seed;       /* Philox key (production mode) */
+    uint32_t flags, _pad;
+    const PtbInjected *injected;   /* host pointer to the struct, or NULL for production (Philox) mode */
+    PtbTrackTable      tracks;     /* used with PTB_TRACKS_FROM_TABLE / PTB_WRITE_TRACKS */
+    PtbHitSlab         slabs[PTB_MAX_PLANES];
+    const PtbBases    *bases_in;   /* device; NULL = all zero */
+    PtbBases          *bases_out;  /* device; bases_in + this call's totals; may alias bases_in; may be NULL */
+    PtbTotals         *totals;     /* device; required */
+    void              *workspace;  /* device; ptb_workspace_bytes(handle, n, capacities) bytes */
+    size_t             workspace_bytes;
+} PtbRun;
+
+typedef struct PtbContext *PtbHandle;
+
+int         ptb_create(const PtbBeam *beam, const PtbDevice *devices, int32_t n_devices, const PtbOptions *opt,
+                       PtbHandle *out);
+void        ptb_destroy(PtbHandle h);
+const char *ptb_last_error(PtbHandle h);
+int32_t     ptb_n_planes(PtbHandle h);
+int32_t     ptb_stage_hits(PtbHandle h);
+
+/* bytes of workspace ptb_simulate needs for n particles and the given slab capacities */
+size_t ptb_workspace_bytes(PtbHandle h, uint64_t n, const uint64_t *capacity /*[n_planes]*/, uint32_t flags);
+
+/* out_dev[0] += accepted particles in [first, first+n); out_dev[1] += sum of their Poisson gaps */
+int ptb_prefix(PtbHandle h, uint64_t first, uint64_t n, uint64_t seed, const PtbInjected *inj, int64_t *out_dev,
+               void *stream);
+
+int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream);
+
+/* SoA slab rows [0, n) -> packed 18-byte records (event_number <i8, frame <u2 = 0, column <u2, row <u2, charge <f4) */
+int ptb_pack_hits(const PtbHitSlab *slab, uint64_t n, void *out_dev, void *stream);
+
+/* number of kernels this library has launched on the calling process since load (bench bookkeeping) */
+uint64_t ptb_launch_count(void);
+
+/* in-job FP64 peak probe: dependent DFMA chains on every SM; returns FLOP/s (2 per DFMA), <0 on error */
+double ptb_measure_fp64_peak(void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTB_H_ */

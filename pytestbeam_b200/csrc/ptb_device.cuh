@@ -1,0 +1,298 @@
+// Device-side building blocks of libptb_b200: counter-based RNG, variate sources and the physics of one
+// particle at one plane.  Everything in here is written from the behavioural spec in SURVEY.md
+// Appendix A; the reference lines each formula answers to are cited next to it.
+//
+// Arithmetic contract (exact build, -fmad=false): every expression is evaluated in IEEE double in the
+// operation order of the reference's Numba code, so that with identical injected variates the results
+// differ from the CPU only through the <=2 ulp of CUDA's tan / exp / pow against glibc's.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "ptb.h"
+
+namespace ptb {
+
+// ---------------------------------------------------------------------------------------------------
+// configuration derived on the host (ptb_create) and passed as a __grid_constant__ kernel parameter,
+// i.e. it lives in the constant bank and is read with uniform LDC
+// ---------------------------------------------------------------------------------------------------
+struct PlaneK {
+    double z;
+    double x_pos, x_neg, y_pos, y_neg;   // acceptance window, main/hit.py:56-59
+    double eps, corr2;                   // thickness/X0 and (1+0.038 ln eps)^2, main/hit.py:294-296
+    double pitch_c, pitch_r, delta_x, delta_y;
+    double half_nc, half_nr;             // number / 2 (true division), main/device.py:356,372
+    double half_pc, half_pr;             // pitch / 2
+    double thr_ke;                       // threshold * 1e-3, main/device.py:152
+    double noise_sigma;                  // sqrt(k_b*300*C)/e, main/device.py:410-415
+    double lan_loc, lan_scale;           // energy loss = loc + scale * lambda (Moyal variable), main/hit.py:399-400
+    double lan_ulo, lan_uspan;           // window of the Moyal CDF that maps onto [0, 0.5] MeV, main/hit.py:99-100
+    int32_t ncol, nrow, triggered, _pad;
+};
+
+struct ConfigK {
+    int32_t n_planes, stage_hits;
+    double  energy, loc_x, sigma_x, loc_y, sigma_y, disp_x, disp_y, angle_x, angle_y;
+    double  theta0_first;                // Highland width of plane 0 at beam energy: event 0 only, main/hit.py:75-80
+    double  accept_p;                    // main/device.py:56
+    // Poisson gap, main/hit.py:33,239
+    double  lam, p_loglam, p_b, p_a, p_log_invalpha, p_vr, p_explam;
+    // charge-cloud constants, main/device.py:186-202
+    double  diff2, qe, c3mu, t90, cden;
+    PlaneK  pl[PTB_MAX_PLANES];
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  key = 64-bit seed, counter = (particle id lo, hi, site, index)
+// ---------------------------------------------------------------------------------------------------
+struct U4 {
+    uint32_t x, y, z, w;
+};
+
+__host__ __device__ __forceinline__ void mulhilo(uint32_t a, uint32_t b, uint32_t &hi, uint32_t &lo)
+{
+#ifdef __CUDA_ARCH__
+    lo = a * b;
+    hi = __umulhi(a, b);
+#else
+    uint64_t p = (uint64_t)a * b;
+    lo = (uint32_t)p;
+    hi = (uint32_t)(p >> 32);
+#endif
+}
+
+__host__ __device__ __forceinline__ U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t h0, l0, h1, l1;
+        mulhilo(0xD2511F53u, c.x, h0, l0);
+        mulhilo(0xCD9E8D57u, c.z, h1, l1);
+        c = U4{h1 ^ c.y ^ k0, l1, h0 ^ c.w ^ k1, l0};
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// draw sites of one particle; plane-dependent sites are SITE_PLANE + 4*plane + {STEP,DIG,PIX}
+enum : uint32_t { SITE_EVENT = 0, SITE_START = 1, SITE_PLANE = 4, SUB_STEP = 0, SUB_DIG = 1, SUB_PIX = 2 };
+
+__device__ __forceinline__ U4 philox_at(uint64_t seed, uint64_t particle, uint32_t site, uint32_t index)
+{
+    return philox4x32_10(U4{(uint32_t)particle, (uint32_t)(particle >> 32), site, index}, (uint32_t)seed,
+                         (uint32_t)(seed >> 32));
+}
+
+// 53-bit uniform in [0,1) the way numpy/numba build it from two words
+__device__ __forceinline__ double u53_closed_open(uint32_t a, uint32_t b)
+{
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+// 53-bit uniform in (0,1)
+__device__ __forceinline__ double u53_open(uint32_t a, uint32_t b)
+{
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+// Box-Muller pair in fp32 arithmetic, returned as doubles (sites that tolerate 24-bit normals)
+__device__ __forceinline__ void normal_pair_f32(uint32_t a, uint32_t b, double &n0, double &n1)
+{
+    float u = fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // (0,1]
+    float v = fmaf((float)b, 4.6566128730773926e-10f, 2.3283064365386963e-10f);   // (0,2]
+    float r = sqrtf(-2.0f * logf(u));
+    float s, c;
+    sincospif(v, &s, &c);
+    n0 = (double)(r * c);
+    n1 = (double)(r * s);
+}
+__device__ __forceinline__ double normal_one_f32(uint32_t a, uint32_t b, bool second)
+{
+    float u = fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    float v = fmaf((float)b, 4.6566128730773926e-10f, 2.3283064365386963e-10f);
+    float r = sqrtf(-2.0f * logf(u));
+    return (double)(r * (second ? sinpif(v) : cospif(v)));
+}
+// Box-Muller pair in fp64 (beam profile: sigma of millimetres against a pitch of micrometres)
+__device__ __forceinline__ void normal_pair_f64(U4 w, double &n0, double &n1)
+{
+    double u = u53_open(w.x, w.y);
+    double v = u53_closed_open(w.z, w.w);
+    double r = sqrt(-2.0 * log(u));
+    double s, c;
+    sincospi(2.0 * v, &s, &c);
+    n0 = r * c;
+    n1 = r * s;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// variate sources.  Both answer the same questions; the kernels are templated on the source so that the
+// deterministic (injected) and the production (Philox) mode run the very same physics code.
+// ---------------------------------------------------------------------------------------------------
+struct PhiloxSource {
+    uint64_t seed;
+
+    __device__ bool accepted(const ConfigK &cfg, uint64_t k) const
+    {
+        U4 w = philox_at(seed, k, SITE_EVENT, 0);
+        return u53_closed_open(w.x, w.y) < cfg.accept_p;
+    }
+    // Poisson(lam): multiplication method below 10, Hoermann's PTRS above (same laws as numpy's legacy
+    // generator that the reference draws from, main/hit.py:239)
+    __device__ int64_t gap(const ConfigK &cfg, uint64_t k) const
+    {
+        const double lam = cfg.lam;
+        if (lam >= 10.0) {
+            for (uint32_t it = 1;; ++it) {
+                U4     w = philox_at(seed, k, SITE_EVENT, it);
+                double U = u53_closed_open(w.x, w.y) - 0.5;
+                double V = u53_closed_open(w.z, w.w);
+                double us = 0.5 - fabs(U);
+                double kk = floor((2.0 * cfg.p_a / us + cfg.p_b) * U + lam + 0.43);
+                if (us >= 0.07 && V <= cfg.p_vr) return (int64_t)kk;
+                if (kk < 0.0 || (us < 0.013 && V > us)) continue;
+                if (log(V) + cfg.p_log_invalpha - log(cfg.p_a / (us * us) + cfg.p_b) <=
+                    -lam + kk * cfg.p_loglam - lgamma(kk + 1.0))
+                    return (int64_t)kk;
+            }
+        }
+        if (lam == 0.0) return 0;
+        int64_t n = 0;
+        double  prod = 1.0;
+        for (uint32_t it = 1;; ++it) {
+            U4 w = philox_at(seed, k, SITE_EVENT, it);
+            prod *= u53_closed_open(w.x, w.y);
+            if (prod <= cfg.p_explam) return n;
+            ++n;
+            prod *= u53_closed_open(w.z, w.w);
+            if (prod <= cfg.p_explam) return n;
+            ++n;
+        }
+    }
+    __device__ void start(uint64_t k, double z[4]) const
+    {
+        normal_pair_f64(philox_at(seed, k, SITE_START, 0), z[0], z[1]);
+        normal_pair_f64(philox_at(seed, k, SITE_START, 1), z[2], z[3]);
+    }
+    // scattering kicks and the Landau loss of plane d come out of one Philox block
+    __device__ void step(const ConfigK &cfg, uint64_t k, int d, double &zkx, double &zky, double &eloss) const
+    {
+        U4 w = philox_at(seed, k, SITE_PLANE + 4 * d + SUB_STEP, 0);
+        normal_pair_f32(w.x, w.y, zkx, zky);
+        eloss = landau(cfg.pl[d], w.z, w.w);
+    }
+    __device__ double eloss_only(const ConfigK &cfg, uint64_t k, int d) const
+    {
+        U4 w = philox_at(seed, k, SITE_PLANE + 4 * d + SUB_STEP, 0);
+        return landau(cfg.pl[d], w.z, w.w);
+    }
+    // truncated Moyal law by inversion: F(lambda) = erfc(exp(-lambda/2)/sqrt2) restricted to the window that
+    // maps onto [0, 0.5] MeV -- the law the reference's accept/reject pool follows (main/hit.py:345-359,
+    // 399-400, 431)
+    __device__ static double landau(const PlaneK &p, uint32_t a, uint32_t b)
+    {
+        double        U = p.lan_ulo + p.lan_uspan * u53_open(a, b);
+        double        s = erfcinv(U);
+        double        lam = -2.0 * log(1.4142135623730951 * s);
+        double        e = p.lan_loc + p.lan_scale * lam;
+        return fmin(fmax(e, 0.0), 0.5);
+    }
+    __device__ void dig(uint64_t k, int d, double &zrx, double &zry, double &zseed) const
+    {
+        U4     w = philox_at(seed, k, SITE_PLANE + 4 * d + SUB_DIG, 0);
+        double spare;
+        normal_pair_f32(w.x, w.y, zrx, zry);
+        normal_pair_f32(w.z, w.w, zseed, spare);
+    }
+    __device__ double pixel(uint64_t k, int d, uint32_t j) const
+    {
+        U4 w = philox_at(seed, k, SITE_PLANE + 4 * d + SUB_PIX, j >> 2);
+        return (j & 2u) ? normal_one_f32(w.z, w.w, j & 1u) : normal_one_f32(w.x, w.y, j & 1u);
+    }
+};
+
+struct InjectedSource {
+    PtbInjected v;
+    uint64_t    first, n;
+
+    __device__ bool accepted(const ConfigK &, uint64_t k) const { return v.accepted[k - first] != 0; }
+    __device__ int64_t gap(const ConfigK &, uint64_t k) const { return v.gap[k - first]; }
+    __device__ void start(uint64_t k, double z[4]) const
+    {
+        const double *p = v.zstart + 4 * (k - first);
+        z[0] = p[0]; z[1] = p[1]; z[2] = p[2]; z[3] = p[3];
+    }
+    __device__ void step(const ConfigK &cfg, uint64_t k, int d, double &zkx, double &zky, double &eloss) const
+    {
+        const double *p = v.zkick + ((k - first) * (uint64_t)(cfg.n_planes - 1) + (uint64_t)(d - 1)) * 2;
+        zkx = p[0];
+        zky = p[1];
+        eloss = v.eloss[(uint64_t)d * n + (k - first)];
+    }
+    // k may be first-1 (the look-back of SURVEY.md Q4)
+    __device__ double eloss_only(const ConfigK &, uint64_t k, int d) const
+    {
+        return (k + 1 == first) ? v.eloss0_prev : v.eloss[(uint64_t)d * n + (k - first)];
+    }
+    __device__ void dig(uint64_t k, int d, double &zrx, double &zry, double &zseed) const
+    {
+        const double *p = v.dig_z + v.dig_off[(uint64_t)d * (n + 1) + (k - first)];
+        zrx = p[0]; zry = p[1]; zseed = p[2];
+    }
+    __device__ double pixel(uint64_t k, int d, uint32_t j) const
+    {
+        return v.dig_z[v.dig_off[(uint64_t)d * (n + 1) + (k - first)] + 3 + j];
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// physics
+// ---------------------------------------------------------------------------------------------------
+
+// Highland width for electrons, main/hit.py:290-297 (the charge factor z=-1 only flips a sign that is squared)
+__host__ __device__ __forceinline__ double highland_theta0(double energy, double eps, double corr2)
+{
+    double p = sqrt(energy * energy - 0.511 * 0.511);
+    double g = energy / 0.511;
+    double beta = sqrt(1.0 - 1.0 / (1.0 + g * g));
+    double lead = 13.6 / (beta * p);
+    return sqrt(lead * lead * eps * corr2);
+}
+
+// width of the collected charge cloud in um, main/device.py:186-202.  np.cbrt under Numba is pow(x, 1/3).
+__device__ __forceinline__ double cloud_sigma(const ConfigK &c, double eloss)
+{
+    double ev = eloss * 1e6;
+    double q = c.qe * ev / 3.6;
+    double carg = c.c3mu * q * c.t90 / c.cden;
+    double coul = 0.2 * pow(carg, 1.0 / 3.0);
+    return sqrt(c.diff2 + coul * coul) * 1e6;
+}
+
+// 1-based pixel index with truncation toward zero, main/device.py:356
+__device__ __forceinline__ int pixel_index(double pos, double delta, double pitch, double half_n)
+{
+    double    t = (pos + delta) / pitch + half_n;
+    long long i = __double2ll_rz(fmin(fmax(t, -1.0e9), 1.0e9)) + 1;
+    return (int)i;
+}
+
+// centre of pixel idx, main/device.py:372
+__device__ __forceinline__ double pixel_centre(int idx, double delta, double pitch, double half_n, double half_pitch)
+{
+    return pitch * ((double)idx - half_n - 1.0) - delta + half_pitch;
+}
+
+#define PTB_SQRT_2PI 2.5066282746310002 /* sqrt(2*pi) rounded as numpy does: np.sqrt(2*np.pi) */
+
+// radius entering the Gaussian profile: clamped below 1 um, main/device.py:400-403
+__device__ __forceinline__ double profile_radius(double r) { return r < 1.0 ? 1.0 / PTB_SQRT_2PI : r; }
+
+// 1/(sigma*sqrt(2 pi)), first factor of main/device.py:378
+__device__ __forceinline__ double profile_norm(double rc) { return 1.0 / (rc * PTB_SQRT_2PI); }
+
+// exp(-(d^2)/(2 sigma^2)), second factor of main/device.py:378
+__device__ __forceinline__ double profile_shape(double d, double rc) { return exp(-(d * d) / (2.0 * (rc * rc))); }
+
+}  // namespace ptb

@@ -1,0 +1,950 @@
+// libptb_b200 -- kernels and C ABI (include/ptb.h).
+//
+// One call of ptb_simulate runs three kernels on the caller's stream:
+//
+//   k_simulate  one warp per group of 32 consecutive particles, one lane per particle for the track part
+//               (beam draw, plane-by-plane propagation, Highland kick, Landau loss, acceptance test);
+//               the cluster digitisation is warp-cooperative: the 32 particles' pixel boxes are flattened
+//               into one work list that the lanes walk 32 items at a time, and hits are compacted in
+//               reference order (particle, column, row) with warp ballots into a shared-memory stage.
+//               After every plane the group reserves room in that plane's scratch slab with one atomic
+//               and flushes the stage with coalesced stores.  Nothing else touches HBM.
+//   k_scan      exclusive prefix over the per-group counters (hits per plane, accepted events, time).
+//   k_gather    copies each group's scratch segment to its final, particle-ordered position in the
+//               structure-of-arrays hit slab and stamps the event numbers.
+//
+// The kernels never wait on each other inside a launch (no look-back spinning), so forward progress
+// does not depend on block scheduling order.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "ptb_device.cuh"
+
+namespace ptb {
+
+constexpr int      WARPS_PER_BLOCK = 4;
+constexpr int      BLOCK = 32 * WARPS_PER_BLOCK;
+constexpr unsigned FULL = 0xffffffffu;
+
+static unsigned long long g_launches = 0;
+
+// ---------------------------------------------------------------------------------------------------
+// workspace layout (device memory owned by the caller)
+// ---------------------------------------------------------------------------------------------------
+struct Workspace {
+    unsigned long long *alloc;      // [PTB_MAX_PLANES * 16] one counter per 128-byte line
+    unsigned long long *table;      // [(2D+5)][n_groups]: hits[D], accepted, tsum, pairs, inside, pixels, base[D]
+    unsigned long long *prefix;     // [(D+2)][n_groups]
+    PtbBases           *bases_used; // copy of bases_in taken by k_scan before bases_out is written
+    uint32_t           *s_cr[PTB_MAX_PLANES];
+    float              *s_q[PTB_MAX_PLANES];
+    uint8_t            *s_ev[PTB_MAX_PLANES];
+    double             *s_q64[PTB_MAX_PLANES];
+    unsigned long long  cap[PTB_MAX_PLANES];
+};
+
+struct KParams {
+    unsigned long long first, n, n_groups;
+    uint32_t           flags, _pad;
+    PtbTrackTable      trk;
+    Workspace          ws;
+    PtbTotals         *totals;
+};
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static size_t carve_workspace(int D, unsigned long long n, const unsigned long long *cap, uint32_t flags, char *base,
+                              Workspace *ws)
+{
+    unsigned long long ng = (n + 31) / 32;
+    size_t             off = 0;
+    auto take = [&](size_t bytes) {
+        size_t at = off;
+        off = align_up(off + bytes, 256);
+        return base ? base + at : (char *)nullptr;
+    };
+    char *p;
+    p = take(sizeof(unsigned long long) * PTB_MAX_PLANES * 16);
+    if (ws) ws->alloc = (unsigned long long *)p;
+    p = take(sizeof(unsigned long long) * (size_t)(2 * D + 5) * ng);
+    if (ws) ws->table = (unsigned long long *)p;
+    p = take(sizeof(unsigned long long) * (size_t)(D + 2) * ng);
+    if (ws) ws->prefix = (unsigned long long *)p;
+    p = take(sizeof(PtbBases));
+    if (ws) ws->bases_used = (PtbBases *)p;
+    for (int d = 0; d < D; ++d) {
+        unsigned long long c = (flags & PTB_DIGITISE) ? cap[d] : 0;
+        p = take(4 * (size_t)c);
+        if (ws) ws->s_cr[d] = (uint32_t *)p;
+        p = take(4 * (size_t)c);
+        if (ws) ws->s_q[d] = (float *)p;
+        p = take((size_t)c);
+        if (ws) ws->s_ev[d] = (uint8_t *)p;
+        p = take((flags & PTB_KEEP_CHARGE64) ? 8 * (size_t)c : 0);
+        if (ws) ws->s_q64[d] = (double *)p;
+        if (ws) ws->cap[d] = c;
+    }
+    return off;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_simulate
+// ---------------------------------------------------------------------------------------------------
+
+// shared memory of one warp: the per-particle cluster descriptors and the hit stage
+struct WarpShared {
+    double   x[32], y[32], rx[32], ry[32], q[32], inx[32], iny[32], seedq[32];
+    int      clo[32], rlo[32], nrows[32], prefix[32];
+    uint32_t seedcr[32];
+    uint8_t  evoff[32];
+};
+
+__host__ __device__ inline size_t warp_shared_bytes(int stage, bool keep64)
+{
+    size_t b = sizeof(WarpShared);
+    b += (size_t)stage * (4 + 4);         // packed (col,row), f32 charge
+    b += keep64 ? (size_t)stage * 8 : 0;  // f64 charge
+    b += (size_t)stage;                   // event offset within the group
+    return (b + 15) / 16 * 16;
+}
+
+__device__ __forceinline__ unsigned lanemask_lt()
+{
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+template <class Src>
+__global__ void __launch_bounds__(BLOCK) k_simulate(const __grid_constant__ ConfigK cfg,
+                                                    const __grid_constant__ KParams P, const Src src)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int                lane = threadIdx.x & 31;
+    const int                wib = threadIdx.x >> 5;
+    const unsigned long long group = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + wib;
+    if (group >= P.n_groups) return;  // whole warps leave; no block-wide barrier is used anywhere below
+
+    const int    D = cfg.n_planes;
+    const int    S = cfg.stage_hits;
+    const bool   keep64 = (P.flags & PTB_KEEP_CHARGE64) != 0;
+    const bool   digitise = (P.flags & PTB_DIGITISE) != 0;
+    const bool   from_table = (P.flags & PTB_TRACKS_FROM_TABLE) != 0;
+    const bool   write_tracks = (P.flags & PTB_WRITE_TRACKS) != 0;
+    const size_t wbytes = warp_shared_bytes(S, keep64);
+
+    unsigned char *wbase = smem_raw + wbytes * wib;
+    WarpShared    &W = *reinterpret_cast<WarpShared *>(wbase);
+    uint32_t      *st_cr = reinterpret_cast<uint32_t *>(wbase + sizeof(WarpShared));
+    float         *st_q = reinterpret_cast<float *>(st_cr + S);
+    double        *st_q64 = reinterpret_cast<double *>(st_q + S);
+    uint8_t       *st_ev = reinterpret_cast<uint8_t *>(st_q + S) + (keep64 ? (size_t)S * 8 : 0);
+
+    const unsigned long long kl = group * 32 + lane;  // index inside this call's range
+    const bool               valid = kl < P.n;
+    const unsigned long long k = P.first + kl;        // global particle id
+
+    // ---- event-level draws: trigger mask and time gap ------------------------------------------------
+    bool    acc = false;
+    int64_t gap = 0;
+    if (valid) {
+        if (from_table) {
+            acc = P.trk.accepted[kl] != 0;
+        } else {
+            acc = src.accepted(cfg, k);
+            gap = src.gap(cfg, k);
+        }
+    }
+    const unsigned accmask = __ballot_sync(FULL, acc);
+    const int      evoff = __popc(accmask & lanemask_lt());  // accepted particles of this group before me
+    int64_t        t_rel = gap;                              // inclusive scan: time relative to the group start
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        int64_t o = __shfl_up_sync(FULL, t_rel, s);
+        if (lane >= s) t_rel += o;
+    }
+    W.evoff[lane] = (uint8_t)evoff;
+
+    // ---- source state (main/hit.py:70-80, 104, 234-238) ----------------------------------------------
+    double E = 0, ax = 0, ay = 0, x = 0, y = 0, e0_self = 0;
+    if (!from_table) {
+        double e0_prev = 0;
+        if (valid) e0_self = src.eloss_only(cfg, k, 0);
+        e0_prev = __shfl_up_sync(FULL, e0_self, 1);
+        if (valid) {
+            if (k == 0)
+                e0_prev = e0_self;                      // event 0 starts from its own plane-0 loss
+            else if (lane == 0)
+                e0_prev = src.eloss_only(cfg, k - 1, 0);     // neighbour group: recomputed / injected look-back
+            double z[4];
+            src.start(k, z);
+            const bool first_event = (k == 0);
+            ax = cfg.angle_x + (first_event ? cfg.theta0_first : cfg.disp_x) * z[0];
+            ay = cfg.angle_y + (first_event ? cfg.theta0_first : cfg.disp_y) * z[1];
+            x = cfg.loc_x + cfg.sigma_x * z[2];
+            y = cfg.loc_y + cfg.sigma_y * z[3];
+            E = cfg.energy - e0_prev;
+        }
+    }
+
+    unsigned long long n_pairs = 0, n_inside = 0, n_pixels = 0;
+    unsigned           err = 0;
+
+    for (int d = 0; d < D; ++d) {
+        const PlaneK &pl = cfg.pl[d];
+        double        eloss = 0;
+        // ---- track step (main/hit.py:211-231) ------------------------------------------------------
+        if (valid) {
+            if (from_table) {
+                x = P.trk.x[kl * D + d];
+                y = P.trk.y[kl * D + d];
+                eloss = P.trk.eloss[(unsigned long long)d * P.n + kl];
+            } else if (d == 0) {
+                eloss = e0_self;   // plane 0 is the start point: never propagated to, never bounds-checked (Q2)
+            } else {
+                x = x + tan(ax) * pl.z;   // absolute z of the target plane (Q1)
+                y = y + tan(ay) * pl.z;
+                const double th = highland_theta0(E, pl.eps, pl.corr2);
+                double       zkx, zky;
+                src.step(cfg, k, d, zkx, zky, eloss);
+                double kx = 0.0 + th * zkx;
+                double ky = 0.0 + th * zky;
+                if (x > pl.x_pos || x < pl.x_neg || y > pl.y_pos || y < pl.y_neg) {
+                    kx = 0.0;
+                    ky = 0.0;
+                    eloss = 0.0;
+                }
+                ax = ax + kx;
+                ay = ay + ky;
+                E = E - eloss;
+            }
+            if (write_tracks) {
+                const unsigned long long o = kl * D + d;
+                P.trk.energy[o] = E;
+                P.trk.angle_x[o] = ax;
+                P.trk.angle_y[o] = ay;
+                P.trk.x[o] = x;
+                P.trk.y[o] = y;
+                P.trk.z[o] = pl.z;
+                P.trk.time_stamp[o] = t_rel;   // k_gather adds the group's base
+                P.trk.eloss[(unsigned long long)d * P.n + kl] = eloss;
+                if (d == 0) P.trk.accepted[kl] = acc ? 1 : 0;
+            }
+        }
+        if (!digitise) continue;
+
+        // ---- cluster descriptors, one lane per particle (main/device.py:137-140, 241-266) -----------
+        int cnt = 0;
+        if (valid && (acc || !pl.triggered)) {
+            ++n_pairs;
+            const double sig = cloud_sigma(cfg, eloss);
+            double       zrx, zry, zseed;
+            src.dig(k, d, zrx, zry, zseed);
+            const double rx = fabs(0.0 + sig * zrx);
+            const double ry = fabs(0.0 + sig * zry);
+            const int    sc = pixel_index(x, pl.delta_x, pl.pitch_c, pl.half_nc);
+            const int    sr = pixel_index(y, pl.delta_y, pl.pitch_r, pl.half_nr);
+            if (sc >= 1 && sc <= pl.ncol && sr >= 1 && sr <= pl.nrow) {
+                ++n_inside;
+                const double inx = profile_norm(profile_radius(rx));
+                const double iny = profile_norm(profile_radius(ry));
+                const double q = eloss * 1e6 / 3.6;
+                const double noise = 0.0 + pl.noise_sigma * zseed;
+                // seed pixel: both profile factors are exp(-0) = 1; no pixel-area factor (Q9)
+                const double seedq = (q * (inx * iny) + noise) * 1e-3;
+                const int    c_hi = pixel_index(x + rx, pl.delta_x, pl.pitch_c, pl.half_nc);
+                const int    c_lo = pixel_index(x - rx, pl.delta_x, pl.pitch_c, pl.half_nc);
+                const int    r_hi = pixel_index(y + ry, pl.delta_y, pl.pitch_r, pl.half_nr);
+                const int    r_lo = pixel_index(y - ry, pl.delta_y, pl.pitch_r, pl.half_nr);
+                const long long nc = (long long)c_hi - c_lo + 1, nr = (long long)r_hi - r_lo + 1;
+                long long       box = (nc > 0 && nr > 0) ? nc * nr : 0;
+                if (box > (1ll << 20)) {
+                    err |= PTB_DEV_BOX_TOO_LARGE;
+                    box = 0;
+                }
+                cnt = (int)box;
+                W.x[lane] = x; W.y[lane] = y; W.rx[lane] = rx; W.ry[lane] = ry;
+                W.q[lane] = q; W.inx[lane] = inx; W.iny[lane] = iny; W.seedq[lane] = seedq;
+                W.clo[lane] = c_lo; W.rlo[lane] = r_lo; W.nrows[lane] = (int)nr;
+                W.seedcr[lane] = (uint32_t)sc | ((uint32_t)sr << 16);
+            }
+        }
+        n_pixels += (unsigned)cnt;
+        int incl = cnt;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            int o = __shfl_up_sync(FULL, incl, s);
+            if (lane >= s) incl += o;
+        }
+        W.prefix[lane] = incl;
+        const int total = __shfl_sync(FULL, incl, 31);
+        __syncwarp();
+
+        // ---- pixel work list: 32 items per step in (particle, column, row) order ---------------------
+        int n_plane = 0;           // hits staged for this plane (warp-uniform)
+        int carry_owner = -1;      // particle whose items straddle the previous step, and its kept count
+        int carry_kept = 0;
+        for (int w0 = 0; w0 < total; w0 += 32) {
+            const int  w = w0 + lane;
+            const bool has = w < total;
+            int        own = 0;
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1)
+                if (W.prefix[own + s - 1] <= w) own += s;
+            own = has ? own : 31;
+            const int excl = own ? W.prefix[own - 1] : 0;
+            const int end = W.prefix[own];
+            const int j = w - excl;
+            bool      keep = false;
+            double    charge = 0;
+            uint32_t  cr = 0;
+            if (has) {
+                const int    nrw = W.nrows[own];
+                const int    ci = j / nrw;
+                const int    ri = j - ci * nrw;
+                const int    col = W.clo[own] + ci;
+                const int    row = W.rlo[own] + ri;
+                const double px = W.x[own], py = W.y[own], rx = W.rx[own], ry = W.ry[own];
+                const double cx = pixel_centre(col, pl.delta_x, pl.pitch_c, pl.half_nc, pl.half_pc);
+                const double cy = pixel_centre(row, pl.delta_y, pl.pitch_r, pl.half_nr, pl.half_pr);
+                const double dx = cx - px, dy = cy - py;
+                const double zn = src.pixel(P.first + group * 32 + own, d, (uint32_t)j);
+                const double noise = 0.0 + pl.noise_sigma * zn;
+                const double gx = W.inx[own] * profile_shape(dx, profile_radius(rx));
+                const double gy = W.iny[own] * profile_shape(dy, profile_radius(ry));
+                const double signal = W.q[own] * (gx * gy);
+                charge = (signal + noise) * 1e-3 * pl.pitch_c * pl.pitch_r;   // main/device.py:275-288
+                keep = charge >= pl.thr_ke && rx > 0.0 && ry > 0.0 &&
+                       (dx * dx) / (rx * rx) + (dy * dy) / (ry * ry) <= 1.0 && col >= 1 && col <= pl.ncol &&
+                       row >= 1 && row <= pl.nrow;                            // main/device.py:289-295
+                cr = (uint32_t)col | ((uint32_t)row << 16);
+            }
+            // kept count of my particle so far: lanes of one particle are contiguous in the work list
+            const unsigned keptmask = __ballot_sync(FULL, keep);
+            const int      lo_lane = has ? max(excl - w0, 0) : 0;
+            const int      hi_lane = has ? min(end - 1 - w0, 31) : 0;
+            const unsigned grp = (hi_lane >= 31 ? FULL : ((1u << (hi_lane + 1)) - 1u)) & ~((1u << lo_lane) - 1u);
+            const int      kept_here = __popc(keptmask & grp);
+            const int      kept_before = (own == carry_owner) ? carry_kept : 0;
+            // seed fallback (main/device.py:299-302): the particle's last box pixel emits the seed pixel
+            // instead when nothing in the box survived
+            bool fallback = false;
+            if (has && w == end - 1 && kept_before + kept_here == 0 && W.seedq[own] >= pl.thr_ke) {
+                fallback = true;
+                charge = W.seedq[own];
+                cr = W.seedcr[own];
+            }
+            const bool     emit = keep || fallback;
+            const unsigned emask = __ballot_sync(FULL, emit);
+            if (emit) {
+                const int pos = n_plane + __popc(emask & lanemask_lt());
+                if (pos < S) {
+                    st_cr[pos] = cr;
+                    st_q[pos] = (float)charge;
+                    st_ev[pos] = W.evoff[own];
+                    if (keep64) st_q64[pos] = charge;
+                } else {
+                    err |= PTB_DEV_STAGE_OVERFLOW;
+                }
+            }
+            n_plane += __popc(emask);
+            // carry for a particle that continues into the next step
+            const int last_lane = min(total - w0, 32) - 1;
+            carry_owner = __shfl_sync(FULL, own, last_lane);
+            carry_kept = __shfl_sync(FULL, kept_before + kept_here, last_lane);
+        }
+        __syncwarp();
+
+        // ---- reserve room in the plane's scratch slab and flush the stage ----------------------------
+        const int          n_out = min(n_plane, S);
+        unsigned long long base = 0;
+        if (lane == 0) {
+            if (n_out > 0) base = atomicAdd(&P.ws.alloc[d * 16], (unsigned long long)n_out);
+            P.ws.table[(unsigned long long)d * P.n_groups + group] = (unsigned long long)n_out;
+            P.ws.table[(unsigned long long)(D + 5 + d) * P.n_groups + group] = base;
+        }
+        base = __shfl_sync(FULL, base, 0);
+        if (base + n_out > P.ws.cap[d]) {
+            err |= PTB_DEV_SLAB_OVERFLOW;
+        } else {
+            for (int i = lane; i < n_out; i += 32) {
+                P.ws.s_cr[d][base + i] = st_cr[i];
+                P.ws.s_q[d][base + i] = st_q[i];
+                P.ws.s_ev[d][base + i] = st_ev[i];
+                if (keep64) P.ws.s_q64[d][base + i] = st_q64[i];
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- per-group counters for k_scan ---------------------------------------------------------------
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        n_pairs += __shfl_xor_sync(FULL, n_pairs, s);
+        n_inside += __shfl_xor_sync(FULL, n_inside, s);
+        n_pixels += __shfl_xor_sync(FULL, n_pixels, s);
+        err |= __shfl_xor_sync(FULL, err, s);
+    }
+    const int64_t tsum = __shfl_sync(FULL, t_rel, 31);
+    if (lane == 0) {
+        unsigned long long *t = P.ws.table + group;
+        if (!digitise)
+            for (int d = 0; d < D; ++d) t[(unsigned long long)d * P.n_groups] = 0;
+        t[(unsigned long long)(D + 0) * P.n_groups] = (unsigned long long)__popc(accmask);
+        t[(unsigned long long)(D + 1) * P.n_groups] = (unsigned long long)tsum;
+        t[(unsigned long long)(D + 2) * P.n_groups] = n_pairs;
+        t[(unsigned long long)(D + 3) * P.n_groups] = n_inside;
+        t[(unsigned long long)(D + 4) * P.n_groups] = n_pixels;
+        if (err) atomicOr(&P.totals->error, err);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_scan: block c scans column c of the group table (exclusive prefix into ws.prefix for c < D+2), writes
+// this call's totals, the bases the gather pass has to use, and the bases of the following range
+// ---------------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_ITEMS = 4;
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan(int D, unsigned long long n_groups, Workspace ws,
+                                                       const PtbBases *bases_in, PtbBases *bases_out, PtbTotals *totals)
+{
+    __shared__ unsigned long long warp_sum[32];
+    __shared__ unsigned long long carry_s;
+    const int                     c = blockIdx.x;
+    const unsigned long long     *col = ws.table + (unsigned long long)c * n_groups;
+    unsigned long long           *out = (c < D + 2) ? ws.prefix + (unsigned long long)c * n_groups : nullptr;
+    const int                     lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (unsigned long long tile = 0; tile < n_groups; tile += (unsigned long long)SCAN_THREADS * SCAN_ITEMS) {
+        const unsigned long long i0 = tile + (unsigned long long)threadIdx.x * SCAN_ITEMS;
+        unsigned long long       v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) {
+            v[i] = (i0 + i < n_groups) ? col[i0 + i] : 0ull;
+            sum += v[i];
+        }
+        unsigned long long incl = sum;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            unsigned long long o = __shfl_up_sync(FULL, incl, s);
+            if (lane >= s) incl += o;
+        }
+        if (lane == 31) warp_sum[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned long long ws_incl = warp_sum[lane];
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                unsigned long long o = __shfl_up_sync(FULL, ws_incl, s);
+                if (lane >= s) ws_incl += o;
+            }
+            warp_sum[lane] = ws_incl;
+        }
+        __syncthreads();
+        const unsigned long long carry = carry_s;
+        unsigned long long       excl = carry + (wid ? warp_sum[wid - 1] : 0ull) + (incl - sum);
+        if (out) {
+#pragma unroll
+            for (int i = 0; i < SCAN_ITEMS; ++i) {
+                if (i0 + i < n_groups) out[i0 + i] = excl;
+                excl += v[i];
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == SCAN_THREADS - 1) carry_s = carry + warp_sum[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const unsigned long long total = carry_s;
+        if (c < D) {
+            const unsigned long long b = bases_in ? bases_in->hits[c] : 0ull;
+            ws.bases_used->hits[c] = b;
+            totals->hits[c] = total;
+            if (bases_out) bases_out->hits[c] = b + total;
+        } else if (c == D) {
+            const int64_t b = bases_in ? bases_in->event : 0;
+            ws.bases_used->event = b;
+            totals->accepted = total;
+            if (bases_out) bases_out->event = b + (int64_t)total;
+        } else if (c == D + 1) {
+            const int64_t b = bases_in ? bases_in->time : 0;
+            ws.bases_used->time = b;
+            totals->time_sum = (int64_t)total;
+            if (bases_out) bases_out->time = b + (int64_t)total;
+        } else if (c == D + 2) {
+            totals->pairs = total;
+        } else if (c == D + 3) {
+            totals->inside = total;
+        } else if (c == D + 4) {
+            totals->pixels = total;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_gather: one warp per group; scratch segment -> final particle-ordered slab rows, event numbers,
+// absolute time stamps of the track records
+// ---------------------------------------------------------------------------------------------------
+struct GatherParams {
+    int                D;
+    uint32_t           flags;
+    unsigned long long n, n_groups;
+    Workspace          ws;
+    PtbHitSlab         slabs[PTB_MAX_PLANES];
+    int64_t           *time_stamp;
+    PtbTotals         *totals;
+};
+
+__global__ void __launch_bounds__(256) k_gather(const __grid_constant__ GatherParams G)
+{
+    const int                lane = threadIdx.x & 31;
+    const unsigned long long group = (unsigned long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (group >= G.n_groups) return;
+    const PtbBases &B = *G.ws.bases_used;
+    const int       D = G.D;
+    if (G.flags & PTB_DIGITISE) {
+        const int64_t ev_base = B.event + (int64_t)G.ws.prefix[(unsigned long long)D * G.n_groups + group] + 1;
+        const bool    keep64 = (G.flags & PTB_KEEP_CHARGE64) != 0;
+        for (int d = 0; d < D; ++d) {
+            const unsigned long long n = G.ws.table[(unsigned long long)d * G.n_groups + group];
+            if (n == 0) continue;
+            const unsigned long long src = G.ws.table[(unsigned long long)(D + 5 + d) * G.n_groups + group];
+            const unsigned long long dst = B.hits[d] + G.ws.prefix[(unsigned long long)d * G.n_groups + group];
+            const PtbHitSlab        &s = G.slabs[d];
+            if (dst + n > s.capacity || src + n > G.ws.cap[d]) {
+                if (lane == 0) atomicOr(&G.totals->error, PTB_DEV_SLAB_OVERFLOW);
+                continue;
+            }
+            for (unsigned long long i = lane; i < n; i += 32) {
+                const uint32_t cr = G.ws.s_cr[d][src + i];
+                s.event[dst + i] = ev_base + (int64_t)G.ws.s_ev[d][src + i];
+                s.col[dst + i] = (uint16_t)(cr & 0xffffu);
+                s.row[dst + i] = (uint16_t)(cr >> 16);
+                s.charge[dst + i] = G.ws.s_q[d][src + i];
+                if (keep64) s.charge64[dst + i] = G.ws.s_q64[d][src + i];
+            }
+        }
+    }
+    if ((G.flags & PTB_WRITE_TRACKS) && !(G.flags & PTB_TRACKS_FROM_TABLE)) {
+        const int64_t            t_base = B.time + (int64_t)G.ws.prefix[(unsigned long long)(D + 1) * G.n_groups + group];
+        const unsigned long long lo = group * 32 * D;
+        const unsigned long long hi = min((group + 1) * 32, G.n) * D;
+        for (unsigned long long i = lo + lane; i < hi; i += 32) G.time_stamp[i] += t_base;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_prefix: accepted-event count and gap sum of a particle range (ptb_prefix)
+// ---------------------------------------------------------------------------------------------------
+template <class Src>
+__global__ void __launch_bounds__(256) k_prefix(const __grid_constant__ ConfigK cfg, unsigned long long first,
+                                                unsigned long long n, const Src src, long long *out)
+{
+    long long acc = 0, tsum = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        acc += src.accepted(cfg, first + i) ? 1 : 0;
+        tsum += src.gap(cfg, first + i);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        acc += __shfl_xor_sync(FULL, acc, s);
+        tsum += __shfl_xor_sync(FULL, tsum, s);
+    }
+    __shared__ long long sa[8], st[8];
+    if ((threadIdx.x & 31) == 0) {
+        sa[threadIdx.x >> 5] = acc;
+        st[threadIdx.x >> 5] = tsum;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) {
+            acc += sa[i];
+            tsum += st[i];
+        }
+        atomicAdd((unsigned long long *)&out[0], (unsigned long long)acc);
+        atomicAdd((unsigned long long *)&out[1], (unsigned long long)tsum);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_pack: SoA slab rows -> the reference's 18-byte records (main/device.py:20-28), 256 rows per block
+// staged in shared memory so that the global stores are contiguous
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pack(PtbHitSlab s, unsigned long long n, uint16_t *out)
+{
+    __shared__ __align__(16) uint16_t tile[256 * 9];
+    const unsigned long long          r0 = (unsigned long long)blockIdx.x * 256;
+    const unsigned long long          r = r0 + threadIdx.x;
+    if (r < n) {
+        const unsigned long long ev = (unsigned long long)s.event[r];
+        const uint32_t           qb = __float_as_uint(s.charge[r]);
+        uint16_t                *t = tile + threadIdx.x * 9;
+        t[0] = (uint16_t)ev; t[1] = (uint16_t)(ev >> 16); t[2] = (uint16_t)(ev >> 32); t[3] = (uint16_t)(ev >> 48);
+        t[4] = 0;
+        t[5] = s.col[r];
+        t[6] = s.row[r];
+        t[7] = (uint16_t)qb; t[8] = (uint16_t)(qb >> 16);
+    }
+    __syncthreads();
+    const unsigned long long rows = min((unsigned long long)256, n - r0);
+    uint16_t                *dst = out + r0 * 9;
+    if (rows == 256 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        const uint4 *t4 = reinterpret_cast<const uint4 *>(tile);
+        uint4       *d4 = reinterpret_cast<uint4 *>(dst);
+        for (int i = threadIdx.x; i < 256 * 18 / 16; i += 256) d4[i] = t4[i];
+    } else {
+        for (unsigned long long i = threadIdx.x; i < rows * 9; i += 256) dst[i] = tile[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_dfma: FP64 pipe probe for the roofline denominator
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dfma(double *out, int iters, double a, double b)
+{
+    double v0 = threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        v0 = fma(v0, a, b); v1 = fma(v1, a, b); v2 = fma(v2, a, b); v3 = fma(v3, a, b);
+        v4 = fma(v4, a, b); v5 = fma(v5, a, b); v6 = fma(v6, a, b); v7 = fma(v7, a, b);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = v0 + v1 + v2 + v3 + v4 + v5 + v6 + v7;
+}
+
+}  // namespace ptb
+
+// =====================================================================================================
+// host side: handle, derived constants, C ABI
+// =====================================================================================================
+using namespace ptb;
+
+struct PtbContext {
+    ConfigK cfg;
+    int     device;
+    int     fast_math;
+    int     sm_count;
+    char    err[512];
+};
+
+static int fail(PtbHandle h, int code, const char *msg)
+{
+    if (h) snprintf(h->err, sizeof(h->err), "%s", msg);
+    return code;
+}
+
+static int fail_cuda(PtbHandle h, cudaError_t e, const char *where)
+{
+    if (h) snprintf(h->err, sizeof(h->err), "%s: %s", where, cudaGetErrorString(e));
+    return PTB_E_CUDA;
+}
+
+// Moyal-form density of the reference in the energy-loss variable (unnormalised), main/hit.py:399-400,431
+static double moyal_density(double delta, double loc, double scale)
+{
+    double lam = (delta - loc) / scale;
+    return exp(-(lam + exp(-lam)) / 2);
+}
+
+// F(lambda) = P(Lambda <= lambda) for the Moyal law = erfc(exp(-lambda/2)/sqrt 2)
+static double moyal_cdf(double lam) { return erfc(exp(-lam / 2) / sqrt(2.0)); }
+
+extern "C" {
+
+int ptb_create(const PtbBeam *beam, const PtbDevice *dev, int32_t n_dev, const PtbOptions *opt, PtbHandle *out)
+{
+    if (!beam || !dev || !out || n_dev < 1 || n_dev > PTB_MAX_PLANES) return PTB_E_INVALID;
+    PtbContext *h = new (std::nothrow) PtbContext;
+    if (!h) return PTB_E_NOMEM;
+    memset(h, 0, sizeof(*h));
+    *out = h;
+    // the reference's stride-D bookkeeping silently assumes exactly one record per plane and particle,
+    // which only holds for z[0] == 0 and distinct consecutive z; refuse anything else
+    if (dev[0].z != 0.0) return fail(h, PTB_E_INVALID, "first device must sit at z_position 0");
+    for (int d = 1; d < n_dev; ++d)
+        if (dev[d].z == dev[d - 1].z) return fail(h, PTB_E_INVALID, "consecutive devices share a z_position");
+    for (int d = 0; d < n_dev; ++d)
+        if (dev[d].ncol < 1 || dev[d].nrow < 1 || dev[d].ncol > 65535 || dev[d].nrow > 65535 ||
+            !(dev[d].pitch_c > 0) || !(dev[d].pitch_r > 0) || !(dev[d].thickness > 0) || !(dev[d].rad_length > 0))
+            return fail(h, PTB_E_INVALID, "device geometry out of range (1..65535 pixels, positive pitch/thickness)");
+    if (!(beam->particle_rate > 0)) return fail(h, PTB_E_INVALID, "particle_rate must be positive");
+
+    ConfigK &c = h->cfg;
+    c.n_planes = n_dev;
+    c.stage_hits = (opt && opt->stage_hits > 0) ? opt->stage_hits : 512;
+    c.stage_hits = (c.stage_hits + 3) / 4 * 4;
+    h->fast_math = opt ? opt->fast_math : 0;
+    c.energy = beam->energy;
+    c.loc_x = beam->loc_x; c.sigma_x = beam->sigma_x;
+    c.loc_y = beam->loc_y; c.sigma_y = beam->sigma_y;
+    c.disp_x = beam->disp_x; c.disp_y = beam->disp_y;
+    c.angle_x = beam->angle_x; c.angle_y = beam->angle_y;
+    c.accept_p = (opt && opt->trigger_accept > 0) ? opt->trigger_accept : 0.7;
+
+    // Poisson gap: lam = 1/rate*1e9 ns (main/hit.py:33) and the PTRS constants
+    c.lam = 1 / beam->particle_rate * 1e9;
+    {
+        double slam = sqrt(c.lam);
+        c.p_loglam = log(c.lam);
+        c.p_b = 0.931 + 2.53 * slam;
+        c.p_a = -0.059 + 0.02483 * c.p_b;
+        c.p_log_invalpha = log(1.1239 + 1.1328 / (c.p_b - 3.4));
+        c.p_vr = 0.9277 - 3.6224 / (c.p_b - 2);
+        c.p_explam = exp(-c.lam);
+    }
+    // charge cloud (main/device.py:186-197), same operation order as the reference
+    {
+        double kb = 1.38 * 1e-23, T = 300, qe = 1.602 * 1e-19, mu = 0.14;
+        double Dc = mu * kb * T / qe;
+        double t = 90 * 1e-9;
+        double diffusion = 0.8 * sqrt(2 * Dc * t);
+        double eps0 = 8.854 * 1e-12, epsr = 11.7;
+        c.diff2 = diffusion * diffusion;
+        c.qe = qe;
+        c.c3mu = 3 * mu;
+        c.t90 = t;
+        c.cden = 4 * M_PI * eps0 * epsr;
+    }
+    double mean_prev = 0.0;   // mean loss in the previous plane; the reference indexes row -1 (all zero) for plane 0
+    for (int d = 0; d < n_dev; ++d) {
+        const PtbDevice &v = dev[d];
+        PlaneK          &p = c.pl[d];
+        p.z = v.z;
+        p.x_pos = v.pitch_c * v.ncol / 2 + v.delta_x;
+        p.x_neg = -v.pitch_c * v.ncol / 2 + v.delta_x;
+        p.y_pos = v.pitch_r * v.nrow / 2 + v.delta_y;
+        p.y_neg = -v.pitch_r * v.nrow / 2 + v.delta_y;
+        p.eps = v.thickness / v.rad_length;
+        double corr = 1 + 0.038 * log(p.eps);
+        p.corr2 = corr * corr;
+        p.pitch_c = v.pitch_c; p.pitch_r = v.pitch_r;
+        p.delta_x = v.delta_x; p.delta_y = v.delta_y;
+        p.half_nc = v.ncol / 2.0; p.half_nr = v.nrow / 2.0;
+        p.half_pc = v.pitch_c / 2; p.half_pr = v.pitch_r / 2;
+        p.thr_ke = v.threshold_e * 1e-3;
+        {
+            double kb = 1.38 * 1e-23, qe = 1.602 * 1e-19, eps0 = 8.854 * 1e-12, epsr = 11.7, T = 300;
+            double cap = eps0 * epsr * v.pitch_r * v.pitch_c / v.thickness * 1e-6;
+            p.noise_sigma = sqrt(kb * T * cap) / qe;
+        }
+        p.ncol = v.ncol; p.nrow = v.nrow; p.triggered = v.triggered ? 1 : 0;
+        // Landau (Moyal form): xi = 0.1535 z^2 Z rho x / (A beta^2), x in cm; lambda = (delta-0.025)/xi - beta^2
+        // - ln(xi/1e-6) - 1 + e   =>   delta = loc + xi*lambda    (main/hit.py:385, 399-400)
+        {
+            double en = beam->energy - mean_prev;
+            double g = en / 0.511;
+            double beta2 = 1 - 1 / (1 + g * g);
+            double xcm = v.thickness * 1e-4;
+            double xi = 0.1535 * v.Z * v.rho * xcm / (v.A * beta2);
+            p.lan_scale = xi;
+            p.lan_loc = 0.025 + xi * (beta2 + log(xi / 1e-6) + 1 - M_E);
+            double lo = (0.0 - p.lan_loc) / xi, hi = (0.5 - p.lan_loc) / xi;
+            p.lan_ulo = moyal_cdf(lo);
+            p.lan_uspan = moyal_cdf(hi) - p.lan_ulo;
+            if (!(p.lan_uspan > 0)) return fail(h, PTB_E_INVALID, "Landau window [0,0.5] MeV carries no probability");
+            // mean of the truncated law by Simpson's rule, feeds beta of the next plane (main/hit.py:91)
+            const int M = 20000;
+            double    num = 0, den = 0, hstep = 0.5 / M;
+            for (int i = 0; i <= M; ++i) {
+                double wgt = (i == 0 || i == M) ? 1 : ((i & 1) ? 4 : 2);
+                double dl = i * hstep;
+                double f = moyal_density(dl, p.lan_loc, xi);
+                num += wgt * f * dl;
+                den += wgt * f;
+            }
+            mean_prev = den > 0 ? num / den : 0.0;
+        }
+    }
+    c.theta0_first = highland_theta0(beam->energy, c.pl[0].eps, c.pl[0].corr2);
+
+    cudaError_t e = cudaGetDevice(&h->device);
+    if (e != cudaSuccess) return fail_cuda(h, e, "cudaGetDevice");
+    e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
+    if (e != cudaSuccess) return fail_cuda(h, e, "cudaDeviceGetAttribute");
+    return PTB_OK;
+}
+
+void ptb_destroy(PtbHandle h) { delete h; }
+
+const char *ptb_last_error(PtbHandle h) { return h ? h->err : "null handle"; }
+
+int32_t ptb_n_planes(PtbHandle h) { return h ? h->cfg.n_planes : 0; }
+
+int32_t ptb_stage_hits(PtbHandle h) { return h ? h->cfg.stage_hits : 0; }
+
+size_t ptb_workspace_bytes(PtbHandle h, uint64_t n, const uint64_t *capacity, uint32_t flags)
+{
+    if (!h) return 0;
+    unsigned long long cap[PTB_MAX_PLANES] = {0};
+    for (int d = 0; d < h->cfg.n_planes; ++d) cap[d] = capacity ? capacity[d] : 0;
+    return carve_workspace(h->cfg.n_planes, n, cap, flags, nullptr, nullptr);
+}
+
+uint64_t ptb_launch_count(void) { return g_launches; }
+
+static bool injected_complete(const PtbInjected *v, uint32_t flags)
+{
+    if (flags & PTB_TRACKS_FROM_TABLE) return v->dig_z && v->dig_off;
+    bool ok = v->zstart && v->gap && v->zkick && v->eloss && v->accepted;
+    if (flags & PTB_DIGITISE) ok = ok && v->dig_z && v->dig_off;
+    return ok;
+}
+
+int ptb_prefix(PtbHandle h, uint64_t first, uint64_t n, uint64_t seed, const PtbInjected *inj, int64_t *out_dev,
+               void *stream)
+{
+    if (!h || !out_dev) return PTB_E_INVALID;
+    if (n == 0) return PTB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int          blocks = (int)std::min<unsigned long long>((n + 255) / 256, (unsigned long long)h->sm_count * 8);
+    if (inj) {
+        if (!inj->accepted || !inj->gap) return fail(h, PTB_E_INVALID, "ptb_prefix: injected accepted/gap missing");
+        InjectedSource src{*inj, first, n};
+        k_prefix<InjectedSource><<<blocks, 256, 0, st>>>(h->cfg, first, n, src, (long long *)out_dev);
+    } else {
+        PhiloxSource src{seed};
+        k_prefix<PhiloxSource><<<blocks, 256, 0, st>>>(h->cfg, first, n, src, (long long *)out_dev);
+    }
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? PTB_OK : fail_cuda(h, e, "k_prefix launch");
+}
+
+int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
+{
+    if (!h || !run || !run->totals) return PTB_E_INVALID;
+    const ConfigK &c = h->cfg;
+    const int      D = c.n_planes;
+    cudaStream_t   st = (cudaStream_t)stream;
+    const uint32_t flags = run->flags;
+    if (run->n == 0) return fail(h, PTB_E_INVALID, "ptb_simulate: empty particle range");
+    if ((flags & PTB_TRACKS_FROM_TABLE) && !(flags & PTB_DIGITISE))
+        return fail(h, PTB_E_INVALID, "PTB_TRACKS_FROM_TABLE without PTB_DIGITISE does nothing");
+    if ((flags & PTB_TRACKS_FROM_TABLE) && (flags & PTB_WRITE_TRACKS))
+        return fail(h, PTB_E_INVALID, "PTB_TRACKS_FROM_TABLE and PTB_WRITE_TRACKS are exclusive");
+    if (flags & (PTB_TRACKS_FROM_TABLE | PTB_WRITE_TRACKS)) {
+        const PtbTrackTable &t = run->tracks;
+        bool ok = t.x && t.y && t.eloss && t.accepted;
+        if (flags & PTB_WRITE_TRACKS) ok = ok && t.energy && t.angle_x && t.angle_y && t.z && t.time_stamp;
+        if (!ok) return fail(h, PTB_E_INVALID, "track table pointers missing");
+    }
+    if (run->injected && !injected_complete(run->injected, flags))
+        return fail(h, PTB_E_INVALID, "injected variate tables incomplete for the requested flags");
+    unsigned long long cap[PTB_MAX_PLANES] = {0};
+    if (flags & PTB_DIGITISE) {
+        for (int d = 0; d < D; ++d) {
+            const PtbHitSlab &s = run->slabs[d];
+            if (!s.event || !s.col || !s.row || !s.charge || ((flags & PTB_KEEP_CHARGE64) && !s.charge64))
+                return fail(h, PTB_E_INVALID, "hit slab pointers missing");
+            cap[d] = s.capacity;
+        }
+    }
+    KParams P;
+    memset(&P, 0, sizeof(P));
+    P.first = run->first;
+    P.n = run->n;
+    P.n_groups = (run->n + 31) / 32;
+    P.flags = flags;
+    P.trk = run->tracks;
+    P.totals = run->totals;
+    size_t need = carve_workspace(D, run->n, cap, flags, (char *)run->workspace, &P.ws);
+    if (!run->workspace || run->workspace_bytes < need) return fail(h, PTB_E_INVALID, "workspace too small");
+    if (P.n_groups > 0x7fffffffull * WARPS_PER_BLOCK) return fail(h, PTB_E_INVALID, "range too large for one call");
+
+    cudaError_t e;
+    e = cudaMemsetAsync(P.ws.alloc, 0, sizeof(unsigned long long) * PTB_MAX_PLANES * 16, st);
+    if (e != cudaSuccess) return fail_cuda(h, e, "memset alloc");
+    e = cudaMemsetAsync(run->totals, 0, sizeof(PtbTotals), st);
+    if (e != cudaSuccess) return fail_cuda(h, e, "memset totals");
+
+    const bool   keep64 = (flags & PTB_KEEP_CHARGE64) != 0;
+    const size_t smem = warp_shared_bytes(c.stage_hits, keep64) * WARPS_PER_BLOCK;
+    const unsigned blocks = (unsigned)((P.n_groups + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+    if (smem > 227 * 1024) return fail(h, PTB_E_INVALID, "stage_hits too large for shared memory");
+    if (run->injected) {
+        InjectedSource src{*run->injected, run->first, run->n};
+        auto           kern = k_simulate<InjectedSource>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail_cuda(h, e, "cudaFuncSetAttribute");
+        kern<<<blocks, BLOCK, smem, st>>>(c, P, src);
+    } else {
+        PhiloxSource src{run->seed};
+        auto         kern = k_simulate<PhiloxSource>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail_cuda(h, e, "cudaFuncSetAttribute");
+        kern<<<blocks, BLOCK, smem, st>>>(c, P, src);
+    }
+    ++g_launches;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(h, e, "k_simulate launch");
+
+    k_scan<<<D + 5, SCAN_THREADS, 0, st>>>(D, P.n_groups, P.ws, run->bases_in, run->bases_out, run->totals);
+    ++g_launches;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(h, e, "k_scan launch");
+
+    if ((flags & PTB_DIGITISE) || (flags & PTB_WRITE_TRACKS)) {
+        GatherParams G;
+        memset(&G, 0, sizeof(G));
+        G.D = D;
+        G.flags = flags;
+        G.n = run->n;
+        G.n_groups = P.n_groups;
+        G.ws = P.ws;
+        for (int d = 0; d < D; ++d) G.slabs[d] = run->slabs[d];
+        G.time_stamp = run->tracks.time_stamp;
+        G.totals = run->totals;
+        k_gather<<<(unsigned)((P.n_groups + 7) / 8), 256, 0, st>>>(G);
+        ++g_launches;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return fail_cuda(h, e, "k_gather launch");
+    }
+    return PTB_OK;
+}
+
+int ptb_pack_hits(const PtbHitSlab *slab, uint64_t n, void *out_dev, void *stream)
+{
+    if (!slab || !out_dev) return PTB_E_INVALID;
+    if (n == 0) return PTB_OK;
+    if (n > slab->capacity) return PTB_E_INVALID;
+    k_pack<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*slab, n, (uint16_t *)out_dev);
+    ++g_launches;
+    return cudaGetLastError() == cudaSuccess ? PTB_OK : PTB_E_CUDA;
+}
+
+double ptb_measure_fp64_peak(void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    int          dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = sms * 8, threads = 256, iters = 1 << 14;
+    double   *buf = nullptr;
+    if (cudaMalloc(&buf, sizeof(double) * blocks * threads) != cudaSuccess) return -1;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    k_dfma<<<blocks, threads, 0, st>>>(buf, iters, 0.999999, 1e-9);
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(a, st);
+        k_dfma<<<blocks, threads, 0, st>>>(buf, iters, 0.999999, 1e-9);
+        cudaEventRecord(b, st);
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        double flops = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3);
+        if (flops > best) best = flops;
+    }
+    g_launches += 6;
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(buf);
+    return cudaGetLastError() == cudaSuccess ? best : -1;
+}
+
+}  // extern "C"

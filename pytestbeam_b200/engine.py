@@ -1,0 +1,290 @@
+"""Host side of the hot path: owns the library handle, allocates the device buffers with PyTorch and
+drives ``ptb_simulate`` / ``ptb_prefix`` / ``ptb_pack_hits`` on the current CUDA stream.
+
+PyTorch is plumbing here (device memory, streams, ``torch.distributed``); all arithmetic happens in the
+hand-written kernels of ``csrc/ptb_kernels.cu``.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import native as N
+
+HITS_DTYPE = np.dtype([("event_number", "<i8"), ("frame", "<u2"), ("column", "<u2"), ("row", "<u2"),
+                       ("charge", "<f4")])
+
+_TOTALS_WORDS = C.sizeof(N.PtbTotals) // 8
+_BASES_WORDS = C.sizeof(N.PtbBases) // 8
+
+
+class PtbError(RuntimeError):
+    pass
+
+
+@dataclass
+class Injected:
+    """Pre-drawn variates of particles [first, first+n) on the device (deterministic mode)."""
+    first: int
+    n: int
+    tensors: dict
+    eloss0_prev: float = 0.0
+
+    def struct(self) -> N.PtbInjected:
+        t = self.tensors
+        p = lambda k: t[k].data_ptr() if k in t and t[k] is not None else None  # noqa: E731
+        return N.PtbInjected(p("zstart"), p("gap"), p("zkick"), p("eloss"), p("accepted"), p("dig_z"), p("dig_off"),
+                             float(self.eloss0_prev))
+
+    @staticmethod
+    def from_numpy(device, first: int, n: int, *, zstart=None, gap=None, zkick=None, eloss=None, accepted=None,
+                   dig_z=None, dig_off=None):
+        """Slice whole-run variate tables (numpy, layout of ``oracle.cpu_oracle.Variates``) to a particle range.
+
+        ``dig_z`` / ``dig_off`` are per-plane lists: normals in consumption order and their CSR offsets [N+1].
+        """
+        t = {}
+        lo, hi = first, first + n
+        up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(device)  # noqa: E731
+        prev = 0.0
+        if zstart is not None:
+            t["zstart"] = up(zstart[lo:hi], np.float64)
+        if gap is not None:
+            t["gap"] = up(gap[lo:hi], np.int64)
+        if zkick is not None:
+            t["zkick"] = up(zkick[lo:hi], np.float64)
+        if eloss is not None:
+            t["eloss"] = up(eloss[:, lo:hi], np.float64)
+            prev = float(eloss[0, lo - 1]) if lo > 0 else 0.0
+        if accepted is not None:
+            t["accepted"] = up(accepted[lo:hi], np.uint8)
+        if dig_z is not None:
+            parts, offs, base = [], [], 0
+            for z, off in zip(dig_z, dig_off):
+                a, b = int(off[lo]), int(off[hi])
+                parts.append(z[a:b])
+                offs.append(off[lo:hi + 1] - a + base)
+                base += b - a
+            t["dig_z"] = up(np.concatenate(parts) if base else np.zeros(1), np.float64)
+            t["dig_off"] = up(np.stack(offs), np.int64)
+        return Injected(first, n, t, prev)
+
+
+@dataclass
+class RunResult:
+    first: int
+    n: int
+    totals: dict
+    slabs: list = field(default_factory=list)      # per plane: dict of device tensors trimmed to the rows produced
+    tracks: dict | None = None                     # device tensors, layout of the reference's hit_tables
+    bases_out: torch.Tensor | None = None
+
+    def hits_numpy(self, plane: int) -> np.ndarray:
+        """Rows of one plane as the reference's structured array (main/device.py:20-28)."""
+        s = self.slabs[plane]
+        out = np.zeros(int(s["event"].numel()), dtype=HITS_DTYPE)
+        out["event_number"] = s["event"].cpu().numpy()
+        out["column"] = s["col"].cpu().numpy().view(np.uint16)
+        out["row"] = s["row"].cpu().numpy().view(np.uint16)
+        out["charge"] = s["charge"].cpu().numpy()
+        return out
+
+
+class Simulator:
+    """One telescope set-up on one GPU."""
+
+    def __init__(self, beam: dict, devices: list, materials: list, device=None, stage_hits: int = 0,
+                 fast_math: bool = False):
+        if not torch.cuda.is_available():
+            raise PtbError("pytestbeam_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.lib = N.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.beam, self.devices, self.materials = dict(beam), list(devices), list(materials)
+        self.D = len(devices)
+        self._opts = dict(stage_hits=int(stage_hits), fast_math=int(bool(fast_math)))
+        self._h = None
+        self._create()
+        self._hits_per_particle = None
+
+    # -- handle ------------------------------------------------------------------------------------
+    def _create(self):
+        self.close()
+        h = C.c_void_p()
+        opt = N.PtbOptions(self._opts["stage_hits"], self._opts["fast_math"], 0.0)
+        with torch.cuda.device(self.device):
+            rc = self.lib.ptb_create(C.byref(N.pack_beam(self.beam)), N.pack_devices(self.devices, self.materials),
+                                     self.D, C.byref(opt), C.byref(h))
+        if rc != 0:
+            msg = self.lib.ptb_last_error(h).decode() if h else "allocation failed"
+            if h:
+                self.lib.ptb_destroy(h)
+            raise ValueError(f"ptb_create failed ({rc}): {msg}")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.ptb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stage_hits(self) -> int:
+        return int(self.lib.ptb_stage_hits(self._h))
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise PtbError(f"{what} failed ({rc}): {self.lib.ptb_last_error(self._h).decode()}")
+
+    # -- buffers -----------------------------------------------------------------------------------
+    def alloc_slabs(self, capacities, keep64=False):
+        slabs = []
+        for c in capacities:
+            c = int(c)
+            s = {"event": torch.empty(c, dtype=torch.int64, device=self.device),
+                 "col": torch.empty(c, dtype=torch.int16, device=self.device),
+                 "row": torch.empty(c, dtype=torch.int16, device=self.device),
+                 "charge": torch.empty(c, dtype=torch.float32, device=self.device)}
+            if keep64:
+                s["charge64"] = torch.empty(c, dtype=torch.float64, device=self.device)
+            slabs.append(s)
+        return slabs
+
+    def alloc_tracks(self, n):
+        D = self.D
+        f8 = lambda m: torch.empty(m, dtype=torch.float64, device=self.device)  # noqa: E731
+        return {"energy": f8(n * D), "angle_x": f8(n * D), "angle_y": f8(n * D), "x": f8(n * D), "y": f8(n * D),
+                "z": f8(n * D), "time_stamp": torch.empty(n * D, dtype=torch.int64, device=self.device),
+                "eloss": f8(D * n), "accepted": torch.empty(n, dtype=torch.uint8, device=self.device)}
+
+    def workspace_bytes(self, n, capacities, flags) -> int:
+        caps = (C.c_uint64 * self.D)(*[int(c) for c in capacities])
+        return int(self.lib.ptb_workspace_bytes(self._h, int(n), caps, int(flags)))
+
+    def new_bases(self) -> torch.Tensor:
+        return torch.zeros(_BASES_WORDS, dtype=torch.int64, device=self.device)
+
+    def hits_per_particle(self, seed=12345, pilot=32768) -> np.ndarray:
+        """Hits per particle and plane measured on a small pilot range (sizes the slabs of large runs)."""
+        if self._hits_per_particle is None:
+            r = self.run(0, pilot, seed=seed, capacities=[pilot * 64] * self.D)
+            self._hits_per_particle = np.array(r.totals["hits"], dtype=np.float64) / pilot
+        return self._hits_per_particle
+
+    def default_capacities(self, n: int):
+        hpp = self.hits_per_particle()
+        return [int(n * h * 1.05 + 8 * np.sqrt(n * max(h, 1e-3) * 30) + 4096) for h in hpp]
+
+    # -- one call of ptb_simulate --------------------------------------------------------------------
+    def launch(self, first, n, *, seed=0, injected: Injected | None = None, flags=N.PTB_DIGITISE, slabs=None,
+               tracks=None, bases_in=None, bases_out=None, totals=None, workspace=None):
+        """Enqueue one ptb_simulate call on the current stream (no synchronisation)."""
+        run = N.PtbRun()
+        run.first, run.n, run.seed, run.flags = int(first), int(n), int(seed) & (2**64 - 1), int(flags)
+        inj_struct = None
+        if injected is not None:
+            if injected.first != first or injected.n != n:
+                raise ValueError("injected tables do not cover the requested particle range")
+            inj_struct = injected.struct()
+            run.injected = C.pointer(inj_struct)
+        if tracks is not None:
+            for k in ("energy", "angle_x", "angle_y", "x", "y", "z", "time_stamp", "eloss", "accepted"):
+                if tracks.get(k) is not None:
+                    setattr(run.tracks, k, tracks[k].data_ptr())
+        if slabs is not None:
+            for d, s in enumerate(slabs):
+                run.slabs[d] = N.PtbHitSlab(s["event"].data_ptr(), s["col"].data_ptr(), s["row"].data_ptr(),
+                                            s["charge"].data_ptr(),
+                                            s["charge64"].data_ptr() if "charge64" in s else None,
+                                            int(s["event"].numel()))
+        run.bases_in = bases_in.data_ptr() if bases_in is not None else None
+        run.bases_out = bases_out.data_ptr() if bases_out is not None else None
+        run.totals = totals.data_ptr()
+        run.workspace = workspace.data_ptr()
+        run.workspace_bytes = workspace.numel()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ptb_simulate(self._h, C.byref(run), C.c_void_p(stream)), "ptb_simulate")
+
+    @staticmethod
+    def decode_totals(t: torch.Tensor, D: int) -> dict:
+        a = t.cpu().numpy()
+        u = a.view(np.uint64)
+        return {"hits": [int(v) for v in u[:D]], "accepted": int(u[32]), "time_sum": int(a[33]), "pairs": int(u[34]),
+                "inside": int(u[35]), "pixels": int(u[36]), "error": int(u[37] & 0xFFFFFFFF)}
+
+    def run(self, first, n, *, seed=0, injected=None, digitise=True, write_tracks=False, tracks_in=None,
+            keep_charge64=False, capacities=None, bases_in=None) -> RunResult:
+        """Simulate particles [first, first+n), synchronise and return trimmed device buffers.
+
+        Retries with exact slab sizes / a larger shared-memory stage when the device reports an overflow.
+        """
+        first, n = int(first), int(n)
+        flags = 0
+        if digitise:
+            flags |= N.PTB_DIGITISE
+        if tracks_in is not None:
+            flags |= N.PTB_TRACKS_FROM_TABLE
+        if write_tracks:
+            flags |= N.PTB_WRITE_TRACKS
+        if keep_charge64:
+            flags |= N.PTB_KEEP_CHARGE64
+        if capacities is None:
+            capacities = [4 * n + 4096] * self.D if digitise else [0] * self.D
+        for attempt in range(8):
+            slabs = self.alloc_slabs(capacities, keep_charge64) if digitise else None
+            tracks = tracks_in if tracks_in is not None else (self.alloc_tracks(n) if write_tracks else None)
+            totals = torch.zeros(_TOTALS_WORDS, dtype=torch.int64, device=self.device)
+            bases_out = self.new_bases()
+            ws = torch.empty(self.workspace_bytes(n, capacities, flags), dtype=torch.uint8, device=self.device)
+            self.launch(first, n, seed=seed, injected=injected, flags=flags, slabs=slabs, tracks=tracks,
+                        bases_in=bases_in, bases_out=bases_out, totals=totals, workspace=ws)
+            torch.cuda.synchronize(self.device)
+            tot = self.decode_totals(totals, self.D)
+            err = tot["error"]
+            if err & N.PTB_DEV_BOX_TOO_LARGE:
+                raise PtbError("a cluster bounding box exceeded 2^20 pixels (check pitch / geometry)")
+            if err & N.PTB_DEV_STAGE_OVERFLOW:
+                self._opts["stage_hits"] = self.stage_hits * 2
+                self._create()
+                continue
+            if err & N.PTB_DEV_SLAB_OVERFLOW:
+                capacities = [max(int(h), 1) for h in tot["hits"]]
+                continue
+            if digitise:
+                slabs = [{k: v[:tot["hits"][d]] for k, v in s.items()} for d, s in enumerate(slabs)]
+            return RunResult(first, n, tot, slabs or [], tracks, bases_out)
+        raise PtbError("ptb_simulate kept overflowing its buffers")
+
+    # -- helpers -------------------------------------------------------------------------------------
+    def prefix(self, first, n, *, seed=0, injected: Injected | None = None):
+        """(accepted particles, sum of time gaps) of a particle range."""
+        out = torch.zeros(2, dtype=torch.int64, device=self.device)
+        inj = C.pointer(injected.struct()) if injected is not None else None
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ptb_prefix(self._h, int(first), int(n), int(seed) & (2**64 - 1), inj, out.data_ptr(),
+                                            C.c_void_p(stream)), "ptb_prefix")
+        a = out.cpu().numpy()
+        return int(a[0]), int(a[1])
+
+    def pack_hits(self, slab: dict, n: int | None = None) -> torch.Tensor:
+        """SoA slab -> device tensor of packed 18-byte reference records (uint8 [n*18])."""
+        n = int(slab["event"].numel() if n is None else n)
+        out = torch.empty(n * 18, dtype=torch.uint8, device=self.device)
+        if n:
+            s = N.PtbHitSlab(slab["event"].data_ptr(), slab["col"].data_ptr(), slab["row"].data_ptr(),
+                             slab["charge"].data_ptr(), None, int(slab["event"].numel()))
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            with torch.cuda.device(self.device):
+                rc = self.lib.ptb_pack_hits(C.byref(s), n, out.data_ptr(), C.c_void_p(stream))
+            if rc != 0:
+                raise PtbError(f"ptb_pack_hits failed ({rc})")
+        return out

@@ -1,0 +1,38 @@
+"""The C-ABI shared library loads without a GPU and exports every symbol include/ptb.h declares."""
+import ctypes
+import os
+import re
+
+from pytestbeam_b200 import build, native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "ptb.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ptb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    build.build()
+    lib = ctypes.CDLL(native.LIB_PATH)
+    names = _declared()
+    assert set(names) == set(native.EXPORTS)
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_struct_sizes_match_header_layout():
+    assert ctypes.sizeof(native.PtbBeam) == 80
+    assert ctypes.sizeof(native.PtbDevice) == 104
+    assert ctypes.sizeof(native.PtbInjected) == 64
+    assert ctypes.sizeof(native.PtbHitSlab) == 48
+    assert ctypes.sizeof(native.PtbBases) == 16 + 8 * 32
+    assert ctypes.sizeof(native.PtbTotals) == 8 * 32 + 8 * 5 + 8
+    assert ctypes.sizeof(native.PtbRun) == 32 + 8 + 72 + 48 * 32 + 8 * 5
+
+
+def test_launch_counter_starts_at_zero_without_gpu_work():
+    lib = native.load()
+    assert lib.ptb_launch_count() >= 0

@@ -1,0 +1,161 @@
+"""Deterministic-mode parity: CUDA kernels fed with the oracle's recorded variates vs the CPU oracle
+(itself pinned bit-exactly to the unmodified reference, tests/test_oracle_golden.py) and vs the golden
+fixtures produced by the reference.  IDs (event, column, row) must be bit-exact; fp64 track state within
+1e-6 relative (BASELINE.json north_star); f4 charges equal up to rounding of values that differ by ulps."""
+import glob
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+TRACK_KEYS = ("energy", "angle_x", "angle_y", "x", "y", "z")
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device")
+    return torch
+
+
+def _sim(setup):
+    from pytestbeam_b200.engine import Simulator
+    beam, devices, materials, names = setup
+    return Simulator(beam, devices, materials)
+
+
+def _compare_hits(res, run, D, exact_charge_fraction=0.999):
+    n_total = 0
+    for d in range(D):
+        got = res.hits_numpy(d)
+        want = run.hits[d]
+        assert len(got) == len(want), f"plane {d}: {len(got)} rows vs {len(want)}"
+        assert np.array_equal(got["event_number"], want["event_number"]), f"plane {d} event_number"
+        assert np.array_equal(got["column"], want["column"]), f"plane {d} column"
+        assert np.array_equal(got["row"], want["row"]), f"plane {d} row"
+        assert np.all(got["frame"] == 0)
+        if len(want):
+            same = got["charge"] == want["charge"]
+            assert same.mean() >= exact_charge_fraction, f"plane {d}: only {same.mean():.5f} of f4 charges identical"
+            ulp = np.abs(got["charge"].view(np.int32).astype(np.int64) - want["charge"].view(np.int32).astype(np.int64))
+            assert ulp.max() <= 1, f"plane {d}: f4 charge differs by {ulp.max()} ulp"
+            if "charge64" in res.slabs[d]:
+                q64 = res.slabs[d]["charge64"].cpu().numpy()
+                assert H.rel_err(q64, run.charge64[d]) < 1e-9
+        n_total += len(want)
+    return n_total
+
+
+@pytest.mark.parametrize("name,n,seeds", [("c1", 20000, (1, 2)), ("c3", 20000, (3, 4)), ("c4", 20000, (5, 6)),
+                                          ("c1", 1, (7, 8)), ("c1", 33, (9, 10))])
+def test_fused_deterministic_vs_oracle(torch_cuda, name, n, seeds):
+    setup, run = H.oracle_run(name, n, *seeds)
+    sim = _sim(setup)
+    D = sim.D
+    res = sim.run(0, n, injected=H.injected_for(sim, run, 0, n), write_tracks=True, keep_charge64=True)
+    for i, k in enumerate(TRACK_KEYS):
+        got = res.tracks[k].cpu().numpy()
+        assert H.rel_err(got, run.tracks[i]) < 1e-6, k
+        if k in ("energy", "z"):
+            assert np.array_equal(got, run.tracks[i]), k   # no transcendental on these paths
+    assert np.array_equal(res.tracks["time_stamp"].cpu().numpy(), run.tracks[6])
+    assert np.array_equal(res.tracks["eloss"].cpu().numpy().reshape(D, n), run.eloss)
+    assert np.array_equal(res.tracks["accepted"].cpu().numpy(), run.variates.accepted)
+    rows = _compare_hits(res, run, D)
+    assert res.totals["hits"] == [len(h) for h in run.hits]
+    assert res.totals["accepted"] == int(run.variates.accepted.sum())
+    assert res.totals["pairs"] == run.census["pairs"]
+    assert res.totals["inside"] == run.census["inside"]
+    assert res.totals["pixels"] == run.census["pixels"]
+    assert rows == sum(res.totals["hits"])
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "full_*.npz"))))
+def test_cuda_vs_reference_golden(torch_cuda, path):
+    """CUDA (injected) against the output of the unmodified reference itself (tests/golden/full_*.npz)."""
+    m = re.match(r"full_(c\d)_n(\d+)_s(\d+)_(\d+)\.npz", os.path.basename(path))
+    name, n, a, b = m.group(1), int(m.group(2)), int(m.group(3)), int(m.group(4))
+    gold = np.load(path)
+    setup, run = H.oracle_run(name, n, a, b)
+    sim = _sim(setup)
+    res = sim.run(0, n, injected=H.injected_for(sim, run, 0, n), write_tracks=True)
+    for gk, k in (("energy", "energy"), ("anglex", "angle_x"), ("angley", "angle_y"), ("x", "x"), ("y", "y")):
+        assert H.rel_err(res.tracks[k].cpu().numpy(), gold[gk]) < 1e-6, k
+    assert np.array_equal(res.tracks["time_stamp"].cpu().numpy(), gold["time_stamp"])
+    for d, dn in enumerate(setup[3]):
+        got, want = res.hits_numpy(d), gold["hits_" + dn]
+        for f in ("event_number", "frame", "column", "row"):
+            assert np.array_equal(got[f], want[f]), (dn, f)
+        if len(want):
+            ulp = np.abs(got["charge"].view(np.int32).astype(np.int64) - want["charge"].view(np.int32).astype(np.int64))
+            assert ulp.max() <= 1
+
+
+@pytest.mark.parametrize("name", ["c1", "c4"])
+def test_shard_invariance_deterministic(torch_cuda, name):
+    """Index-range shards with chained bases reproduce the unsharded hit tables byte for byte."""
+    n = 10007
+    setup, run = H.oracle_run(name, n, 21, 22)
+    sim = _sim(setup)
+    whole = sim.run(0, n, injected=H.injected_for(sim, run, 0, n), write_tracks=True)
+    for cuts in ([0, 5000, n], [0, 31, 4097, 4098, n]):
+        bases = None
+        parts, tparts = [], []
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            r = sim.run(lo, hi - lo, injected=H.injected_for(sim, run, lo, hi - lo), write_tracks=True,
+                        bases_in=bases)
+            bases = r.bases_out
+            parts.append([r.hits_numpy(d) for d in range(sim.D)])
+            tparts.append({k: v.cpu().numpy() for k, v in r.tracks.items()})
+        for d in range(sim.D):
+            cat = np.concatenate([p[d] for p in parts])
+            assert cat.tobytes() == whole.hits_numpy(d).tobytes(), (cuts, d)
+        for k in ("energy", "x", "y", "time_stamp"):
+            cat = np.concatenate([t[k] for t in tparts])
+            assert np.array_equal(cat, whole.tracks[k].cpu().numpy()), k
+
+
+def test_digitise_from_track_table(torch_cuda):
+    """PTB_TRACKS_FROM_TABLE = calc_position alone (main/device.py:91-168), fed from a hit_tables tuple."""
+    import torch
+    n = 15000
+    setup, run = H.oracle_run("c4", n, 31, 32)
+    sim = _sim(setup)
+    D = sim.D
+    dev = sim.device
+    tracks_in = {"x": torch.from_numpy(run.tracks[3]).to(dev), "y": torch.from_numpy(run.tracks[4]).to(dev),
+                 "eloss": torch.from_numpy(np.ascontiguousarray(run.eloss)).to(dev),
+                 "accepted": torch.from_numpy(run.variates.accepted).to(dev)}
+    from pytestbeam_b200.engine import Injected
+    inj = Injected.from_numpy(dev, 0, n, dig_z=run.variates.dig_z, dig_off=run.variates.dig_off)
+    res = sim.run(0, n, injected=inj, tracks_in=tracks_in, keep_charge64=True)
+    _compare_hits(res, run, D, exact_charge_fraction=1.0)   # same x, y, e bits in: charges must be identical up to exp()
+
+
+def test_prefix_and_pack(torch_cuda):
+    n = 5000
+    setup, run = H.oracle_run("c1", n, 41, 42)
+    sim = _sim(setup)
+    inj = H.injected_for(sim, run, 0, n)
+    acc, tsum = sim.prefix(0, n, injected=inj)
+    assert acc == int(run.variates.accepted.sum())
+    assert tsum == int(run.variates.gap.sum())
+    res = sim.run(0, n, injected=inj)
+    for d in range(sim.D):
+        packed = sim.pack_hits(res.slabs[d]).cpu().numpy()
+        assert packed.tobytes() == res.hits_numpy(d).tobytes()
+        assert packed.tobytes() == run.hits[d].tobytes() or len(run.hits[d]) > 0
+
+
+def test_geometry_is_refused_like_the_oracle(torch_cuda):
+    from pytestbeam_b200.engine import Simulator
+    beam, devices, materials, _ = H.setup("c1", 10)
+    devices[0]["z_position"] = 5
+    with pytest.raises(ValueError):
+        Simulator(beam, devices, materials)
