@@ -54,6 +54,7 @@ extern "C" {
 #define PTB_TRACKS_FROM_TABLE 2u /* do not generate tracks: read x, y, eloss from PtbRun.tracks (calc_position alone) */
 #define PTB_WRITE_TRACKS 4u      /* store the per-plane track records into PtbRun.tracks */
 #define PTB_KEEP_CHARGE64 8u     /* also store the f8 charge of every hit (PtbHitSlab.charge64) */
+#define PTB_RECYCLE_SLABS 16u    /* rows start at 0 of each slab: ignore bases_in->hits and write bases_out->hits = 0 */
 
 /* beam block of setup.yml; lengths um, angles rad, energy MeV, rate Hz */
 typedef struct PtbBeam {

@@ -216,13 +216,18 @@ HITS_DTYPE = np.dtype([("event_number", "<i8"), ("frame", "<u2"), ("column", "<u
                        ("charge", "<f4")])
 
 
-def draw_interpreter_side(beam, devices, materials, n, seed_interp):
-    """Consume RandomState(seed_interp) in the reference's order; return (zx0, zy0, t0, table, accepted)."""
+def draw_interpreter_side(beam, devices, materials, n, seed_interp, table_override=None):
+    """Consume RandomState(seed_interp) in the reference's order; return (zx0, zy0, t0, table, accepted).
+
+    With ``table_override`` the Landau table is not drawn (tiny N, where the reference itself raises)."""
     rs = np.random.RandomState(seed_interp)
     zx0 = rs.standard_normal()      # np.random.normal(loc, s) == loc + s * this   (main/hit.py:70)
     zy0 = rs.standard_normal()      # main/hit.py:71
     t0 = rs.poisson(particle_distance(beam))                     # main/hit.py:73
-    table = landau_table(rs, beam, devices, materials, n)        # main/hit.py:84-102
+    if table_override is not None:
+        table = np.ascontiguousarray(table_override, dtype=np.float64)
+    else:
+        table = landau_table(rs, beam, devices, materials, n)    # main/hit.py:84-102
     accepted = rs.uniform(0, 1, n) < 0.7                         # main/device.py:56
     return zx0, zy0, int(t0), table, accepted.astype(np.uint8)
 
@@ -271,9 +276,7 @@ def run(beam: dict, devices: list, materials: list, n: int | None = None, seed_i
     """Replay one full reference run (tracks + every plane's digitisation) on the CPU."""
     n = int(beam["nmb_particles"] if n is None else n)
     D = len(devices)
-    zx0, zy0, t0, table, accepted = draw_interpreter_side(beam, devices, materials, n, seed_interp)
-    if table_override is not None:
-        table = np.ascontiguousarray(table_override, dtype=np.float64)
+    zx0, zy0, t0, table, accepted = draw_interpreter_side(beam, devices, materials, n, seed_interp, table_override)
     mt = MT(seed_numba)
     zstart = np.zeros((n, 4))
     gap = np.zeros(n, dtype=np.int64)

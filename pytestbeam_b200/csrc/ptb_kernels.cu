@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(BLOCK) k_simulate(const __grid_constant__ Conf
 constexpr int SCAN_THREADS = 1024;
 constexpr int SCAN_ITEMS = 4;
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan(int D, unsigned long long n_groups, Workspace ws,
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan(int D, unsigned long long n_groups, uint32_t flags, Workspace ws,
                                                        const PtbBases *bases_in, PtbBases *bases_out, PtbTotals *totals)
 {
     __shared__ unsigned long long warp_sum[32];
@@ -462,10 +462,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(int D, unsigned long long
     if (threadIdx.x == 0) {
         const unsigned long long total = carry_s;
         if (c < D) {
-            const unsigned long long b = bases_in ? bases_in->hits[c] : 0ull;
+            const bool               recycle = (flags & PTB_RECYCLE_SLABS) != 0;
+            const unsigned long long b = (bases_in && !recycle) ? bases_in->hits[c] : 0ull;
             ws.bases_used->hits[c] = b;
             totals->hits[c] = total;
-            if (bases_out) bases_out->hits[c] = b + total;
+            if (bases_out) bases_out->hits[c] = recycle ? 0ull : b + total;
         } else if (c == D) {
             const int64_t b = bases_in ? bases_in->event : 0;
             ws.bases_used->event = b;
@@ -882,7 +883,7 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(h, e, "k_simulate launch");
 
-    k_scan<<<D + 5, SCAN_THREADS, 0, st>>>(D, P.n_groups, P.ws, run->bases_in, run->bases_out, run->totals);
+    k_scan<<<D + 5, SCAN_THREADS, 0, st>>>(D, P.n_groups, flags, P.ws, run->bases_in, run->bases_out, run->totals);
     ++g_launches;
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(h, e, "k_scan launch");

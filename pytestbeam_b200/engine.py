@@ -227,7 +227,7 @@ class Simulator:
         Retries with exact slab sizes / a larger shared-memory stage when the device reports an overflow.
         """
         first, n = int(first), int(n)
-        flags = 0
+        flags = N.PTB_RECYCLE_SLABS   # every call of run() gets fresh slabs
         if digitise:
             flags |= N.PTB_DIGITISE
         if tracks_in is not None:

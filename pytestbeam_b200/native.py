@@ -14,6 +14,7 @@ PTB_DIGITISE = 1
 PTB_TRACKS_FROM_TABLE = 2
 PTB_WRITE_TRACKS = 4
 PTB_KEEP_CHARGE64 = 8
+PTB_RECYCLE_SLABS = 16
 
 PTB_DEV_STAGE_OVERFLOW = 1
 PTB_DEV_SLAB_OVERFLOW = 2
