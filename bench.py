@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""Benchmark of the pytestbeam hot path (BASELINE.json metric: simulated electrons/s, tracked + digitised).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--chunk C] [--impl reference]
+
+One step = one pass of the fused hot path (beam draw, 6 plane steps, Landau loss, Highland kicks, 7-plane cluster
+digitisation, ordered hit collection into structure-of-arrays slabs) over one chunk of C electrons of the default
+7-plane telescope, production (Philox) mode.  With the defaults (C=1e7, K=10) the timed region is BASELINE
+config 2: 1e8 electrons on one B200.  N>1 (torchrun): every rank owns a contiguous index range of K*C electrons,
+event-number / time bases come from one all-gather of per-rank prefixes, no data-path collective (weak scaling).
+
+--impl reference times the CPU port of the reference algorithm (oracle/, kind "port": the reference is Python+Numba
+and cannot travel to the GPU box) on all host cores for the same workload, metric and unit.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "simulated electrons/sec (tracked+digitised)"
+UNIT = "electrons/s"
+WORKLOAD = "default 7-plane telescope (6 MIMOSA26 + ITkPix, triggered), production RNG"
+
+
+def flops_per_particle(tot: dict, n: int, D: int) -> float:
+    """Algorithmic FP64 flop count of SURVEY.md section 8(d), from the kernel's own census counters."""
+    P, S, G, A, X = n, n * (D - 1), tot["pairs"], tot["inside"], tot["pixels"]
+    V = 4 * P + 2 * S + D * P + 3 * G + X
+    return (9 * P + 38 * S + 7 * D * P + 58 * G + 24 * A + 55 * X + 8 * V) / n
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        sm.sort()
+        busy = [v for v in sm if mx and v > 0.5 * mx] or sm
+        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------------------
+# CPU port of the reference (oracle/) -- the only places bench.py executes anything under oracle/
+# --------------------------------------------------------------------------------------------------------------
+
+def _cpu_worker(args):
+    n, seed = args
+    from oracle import cpu_oracle as co
+    from pytestbeam_b200 import config as cfg
+    beam, devices, materials, _ = cfg.flatten(cfg.default_setup(n))
+    t = time.perf_counter()
+    r = co.run(beam, devices, materials, n, seed, seed + 1)
+    return time.perf_counter() - t, sum(len(h) for h in r.hits)
+
+
+def cpu_port_rate(sample: int, workers: int, seed: int = 1):
+    """electrons/s of the CPU port on `workers` processes, each simulating `sample` electrons (distinct seeds)."""
+    from oracle import cpu_oracle as co
+    co.build()
+    if workers == 1:
+        dt, hits = _cpu_worker((sample, seed))
+        return sample / dt, hits / dt
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    t = time.perf_counter()
+    with ctx.Pool(workers) as pool:
+        res = pool.map(_cpu_worker, [(sample, seed + 17 * i) for i in range(workers)])
+    wall = time.perf_counter() - t
+    return sample * workers / wall, sum(h for _, h in res) / wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 64))
+    sample = args.cpu_sample or 200_000
+    rates = []
+    for s in range(args.warmup + args.steps):
+        r, h = cpu_port_rate(sample, workers, seed=1 + 1000 * s)
+        if s >= args.warmup:
+            rates.append((r, h))
+    value = sum(r for r, _ in rates) / len(rates)
+    hits = sum(h for _, h in rates) / len(rates)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sample * workers / value * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "hits_per_s": hits,
+            "config": {"workload": WORKLOAD, "electrons_per_step": sample * workers, "planes": 7},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
+                             "sample": f"{workers} processes x {sample} electrons per step, distinct seeds; the "
+                                       "reference itself is single-threaded Python+Numba and cannot travel"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------------------
+
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from pytestbeam_b200 import config as cfg
+    from pytestbeam_b200 import native as N
+    from pytestbeam_b200.engine import Simulator
+    from pytestbeam_b200.pipeline import ChunkPipeline, exclusive_prefix
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    K, W, chunk, seed = args.steps, args.warmup, args.chunk, args.seed
+    beam, devices, materials, _ = cfg.flatten(cfg.default_setup(chunk * K * world))
+    sim = Simulator(beam, devices, materials)
+    D = sim.D
+    lib = sim.lib
+    n_rank = chunk * K
+    first = rank * n_rank            # contiguous index range of this rank
+    pipe = ChunkPipeline(sim, chunk, seed=seed)
+    host_pipe = ChunkPipeline(sim, chunk, seed=seed, host=True, capacities=pipe.caps)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def job(p, to_host):
+        """The timed region: shard prefixes (N>1), then K chunks."""
+        if world > 1:
+            acc, tsum = sim.prefix(first, n_rank, seed=seed)
+            mine = torch.tensor([acc, tsum], dtype=torch.int64, device=sim.device)
+            allv = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allv, mine)
+            base = exclusive_prefix(torch.stack(allv).cpu().numpy(), rank)
+            p.set_bases(int(base[0]), int(base[1]))
+        else:
+            p.set_bases(0, 0)
+        if to_host:
+            return p.run_to_host(first, K)
+        p.run(first, K)
+        return None
+
+    # warm-up: W untimed steps on both paths
+    pipe.set_bases(0, 0)
+    pipe.run(first, W)
+    host_pipe.set_bases(0, 0)
+    host_pipe.run_to_host(first, max(W, 2))
+    sync_all()
+
+    fp64_peak = lib.ptb_measure_fp64_peak(None) if rank == 0 else 0.0
+    sync_all()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.ptb_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sim.timing(True)                 # CUDA events around every k_simulate launch, on the launch stream
+    sync_all()
+    e0.record()
+    job(pipe, False)
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = lib.ptb_launch_count() - launches0
+    sim_ms, sim_launches = sim.timing_read()
+    sim.timing(False)
+    launch_ms = sim_ms / max(sim_launches, 1)
+    clocks = sampler.stop() if rank == 0 else None
+    tot = pipe.totals(0)
+    if tot["error"]:
+        raise SystemExit(f"device error bits {tot['error']:#x}")
+
+    # end to end through the public API: host buffers, D2H of every chunk's hits inside the timed region
+    sync_all()
+    t0 = time.perf_counter()
+    e0.record()
+    rows, d2h = job(host_pipe, True)
+    e1.record()
+    sync_all()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)   # wall clock: what the caller waits for
+
+    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=sim.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = (float(v) for v in t.cpu())
+    total_particles = n_rank * world
+    value = total_particles / (ms * 1e-3)
+    hits_per_particle = sum(tot["hits"]) / chunk
+
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        F = flops_per_particle(tot, chunk, D)
+        alg_bytes = 18.0 * sum(tot["hits"])            # 18 B per hit row, nothing read
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                tj = json.load(f)
+            traffic = tj["dram_bytes_per_launch"] * (chunk / tj["chunk"])
+        except Exception:
+            pass
+        ach_tf = F * chunk / (launch_ms * 1e-3) / 1e12
+        ach_gb = alg_bytes / (launch_ms * 1e-3) / 1e9
+        roof = {"bound": "fp64", "kernel": "k_simulate<PhiloxSource>", "achieved": ach_tf, "peak": fp64_peak / 1e12,
+                "unit": "TFLOP/s", "frac": ach_tf / (fp64_peak / 1e12) if fp64_peak > 0 else None,
+                "peak_source": "in-job DFMA probe (ptb_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
+                "flops_per_electron": F, "launch_ms": launch_ms, "launches_timed": sim_launches,
+                "share_of_step": launch_ms / (ms / K), "traffic": traffic,
+                "hbm": {"achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
+                        "bytes_per_electron": alg_bytes / chunk, "peak_source": hbm_src}}
+        cpu_sample = args.cpu_sample or 1_000_000
+        cpu_val, cpu_hits = cpu_port_rate(cpu_sample, 1) if world == 1 else (None, None)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": WORKLOAD + f", {total_particles:.3g} electrons", "electrons_per_step": chunk,
+                           "planes": D, "hits_per_electron": hits_per_particle, "seed": seed,
+                           "parallelism": f"index-range shards x{world}",
+                           "l2": "no inputs; 1.2 GB of hit rows written per step (> 126 MB L2)"},
+                "hits_per_s": value * hits_per_particle,
+                "clocks": clocks,
+                "e2e": {"value": total_particles / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": d2h / K, "rows_per_step": rows / K,
+                        "note": "ChunkPipeline.run_to_host: SoA hit slabs copied to pinned host memory on a second "
+                                "stream; production mode has no per-step input arrays"},
+                "gpu_launches": int(launches),
+                "roofline": roof}
+        if cpu_val is not None:
+            line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": f"{cpu_sample} electrons, default telescope, single thread "
+                                              "(oracle/ C + numpy port of the reference's sequential loops)",
+                                    "hits_per_s": cpu_hits}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--chunk", type=int, default=10_000_000)
+    ap.add_argument("--seed", type=int, default=20261019)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

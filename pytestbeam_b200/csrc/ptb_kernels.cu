@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "ptb_device.cuh"
 
@@ -629,6 +630,9 @@ struct PtbContext {
     int     device;
     int     fast_math;
     int     sm_count;
+    int     timing;
+    std::vector<cudaEvent_t> ev;   // (start, stop) pairs of k_simulate launches, when timing is enabled
+    size_t  ev_used;
     char    err[512];
 };
 
@@ -659,9 +663,12 @@ extern "C" {
 int ptb_create(const PtbBeam *beam, const PtbDevice *dev, int32_t n_dev, const PtbOptions *opt, PtbHandle *out)
 {
     if (!beam || !dev || !out || n_dev < 1 || n_dev > PTB_MAX_PLANES) return PTB_E_INVALID;
-    PtbContext *h = new (std::nothrow) PtbContext;
+    PtbContext *h = new (std::nothrow) PtbContext();
     if (!h) return PTB_E_NOMEM;
-    memset(h, 0, sizeof(*h));
+    memset(&h->cfg, 0, sizeof(h->cfg));
+    h->timing = 0;
+    h->ev_used = 0;
+    h->err[0] = 0;
     *out = h;
     // the reference's stride-D bookkeeping silently assumes exactly one record per plane and particle,
     // which only holds for z[0] == 0 and distinct consecutive z; refuse anything else
@@ -769,7 +776,53 @@ int ptb_create(const PtbBeam *beam, const PtbDevice *dev, int32_t n_dev, const P
     return PTB_OK;
 }
 
-void ptb_destroy(PtbHandle h) { delete h; }
+void ptb_destroy(PtbHandle h)
+{
+    if (!h) return;
+    for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+    delete h;
+}
+
+int ptb_timing_enable(PtbHandle h, int32_t on)
+{
+    if (!h) return PTB_E_INVALID;
+    h->timing = on ? 1 : 0;
+    return PTB_OK;
+}
+
+int ptb_timing_read(PtbHandle h, double *simulate_ms, uint64_t *launches)
+{
+    if (!h || !simulate_ms || !launches) return PTB_E_INVALID;
+    double sum = 0;
+    for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
+        cudaError_t e = cudaEventSynchronize(h->ev[i + 1]);
+        if (e != cudaSuccess) return fail_cuda(h, e, "cudaEventSynchronize");
+        float ms = 0;
+        e = cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]);
+        if (e != cudaSuccess) return fail_cuda(h, e, "cudaEventElapsedTime");
+        sum += ms;
+    }
+    *simulate_ms = sum;
+    *launches = h->ev_used / 2;
+    h->ev_used = 0;
+    return PTB_OK;
+}
+
+// next (start, stop) event pair of the timing record, or nullptr when timing is off
+static cudaEvent_t *timing_pair(PtbHandle h)
+{
+    if (!h->timing) return nullptr;
+    if (h->ev_used + 2 > h->ev.size()) {
+        for (int i = 0; i < 2; ++i) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+            h->ev.push_back(e);
+        }
+    }
+    cudaEvent_t *p = &h->ev[h->ev_used];
+    h->ev_used += 2;
+    return p;
+}
 
 const char *ptb_last_error(PtbHandle h) { return h ? h->err : "null handle"; }
 
@@ -866,6 +919,8 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
     const size_t smem = warp_shared_bytes(c.stage_hits, keep64) * WARPS_PER_BLOCK;
     const unsigned blocks = (unsigned)((P.n_groups + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
     if (smem > 227 * 1024) return fail(h, PTB_E_INVALID, "stage_hits too large for shared memory");
+    cudaEvent_t *tp = timing_pair(h);
+    if (tp) cudaEventRecord(tp[0], st);
     if (run->injected) {
         InjectedSource src{*run->injected, run->first, run->n};
         auto           kern = k_simulate<InjectedSource>;
@@ -880,6 +935,7 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
         kern<<<blocks, BLOCK, smem, st>>>(c, P, src);
     }
     ++g_launches;
+    if (tp) cudaEventRecord(tp[1], st);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(h, e, "k_simulate launch");
 

@@ -263,6 +263,16 @@ class Simulator:
             return RunResult(first, n, tot, slabs or [], tracks, bases_out)
         raise PtbError("ptb_simulate kept overflowing its buffers")
 
+    def timing(self, on: bool):
+        """Bracket every k_simulate launch with CUDA events on its stream (read back with timing_read)."""
+        self._check(self.lib.ptb_timing_enable(self._h, int(on)), "ptb_timing_enable")
+
+    def timing_read(self):
+        """(summed k_simulate milliseconds, launches) since the last read; waits for the recorded events."""
+        ms, n = C.c_double(), C.c_uint64()
+        self._check(self.lib.ptb_timing_read(self._h, C.byref(ms), C.byref(n)), "ptb_timing_read")
+        return float(ms.value), int(n.value)
+
     # -- helpers -------------------------------------------------------------------------------------
     def prefix(self, first, n, *, seed=0, injected: Injected | None = None):
         """(accepted particles, sum of time gaps) of a particle range."""
