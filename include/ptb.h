@@ -72,8 +72,10 @@ typedef struct PtbDevice {
 } PtbDevice;
 
 typedef struct PtbOptions {
-    int32_t stage_hits;   /* hits one 32-particle group may produce on one plane; 0 = choose from the geometry */
+    int32_t stage_hits;   /* hits one 32-particle group may stage per plane in shared memory; 0 = default (256) */
+    int32_t pool_entries; /* box columns + rows one round of a group may hold in shared memory; 0 = default (256) */
     int32_t fast_math;    /* 0: IEEE operation order of the reference, no FMA contraction; 1: contracted build */
+    int32_t _pad;
     double  trigger_accept; /* main/device.py:56 hard-codes 0.7; 0 = use that */
 } PtbOptions;
 

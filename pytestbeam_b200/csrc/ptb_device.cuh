@@ -32,7 +32,7 @@ struct PlaneK {
 };
 
 struct ConfigK {
-    int32_t n_planes, stage_hits;
+    int32_t n_planes, stage_hits, pool_entries, _pad0;
     double  energy, loc_x, sigma_x, loc_y, sigma_y, disp_x, disp_y, angle_x, angle_y;
     double  theta0_first;                // Highland width of plane 0 at beam energy: event 0 only, main/hit.py:75-80
     double  accept_p;                    // main/device.py:56
@@ -106,13 +106,6 @@ __device__ __forceinline__ void normal_pair_f32(uint32_t a, uint32_t b, double &
     sincospif(v, &s, &c);
     n0 = (double)(r * c);
     n1 = (double)(r * s);
-}
-__device__ __forceinline__ double normal_one_f32(uint32_t a, uint32_t b, bool second)
-{
-    float u = fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-    float v = fmaf((float)b, 4.6566128730773926e-10f, 2.3283064365386963e-10f);
-    float r = sqrtf(-2.0f * logf(u));
-    return (double)(r * (second ? sinpif(v) : cospif(v)));
 }
 // Box-Muller pair in fp64 (beam profile: sigma of millimetres against a pitch of micrometres)
 __device__ __forceinline__ void normal_pair_f64(U4 w, double &n0, double &n1)
@@ -205,10 +198,12 @@ struct PhiloxSource {
         normal_pair_f32(w.x, w.y, zrx, zry);
         normal_pair_f32(w.z, w.w, zseed, spare);
     }
-    __device__ double pixel(uint64_t k, int d, uint32_t j) const
+    // noise normals of box pixels 4q .. 4q+3 of particle k on plane d: one Philox block
+    __device__ void pixel4(uint64_t k, int d, uint32_t q, int /*count*/, double z[4]) const
     {
-        U4 w = philox_at(seed, k, SITE_PLANE + 4 * d + SUB_PIX, j >> 2);
-        return (j & 2u) ? normal_one_f32(w.z, w.w, j & 1u) : normal_one_f32(w.x, w.y, j & 1u);
+        U4 w = philox_at(seed, k, SITE_PLANE + 4 * d + SUB_PIX, q);
+        normal_pair_f32(w.x, w.y, z[0], z[1]);
+        normal_pair_f32(w.z, w.w, z[2], z[3]);
     }
 };
 
@@ -240,9 +235,11 @@ struct InjectedSource {
         const double *p = v.dig_z + v.dig_off[(uint64_t)d * (n + 1) + (k - first)];
         zrx = p[0]; zry = p[1]; zseed = p[2];
     }
-    __device__ double pixel(uint64_t k, int d, uint32_t j) const
+    __device__ void pixel4(uint64_t k, int d, uint32_t q, int count, double z[4]) const
     {
-        return v.dig_z[v.dig_off[(uint64_t)d * (n + 1) + (k - first)] + 3 + j];
+        const double *p = v.dig_z + v.dig_off[(uint64_t)d * (n + 1) + (k - first)] + 3 + 4 * (uint64_t)q;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) z[i] = i < count ? p[i] : 0.0;
     }
 };
 

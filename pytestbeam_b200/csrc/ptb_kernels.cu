@@ -98,14 +98,17 @@ static size_t carve_workspace(int D, unsigned long long n, const unsigned long l
 // shared memory of one warp: the per-particle cluster descriptors and the hit stage
 struct WarpShared {
     double   x[32], y[32], rx[32], ry[32], q[32], inx[32], iny[32], seedq[32];
-    int      clo[32], rlo[32], nrows[32], prefix[32];
+    int      clo[32], rlo[32], ncols[32], nrows[32];
+    int      pprefix[32], qprefix[32], poff[32];   // work-list prefixes: profile entries, pixel quads; pool offset
     uint32_t seedcr[32];
     uint8_t  evoff[32];
 };
 
-__host__ __device__ inline size_t warp_shared_bytes(int stage, bool keep64)
+// bytes of one warp's region: descriptors, profile pool (2 doubles per column / row), hit stage
+__host__ __device__ inline size_t warp_shared_bytes(int stage, int pool, bool keep64)
 {
     size_t b = sizeof(WarpShared);
+    b += (size_t)pool * 16;               // profile value and ellipse term per box column / row
     b += (size_t)stage * (4 + 4);         // packed (col,row), f32 charge
     b += keep64 ? (size_t)stage * 8 : 0;  // f64 charge
     b += (size_t)stage;                   // event offset within the group
@@ -131,15 +134,18 @@ __global__ void __launch_bounds__(BLOCK) k_simulate(const __grid_constant__ Conf
 
     const int    D = cfg.n_planes;
     const int    S = cfg.stage_hits;
+    const int    PC = cfg.pool_entries;
     const bool   keep64 = (P.flags & PTB_KEEP_CHARGE64) != 0;
     const bool   digitise = (P.flags & PTB_DIGITISE) != 0;
     const bool   from_table = (P.flags & PTB_TRACKS_FROM_TABLE) != 0;
     const bool   write_tracks = (P.flags & PTB_WRITE_TRACKS) != 0;
-    const size_t wbytes = warp_shared_bytes(S, keep64);
+    const size_t wbytes = warp_shared_bytes(S, PC, keep64);
 
     unsigned char *wbase = smem_raw + wbytes * wib;
     WarpShared    &W = *reinterpret_cast<WarpShared *>(wbase);
-    uint32_t      *st_cr = reinterpret_cast<uint32_t *>(wbase + sizeof(WarpShared));
+    double        *pool_g = reinterpret_cast<double *>(wbase + sizeof(WarpShared));
+    double        *pool_e = pool_g + PC;
+    uint32_t      *st_cr = reinterpret_cast<uint32_t *>(pool_e + PC);
     float         *st_q = reinterpret_cast<float *>(st_cr + S);
     double        *st_q64 = reinterpret_cast<double *>(st_q + S);
     uint8_t       *st_ev = reinterpret_cast<uint8_t *>(st_q + S) + (keep64 ? (size_t)S * 8 : 0);
@@ -238,7 +244,7 @@ __global__ void __launch_bounds__(BLOCK) k_simulate(const __grid_constant__ Conf
         if (!digitise) continue;
 
         // ---- cluster descriptors, one lane per particle (main/device.py:137-140, 241-266) -----------
-        int cnt = 0;
+        int cnt = 0, nprof = 0;
         if (valid && (acc || !pl.triggered)) {
             ++n_pairs;
             const double sig = cloud_sigma(cfg, eloss);
@@ -262,100 +268,179 @@ __global__ void __launch_bounds__(BLOCK) k_simulate(const __grid_constant__ Conf
                 const int    r_lo = pixel_index(y - ry, pl.delta_y, pl.pitch_r, pl.half_nr);
                 const long long nc = (long long)c_hi - c_lo + 1, nr = (long long)r_hi - r_lo + 1;
                 long long       box = (nc > 0 && nr > 0) ? nc * nr : 0;
-                if (box > (1ll << 20)) {
+                if (box > (1ll << 20) || nc + nr > PC) {
                     err |= PTB_DEV_BOX_TOO_LARGE;
                     box = 0;
                 }
-                cnt = (int)box;
+                if (box > 0) {
+                    cnt = (int)box;
+                    nprof = (int)(nc + nr);
+                }
                 W.x[lane] = x; W.y[lane] = y; W.rx[lane] = rx; W.ry[lane] = ry;
                 W.q[lane] = q; W.inx[lane] = inx; W.iny[lane] = iny; W.seedq[lane] = seedq;
-                W.clo[lane] = c_lo; W.rlo[lane] = r_lo; W.nrows[lane] = (int)nr;
+                W.clo[lane] = c_lo; W.rlo[lane] = r_lo; W.ncols[lane] = (int)nc; W.nrows[lane] = (int)nr;
                 W.seedcr[lane] = (uint32_t)sc | ((uint32_t)sr << 16);
             }
         }
         n_pixels += (unsigned)cnt;
-        int incl = cnt;
-#pragma unroll
-        for (int s = 1; s < 32; s <<= 1) {
-            int o = __shfl_up_sync(FULL, incl, s);
-            if (lane >= s) incl += o;
-        }
-        W.prefix[lane] = incl;
-        const int total = __shfl_sync(FULL, incl, 31);
-        __syncwarp();
 
-        // ---- pixel work list: 32 items per step in (particle, column, row) order ---------------------
-        int n_plane = 0;           // hits staged for this plane (warp-uniform)
-        int carry_owner = -1;      // particle whose items straddle the previous step, and its kept count
-        int carry_kept = 0;
-        for (int w0 = 0; w0 < total; w0 += 32) {
-            const int  w = w0 + lane;
-            const bool has = w < total;
-            int        own = 0;
+        // The particles of the group are served in rounds so that the 1-D profiles of one round fit the
+        // shared-memory pool (one round in all but pathological geometries).
+        int n_plane = 0;   // hits staged for this plane (warp-uniform)
+        int o_begin = 0;
+        while (true) {
+            // inclusive prefix of the profile entries of lanes >= o_begin
+            int pin = (lane >= o_begin) ? nprof : 0;
 #pragma unroll
-            for (int s = 16; s > 0; s >>= 1)
-                if (W.prefix[own + s - 1] <= w) own += s;
-            own = has ? own : 31;
-            const int excl = own ? W.prefix[own - 1] : 0;
-            const int end = W.prefix[own];
-            const int j = w - excl;
-            bool      keep = false;
-            double    charge = 0;
-            uint32_t  cr = 0;
-            if (has) {
-                const int    nrw = W.nrows[own];
-                const int    ci = j / nrw;
-                const int    ri = j - ci * nrw;
-                const int    col = W.clo[own] + ci;
-                const int    row = W.rlo[own] + ri;
-                const double px = W.x[own], py = W.y[own], rx = W.rx[own], ry = W.ry[own];
-                const double cx = pixel_centre(col, pl.delta_x, pl.pitch_c, pl.half_nc, pl.half_pc);
-                const double cy = pixel_centre(row, pl.delta_y, pl.pitch_r, pl.half_nr, pl.half_pr);
-                const double dx = cx - px, dy = cy - py;
-                const double zn = src.pixel(P.first + group * 32 + own, d, (uint32_t)j);
-                const double noise = 0.0 + pl.noise_sigma * zn;
-                const double gx = W.inx[own] * profile_shape(dx, profile_radius(rx));
-                const double gy = W.iny[own] * profile_shape(dy, profile_radius(ry));
-                const double signal = W.q[own] * (gx * gy);
-                charge = (signal + noise) * 1e-3 * pl.pitch_c * pl.pitch_r;   // main/device.py:275-288
-                keep = charge >= pl.thr_ke && rx > 0.0 && ry > 0.0 &&
-                       (dx * dx) / (rx * rx) + (dy * dy) / (ry * ry) <= 1.0 && col >= 1 && col <= pl.ncol &&
-                       row >= 1 && row <= pl.nrow;                            // main/device.py:289-295
-                cr = (uint32_t)col | ((uint32_t)row << 16);
+            for (int s = 1; s < 32; s <<= 1) {
+                int o = __shfl_up_sync(FULL, pin, s);
+                if (lane >= s) pin += o;
             }
-            // kept count of my particle so far: lanes of one particle are contiguous in the work list
-            const unsigned keptmask = __ballot_sync(FULL, keep);
-            const int      lo_lane = has ? max(excl - w0, 0) : 0;
-            const int      hi_lane = has ? min(end - 1 - w0, 31) : 0;
-            const unsigned grp = (hi_lane >= 31 ? FULL : ((1u << (hi_lane + 1)) - 1u)) & ~((1u << lo_lane) - 1u);
-            const int      kept_here = __popc(keptmask & grp);
-            const int      kept_before = (own == carry_owner) ? carry_kept : 0;
-            // seed fallback (main/device.py:299-302): the particle's last box pixel emits the seed pixel
-            // instead when nothing in the box survived
-            bool fallback = false;
-            if (has && w == end - 1 && kept_before + kept_here == 0 && W.seedq[own] >= pl.thr_ke) {
-                fallback = true;
-                charge = W.seedq[own];
-                cr = W.seedcr[own];
+            const unsigned fits = __ballot_sync(FULL, pin <= PC);           // a prefix: monotone in the lane
+            const int      o_end = (fits == FULL) ? 32 : __ffs(~fits) - 1;  // first lane that does not fit
+            const bool     mine = lane >= o_begin && lane < o_end;
+            const int      my_prof = mine ? nprof : 0;
+            const int      my_quads = mine ? (cnt + 3) >> 2 : 0;
+            int            qin = my_quads;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                int o = __shfl_up_sync(FULL, qin, s);
+                if (lane >= s) qin += o;
             }
-            const bool     emit = keep || fallback;
-            const unsigned emask = __ballot_sync(FULL, emit);
-            if (emit) {
-                const int pos = n_plane + __popc(emask & lanemask_lt());
-                if (pos < S) {
-                    st_cr[pos] = cr;
-                    st_q[pos] = (float)charge;
-                    st_ev[pos] = W.evoff[own];
-                    if (keep64) st_q64[pos] = charge;
-                } else {
-                    err |= PTB_DEV_STAGE_OVERFLOW;
+            const int prof_total = __shfl_sync(FULL, pin, o_end - 1);   // o_end > o_begin: one box always fits
+            const int quad_total = __shfl_sync(FULL, qin, 31);
+            __syncwarp();
+            W.pprefix[lane] = mine ? pin : (lane < o_begin ? 0 : prof_total);
+            W.qprefix[lane] = qin;
+            W.poff[lane] = pin - my_prof;
+            __syncwarp();
+
+            // ---- phase A: the separable parts of every pixel of the round, once per column and per row:
+            //      profile = 1/(sigma sqrt(2pi)) exp(-(d^2)/(2 sigma^2))  (main/device.py:378)
+            //      ellipse = d^2 / r^2                                    (main/device.py:291-293)
+            for (int t0 = 0; t0 < prof_total; t0 += 32) {
+                const int t = t0 + lane;
+                if (t < prof_total) {
+                    int own = 0;
+#pragma unroll
+                    for (int s = 16; s > 0; s >>= 1)
+                        if (W.pprefix[own + s - 1] <= t) own += s;
+                    const int    e = t - W.poff[own];
+                    const int    ncl = W.ncols[own];
+                    const bool   is_row = e >= ncl;
+                    const int    idx = is_row ? W.rlo[own] + (e - ncl) : W.clo[own] + e;
+                    const double ctr = is_row ? pixel_centre(idx, pl.delta_y, pl.pitch_r, pl.half_nr, pl.half_pr)
+                                              : pixel_centre(idx, pl.delta_x, pl.pitch_c, pl.half_nc, pl.half_pc);
+                    const double pos = is_row ? W.y[own] : W.x[own];
+                    const double r = is_row ? W.ry[own] : W.rx[own];
+                    const double nrm = is_row ? W.iny[own] : W.inx[own];
+                    const double dd = ctr - pos;
+                    pool_g[t] = nrm * profile_shape(dd, profile_radius(r));
+                    pool_e[t] = (dd * dd) / (r * r);
                 }
             }
-            n_plane += __popc(emask);
-            // carry for a particle that continues into the next step
-            const int last_lane = min(total - w0, 32) - 1;
-            carry_owner = __shfl_sync(FULL, own, last_lane);
-            carry_kept = __shfl_sync(FULL, kept_before + kept_here, last_lane);
+            __syncwarp();
+
+            // ---- phase B: pixels in (particle, column, row) order, four per lane and step -----------------
+            int carry_owner = -1;   // particle whose pixels straddle the previous step, and its kept count
+            int carry_kept = 0;
+            for (int w0 = 0; w0 < quad_total; w0 += 32) {
+                const int  w = w0 + lane;
+                const bool has = w < quad_total;
+                int        own = 0;
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1)
+                    if (W.qprefix[own + s - 1] <= w) own += s;
+                own = has ? own : 31;
+                const int excl = own ? W.qprefix[own - 1] : 0;
+                const int end = W.qprefix[own];
+                const int qi = w - excl;            // quad index inside the particle's box
+                int       kq = 0;                   // pixels of this quad that survive
+                unsigned  kmask = 0;                // ... and which ones
+                double    hq[4];
+                uint32_t  hcr[4];
+                if (has) {
+                    const int    ncl = W.ncols[own], nrw = W.nrows[own];
+                    const int    box = ncl * nrw;
+                    const int    po = W.poff[own];
+                    const double qtot = W.q[own];
+                    const bool   rpos = W.rx[own] > 0.0 && W.ry[own] > 0.0;
+                    const int    clo = W.clo[own], rlo = W.rlo[own];
+                    double       zn[4];
+                    src.pixel4(P.first + group * 32 + own, d, (uint32_t)qi, min(4, box - 4 * qi), zn);
+                    // column / row of the quad's first pixel; the following ones advance row-first
+                    int ci = (4 * qi) / nrw;
+                    int ri = 4 * qi - ci * nrw;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (4 * qi + i < box) {
+                            const int    col = clo + ci, row = rlo + ri;
+                            const double noise = 0.0 + pl.noise_sigma * zn[i];
+                            const double signal = qtot * (pool_g[po + ci] * pool_g[po + ncl + ri]);
+                            const double charge = (signal + noise) * 1e-3 * pl.pitch_c * pl.pitch_r;  // device.py:275-288
+                            const bool   keep = charge >= pl.thr_ke && rpos &&
+                                              pool_e[po + ci] + pool_e[po + ncl + ri] <= 1.0 && col >= 1 &&
+                                              col <= pl.ncol && row >= 1 && row <= pl.nrow;         // device.py:289-295
+                            hq[i] = charge;
+                            hcr[i] = (uint32_t)col | ((uint32_t)row << 16);
+                            if (keep) {
+                                kmask |= 1u << i;
+                                ++kq;
+                            }
+                            if (++ri == nrw) {
+                                ri = 0;
+                                ++ci;
+                            }
+                        }
+                    }
+                }
+                // kept pixels of my particle so far: the lanes of one particle are contiguous in the work list
+                int kin = kq;
+#pragma unroll
+                for (int s = 1; s < 32; s <<= 1) {
+                    int o = __shfl_up_sync(FULL, kin, s);
+                    if (lane >= s) kin += o;
+                }
+                const int lo_lane = has ? max(excl - w0, 0) : 0;
+                const int hi_lane = has ? min(end - 1 - w0, 31) : 0;
+                const int k_hi = __shfl_sync(FULL, kin, hi_lane);
+                const int k_lo = __shfl_sync(FULL, kin, max(lo_lane - 1, 0));
+                const int kept_here = k_hi - (lo_lane > 0 ? k_lo : 0);
+                const int kept_before = (own == carry_owner) ? carry_kept : 0;
+                // seed fallback (main/device.py:299-302): the lane holding the particle's last quad emits the
+                // seed pixel when nothing in the box survived (its own kq is then 0)
+                const bool fb = has && w == end - 1 && kept_before + kept_here == 0 && W.seedq[own] >= pl.thr_ke;
+                if (fb) {
+                    hq[0] = W.seedq[own];
+                    hcr[0] = W.seedcr[own];
+                    kmask = 1u;
+                }
+                const unsigned fbmask = __ballot_sync(FULL, fb);
+                // position = hits of earlier steps + kept pixels of lower lanes + fallbacks of lower lanes
+                int       pos = n_plane + (kin - kq) + __popc(fbmask & lanemask_lt());
+                const int ev_off = W.evoff[own];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (kmask & (1u << i)) {
+                        if (pos < S) {
+                            st_cr[pos] = hcr[i];
+                            st_q[pos] = (float)hq[i];
+                            st_ev[pos] = (uint8_t)ev_off;
+                            if (keep64) st_q64[pos] = hq[i];
+                        } else {
+                            err |= PTB_DEV_STAGE_OVERFLOW;
+                        }
+                        ++pos;
+                    }
+                }
+                n_plane += __shfl_sync(FULL, kin, 31) + __popc(fbmask);
+                // carry for a particle that continues into the next step
+                const int last_lane = min(quad_total - w0, 32) - 1;
+                carry_owner = __shfl_sync(FULL, own, last_lane);
+                carry_kept = __shfl_sync(FULL, kept_before + kept_here, last_lane);
+            }
+            if (o_end >= 32) break;
+            o_begin = o_end;
         }
         __syncwarp();
 
@@ -683,8 +768,10 @@ int ptb_create(const PtbBeam *beam, const PtbDevice *dev, int32_t n_dev, const P
 
     ConfigK &c = h->cfg;
     c.n_planes = n_dev;
-    c.stage_hits = (opt && opt->stage_hits > 0) ? opt->stage_hits : 512;
+    c.stage_hits = (opt && opt->stage_hits > 0) ? opt->stage_hits : 256;
     c.stage_hits = (c.stage_hits + 3) / 4 * 4;
+    c.pool_entries = (opt && opt->pool_entries > 0) ? opt->pool_entries : 256;
+    c.pool_entries = (c.pool_entries + 1) / 2 * 2;
     h->fast_math = opt ? opt->fast_math : 0;
     c.energy = beam->energy;
     c.loc_x = beam->loc_x; c.sigma_x = beam->sigma_x;
@@ -916,7 +1003,7 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
     if (e != cudaSuccess) return fail_cuda(h, e, "memset totals");
 
     const bool   keep64 = (flags & PTB_KEEP_CHARGE64) != 0;
-    const size_t smem = warp_shared_bytes(c.stage_hits, keep64) * WARPS_PER_BLOCK;
+    const size_t smem = warp_shared_bytes(c.stage_hits, c.pool_entries, keep64) * WARPS_PER_BLOCK;
     const unsigned blocks = (unsigned)((P.n_groups + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
     if (smem > 227 * 1024) return fail(h, PTB_E_INVALID, "stage_hits too large for shared memory");
     cudaEvent_t *tp = timing_pair(h);
@@ -926,12 +1013,14 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
         auto           kern = k_simulate<InjectedSource>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail_cuda(h, e, "cudaFuncSetAttribute");
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         kern<<<blocks, BLOCK, smem, st>>>(c, P, src);
     } else {
         PhiloxSource src{run->seed};
         auto         kern = k_simulate<PhiloxSource>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail_cuda(h, e, "cudaFuncSetAttribute");
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         kern<<<blocks, BLOCK, smem, st>>>(c, P, src);
     }
     ++g_launches;

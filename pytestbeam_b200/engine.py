@@ -113,7 +113,7 @@ class Simulator:
     def _create(self):
         self.close()
         h = C.c_void_p()
-        opt = N.PtbOptions(self._opts["stage_hits"], self._opts["fast_math"], 0.0)
+        opt = N.PtbOptions(self._opts["stage_hits"], 0, self._opts["fast_math"], 0, 0.0)
         with torch.cuda.device(self.device):
             rc = self.lib.ptb_create(C.byref(N.pack_beam(self.beam)), N.pack_devices(self.devices, self.materials),
                                      self.D, C.byref(opt), C.byref(h))

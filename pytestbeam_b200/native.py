@@ -40,7 +40,8 @@ class PtbDevice(C.Structure):
 
 
 class PtbOptions(C.Structure):
-    _fields_ = [("stage_hits", C.c_int32), ("fast_math", C.c_int32), ("trigger_accept", C.c_double)]
+    _fields_ = [("stage_hits", C.c_int32), ("pool_entries", C.c_int32), ("fast_math", C.c_int32), ("_pad", C.c_int32),
+                ("trigger_accept", C.c_double)]
 
 
 class PtbInjected(C.Structure):
