@@ -28,7 +28,8 @@ struct PlaneK {
     double noise_sigma;                  // sqrt(k_b*300*C)/e, main/device.py:410-415
     double lan_loc, lan_scale;           // energy loss = loc + scale * lambda (Moyal variable), main/hit.py:399-400
     double lan_ulo, lan_uspan;           // window of the Moyal CDF that maps onto [0, 0.5] MeV, main/hit.py:99-100
-    int32_t ncol, nrow, triggered, _pad;
+    int32_t ncol, nrow, triggered;
+    int32_t lan_direct;                  // 1: the window holds essentially all of the Moyal law: sample -ln(Z^2) directly
 };
 
 struct ConfigK {
@@ -40,6 +41,7 @@ struct ConfigK {
     double  lam, p_loglam, p_b, p_a, p_log_invalpha, p_vr, p_explam;
     // charge-cloud constants, main/device.py:186-202
     double  diff2, qe, c3mu, t90, cden;
+    double  sigma0;                      // cloud width for a vanishing deposit
     PlaneK  pl[PTB_MAX_PLANES];
 };
 
@@ -173,22 +175,39 @@ struct PhiloxSource {
     {
         U4 w = philox_at(seed, k, SITE_PLANE + 4 * d + SUB_STEP, 0);
         normal_pair_f32(w.x, w.y, zkx, zky);
-        eloss = landau(cfg.pl[d], w.z, w.w);
+        eloss = landau(cfg.pl[d], k, d, w.z, w.w);
     }
     __device__ double eloss_only(const ConfigK &cfg, uint64_t k, int d) const
     {
         U4 w = philox_at(seed, k, SITE_PLANE + 4 * d + SUB_STEP, 0);
-        return landau(cfg.pl[d], w.z, w.w);
+        return landau(cfg.pl[d], k, d, w.z, w.w);
     }
-    // truncated Moyal law by inversion: F(lambda) = erfc(exp(-lambda/2)/sqrt2) restricted to the window that
-    // maps onto [0, 0.5] MeV -- the law the reference's accept/reject pool follows (main/hit.py:345-359,
-    // 399-400, 431)
-    __device__ static double landau(const PlaneK &p, uint32_t a, uint32_t b)
+    // Energy loss: the Moyal-form law the reference's accept/reject pool follows (main/hit.py:345-359, 399-400,
+    // 431), restricted to [0, 0.5] MeV.  If Z ~ N(0,1) then -ln(Z^2) is Moyal distributed, so when
+    // the window holds practically all of the law two normals are tried and the (astronomically rare) leftovers
+    // go to the inversion below; planes whose window is a thin slice of the law (thick absorbers) always invert.
+    __device__ double landau(const PlaneK &p, uint64_t k, int d, uint32_t a, uint32_t b) const
     {
-        double        U = p.lan_ulo + p.lan_uspan * u53_open(a, b);
-        double        s = erfcinv(U);
-        double        lam = -2.0 * log(1.4142135623730951 * s);
-        double        e = p.lan_loc + p.lan_scale * lam;
+        if (p.lan_direct) {
+            double z0, z1;
+            normal_pair_f32(a, b, z0, z1);
+            double e = p.lan_loc + p.lan_scale * (double)(-2.0f * logf(fabsf((float)z0)));
+            if (e >= 0.0 && e <= 0.5) return e;
+            e = p.lan_loc + p.lan_scale * (double)(-2.0f * logf(fabsf((float)z1)));
+            if (e >= 0.0 && e <= 0.5) return e;
+            U4 w = philox_at(seed, k, SITE_PLANE + 4 * d + SUB_STEP, 1);
+            a = w.x;
+            b = w.y;
+        }
+        return landau_inverse(p, a, b);
+    }
+    // inversion of F(lambda) = erfc(exp(-lambda/2)/sqrt2) on the window
+    __device__ static __noinline__ double landau_inverse(const PlaneK &p, uint32_t a, uint32_t b)
+    {
+        double U = p.lan_ulo + p.lan_uspan * u53_open(a, b);
+        double s = erfcinv(U);
+        double lam = -2.0 * log(1.4142135623730951 * s);
+        double e = p.lan_loc + p.lan_scale * lam;
         return fmin(fmax(e, 0.0), 0.5);
     }
     __device__ void dig(uint64_t k, int d, double &zrx, double &zry, double &zseed) const
@@ -258,12 +277,22 @@ __host__ __device__ __forceinline__ double highland_theta0(double energy, double
 }
 
 // width of the collected charge cloud in um, main/device.py:186-202.  np.cbrt under Numba is pow(x, 1/3).
+// pow(x, 1.0/3.0) for x > 0, i.e. with the exponent rounded to double as the reference evaluates it:
+// x^(1/3 + delta) = cbrt(x) * (1 + delta ln x), delta = double(1/3) - 1/3 = -1.85e-17 (the correction is a fraction
+// of an ulp, so a float logarithm is ample).  ~6x fewer instructions than the generic pow and no far call.
+__device__ __forceinline__ double pow_one_third(double x)
+{
+    const double c = cbrt(x);
+    return fma(c, -1.850371707708594e-17 * (double)logf((float)x), c);
+}
+
 __device__ __forceinline__ double cloud_sigma(const ConfigK &c, double eloss)
 {
+    if (eloss == 0.0) return c.sigma0;   // misses deposit nothing; also keeps 0/x off the division slow path
     double ev = eloss * 1e6;
     double q = c.qe * ev / 3.6;
     double carg = c.c3mu * q * c.t90 / c.cden;
-    double coul = 0.2 * pow(carg, 1.0 / 3.0);
+    double coul = 0.2 * pow_one_third(carg);
     return sqrt(c.diff2 + coul * coul) * 1e6;
 }
 

@@ -123,7 +123,7 @@ __device__ __forceinline__ unsigned lanemask_lt()
 }
 
 template <class Src>
-__global__ void __launch_bounds__(BLOCK) k_simulate(const __grid_constant__ ConfigK cfg,
+__global__ void __launch_bounds__(BLOCK, 5) k_simulate(const __grid_constant__ ConfigK cfg,
                                                     const __grid_constant__ KParams P, const Src src)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(BLOCK) k_simulate(const __grid_constant__ Conf
                 ++n_inside;
                 const double inx = profile_norm(profile_radius(rx));
                 const double iny = profile_norm(profile_radius(ry));
-                const double q = eloss * 1e6 / 3.6;
+                const double q = eloss == 0.0 ? 0.0 : eloss * 1e6 / 3.6;
                 const double noise = 0.0 + pl.noise_sigma * zseed;
                 // seed pixel: both profile factors are exp(-0) = 1; no pixel-area factor (Q9)
                 const double seedq = (q * (inx * iny) + noise) * 1e-3;
@@ -803,6 +803,7 @@ int ptb_create(const PtbBeam *beam, const PtbDevice *dev, int32_t n_dev, const P
         c.c3mu = 3 * mu;
         c.t90 = t;
         c.cden = 4 * M_PI * eps0 * epsr;
+        c.sigma0 = sqrt(c.diff2 + 0.0) * 1e6;
     }
     double mean_prev = 0.0;   // mean loss in the previous plane; the reference indexes row -1 (all zero) for plane 0
     for (int d = 0; d < n_dev; ++d) {
@@ -841,6 +842,7 @@ int ptb_create(const PtbBeam *beam, const PtbDevice *dev, int32_t n_dev, const P
             p.lan_ulo = moyal_cdf(lo);
             p.lan_uspan = moyal_cdf(hi) - p.lan_ulo;
             if (!(p.lan_uspan > 0)) return fail(h, PTB_E_INVALID, "Landau window [0,0.5] MeV carries no probability");
+            p.lan_direct = (p.lan_uspan > 0.999) ? 1 : 0;
             // mean of the truncated law by Simpson's rule, feeds beta of the next plane (main/hit.py:91)
             const int M = 20000;
             double    num = 0, den = 0, hstep = 0.5 / M;
