@@ -37,6 +37,13 @@ def flops_per_particle(tot: dict, n: int, D: int) -> float:
     return (9 * P + 38 * S + 7 * D * P + 58 * G + 24 * A + 55 * X + 8 * V) / n
 
 
+def digitise_flops_per_particle(tot: dict, n: int) -> float:
+    """The terms of the SURVEY 8(d) count that belong to the digitisation kernel: 58 per digitised pair, 24 per
+    in-acceptance pair, 55 per pixel evaluation, 8 per normal drawn there (3 per pair + 1 per pixel)."""
+    G, A, X = tot["pairs"], tot["inside"], tot["pixels"]
+    return (58 * G + 24 * A + 55 * X + 8 * (3 * G + X)) / n
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -215,9 +222,10 @@ def run_gpu(args):
     sync_all()
     ms = e0.elapsed_time(e1)
     launches = lib.ptb_launch_count() - launches0
-    sim_ms, sim_launches = sim.timing_read()
+    trk_ms, dig_ms, sim_launches = sim.timing_read()
     sim.timing(False)
-    launch_ms = sim_ms / max(sim_launches, 1)
+    launch_ms = dig_ms / max(sim_launches, 1)        # dominant kernel: k_digitise
+    tracks_launch_ms = trk_ms / max(sim_launches, 1)
     clocks = sampler.stop() if rank == 0 else None
     tot = pipe.totals(0)
     if tot["error"]:
@@ -249,7 +257,8 @@ def run_gpu(args):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        F = flops_per_particle(tot, chunk, D)
+        F_all = flops_per_particle(tot, chunk, D)
+        F = digitise_flops_per_particle(tot, chunk)    # the share of SURVEY 8(d)'s count that k_digitise executes
         alg_bytes = 18.0 * sum(tot["hits"])            # 18 B per hit row, nothing read
         traffic = None
         try:
@@ -260,10 +269,11 @@ def run_gpu(args):
             pass
         ach_tf = F * chunk / (launch_ms * 1e-3) / 1e12
         ach_gb = alg_bytes / (launch_ms * 1e-3) / 1e9
-        roof = {"bound": "fp64", "kernel": "k_simulate<PhiloxSource>", "achieved": ach_tf, "peak": fp64_peak / 1e12,
+        roof = {"bound": "fp64", "kernel": "k_digitise<PhiloxSource>", "achieved": ach_tf, "peak": fp64_peak / 1e12,
                 "unit": "TFLOP/s", "frac": ach_tf / (fp64_peak / 1e12) if fp64_peak > 0 else None,
                 "peak_source": "in-job DFMA probe (ptb_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
-                "flops_per_electron": F, "launch_ms": launch_ms, "launches_timed": sim_launches,
+                "flops_per_electron": F, "flops_per_electron_whole_path": F_all, "launch_ms": launch_ms,
+                "k_tracks_launch_ms": tracks_launch_ms, "launches_timed": sim_launches,
                 "share_of_step": launch_ms / (ms / K), "traffic": traffic,
                 "hbm": {"achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
                         "bytes_per_electron": alg_bytes / chunk, "peak_source": hbm_src}}

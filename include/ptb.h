@@ -164,12 +164,12 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream);
 int ptb_pack_hits(const PtbHitSlab *slab, uint64_t n, void *out_dev, void *stream);
 
 /*
- * Optional per-kernel timing: while enabled, every ptb_simulate brackets its k_simulate launch with CUDA events
- * on the caller's stream.  ptb_timing_read waits for the recorded events, returns the summed k_simulate time
- * in milliseconds and the number of launches, and clears the record.
+ * Optional per-kernel timing: while enabled, every ptb_simulate brackets its k_tracks and k_digitise launches
+ * with CUDA events on the caller's stream.  ptb_timing_read waits for the recorded events, returns the summed
+ * duration of each kernel in milliseconds and the number of ptb_simulate calls covered, and clears the record.
  */
 int ptb_timing_enable(PtbHandle h, int32_t on);
-int ptb_timing_read(PtbHandle h, double *simulate_ms, uint64_t *launches);
+int ptb_timing_read(PtbHandle h, double *tracks_ms, double *digitise_ms, uint64_t *calls);
 
 /* number of kernels this library has launched on the calling process since load (bench bookkeeping) */
 uint64_t ptb_launch_count(void);

@@ -1,14 +1,17 @@
 // libptb_b200 -- kernels and C ABI (include/ptb.h).
 //
-// One call of ptb_simulate runs three kernels on the caller's stream:
+// One call of ptb_simulate runs four kernels on the caller's stream:
 //
-//   k_simulate  one warp per group of 32 consecutive particles, one lane per particle for the track part
-//               (beam draw, plane-by-plane propagation, Highland kick, Landau loss, acceptance test);
-//               the cluster digitisation is warp-cooperative: the 32 particles' pixel boxes are flattened
-//               into one work list that the lanes walk 32 items at a time, and hits are compacted in
-//               reference order (particle, column, row) with warp ballots into a shared-memory stage.
-//               After every plane the group reserves room in that plane's scratch slab with one atomic
-//               and flushes the stage with coalesced stores.  Nothing else touches HBM.
+//   k_tracks    one lane per particle, one warp per group of 32 consecutive particles: beam draw, plane-by-
+//               plane propagation, Highland kick, Landau loss, acceptance test.  Hands the per-plane
+//               (x, y, energy loss) of the group to k_digitise through a coalesced, L2-resident park.
+//   k_digitise  one warp per group, warp-cooperative: the 32 particles' pixel boxes are flattened into work
+//               lists that the lanes walk 32 items at a time (first the separable per-column / per-row
+//               profiles, then four pixels per lane), and hits are compacted in reference order (particle,
+//               column, row) with warp scans into a shared-memory stage.  After every plane the group
+//               reserves room in that plane's scratch slab with one atomic and flushes the stage with
+//               coalesced stores.  (Two kernels rather than one: fused, the code no longer fits the
+//               instruction cache and ran 26 % slower -- profiles/.)
 //   k_scan      exclusive prefix over the per-group counters (hits per plane, accepted events, time).
 //   k_gather    copies each group's scratch segment to its final, particle-ordered position in the
 //               structure-of-arrays hit slab and stamps the event numbers.
@@ -26,8 +29,10 @@
 
 namespace ptb {
 
-constexpr int      WARPS_PER_BLOCK = 4;
+constexpr int      WARPS_PER_BLOCK = 4;                 // k_digitise
 constexpr int      BLOCK = 32 * WARPS_PER_BLOCK;
+constexpr int      DIGI_MIN_BLOCKS = 7;
+constexpr int      TRACK_BLOCK = 128;                   // k_tracks
 constexpr unsigned FULL = 0xffffffffu;
 
 static unsigned long long g_launches = 0;
@@ -40,6 +45,8 @@ struct Workspace {
     unsigned long long *table;      // [(2D+5)][n_groups]: hits[D], accepted, tsum, pairs, inside, pixels, base[D]
     unsigned long long *prefix;     // [(D+2)][n_groups]
     PtbBases           *bases_used; // copy of bases_in taken by k_scan before bases_out is written
+    double             *park;       // [n_groups][D][3][32] digitisation inputs handed from k_tracks to k_digitise
+    unsigned           *accmask;    // [n_groups] trigger ballot of every group
     uint32_t           *s_cr[PTB_MAX_PLANES];
     float              *s_q[PTB_MAX_PLANES];
     uint8_t            *s_ev[PTB_MAX_PLANES];
@@ -76,6 +83,10 @@ static size_t carve_workspace(int D, unsigned long long n, const unsigned long l
     if (ws) ws->prefix = (unsigned long long *)p;
     p = take(sizeof(PtbBases));
     if (ws) ws->bases_used = (PtbBases *)p;
+    p = take((flags & PTB_DIGITISE) ? sizeof(double) * 96 * (size_t)D * ng : 0);
+    if (ws) ws->park = (double *)p;
+    p = take(sizeof(unsigned) * ng);
+    if (ws) ws->accmask = (unsigned *)p;
     for (int d = 0; d < D; ++d) {
         unsigned long long c = (flags & PTB_DIGITISE) ? cap[d] : 0;
         p = take(4 * (size_t)c);
@@ -91,9 +102,6 @@ static size_t carve_workspace(int D, unsigned long long n, const unsigned long l
     return off;
 }
 
-// ---------------------------------------------------------------------------------------------------
-// k_simulate
-// ---------------------------------------------------------------------------------------------------
 
 // shared memory of one warp: the per-particle cluster descriptors and the hit stage
 struct WarpShared {
@@ -122,33 +130,24 @@ __device__ __forceinline__ unsigned lanemask_lt()
     return m;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// k_tracks: one lane per particle, one warp per group of 32 consecutive particles.  Event draws (trigger
+// mask, Poisson gap), the source state and the plane-by-plane propagation (main/hit.py:70-80, 104, 209-239).
+// Leaves behind, per group: the digitisation inputs (x, y, energy loss) of every plane in the workspace
+// ("park", [D][3][32] doubles, coalesced), the trigger ballot, and the group's accepted / time counters.
+// ---------------------------------------------------------------------------------------------------
 template <class Src>
-__global__ void __launch_bounds__(BLOCK, 5) k_simulate(const __grid_constant__ ConfigK cfg,
-                                                    const __grid_constant__ KParams P, const Src src)
+__global__ void __launch_bounds__(TRACK_BLOCK) k_tracks(const __grid_constant__ ConfigK cfg,
+                                                       const __grid_constant__ KParams P, const Src src)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int                lane = threadIdx.x & 31;
-    const int                wib = threadIdx.x >> 5;
-    const unsigned long long group = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + wib;
-    if (group >= P.n_groups) return;  // whole warps leave; no block-wide barrier is used anywhere below
+    const unsigned long long group = (unsigned long long)blockIdx.x * (TRACK_BLOCK / 32) + (threadIdx.x >> 5);
+    if (group >= P.n_groups) return;
 
-    const int    D = cfg.n_planes;
-    const int    S = cfg.stage_hits;
-    const int    PC = cfg.pool_entries;
-    const bool   keep64 = (P.flags & PTB_KEEP_CHARGE64) != 0;
-    const bool   digitise = (P.flags & PTB_DIGITISE) != 0;
-    const bool   from_table = (P.flags & PTB_TRACKS_FROM_TABLE) != 0;
-    const bool   write_tracks = (P.flags & PTB_WRITE_TRACKS) != 0;
-    const size_t wbytes = warp_shared_bytes(S, PC, keep64);
-
-    unsigned char *wbase = smem_raw + wbytes * wib;
-    WarpShared    &W = *reinterpret_cast<WarpShared *>(wbase);
-    double        *pool_g = reinterpret_cast<double *>(wbase + sizeof(WarpShared));
-    double        *pool_e = pool_g + PC;
-    uint32_t      *st_cr = reinterpret_cast<uint32_t *>(pool_e + PC);
-    float         *st_q = reinterpret_cast<float *>(st_cr + S);
-    double        *st_q64 = reinterpret_cast<double *>(st_q + S);
-    uint8_t       *st_ev = reinterpret_cast<uint8_t *>(st_q + S) + (keep64 ? (size_t)S * 8 : 0);
+    const int  D = cfg.n_planes;
+    const bool digitise = (P.flags & PTB_DIGITISE) != 0;
+    const bool write_tracks = (P.flags & PTB_WRITE_TRACKS) != 0;
+    double    *park = P.ws.park + group * (unsigned long long)(D * 96) + lane;
 
     const unsigned long long kl = group * 32 + lane;  // index inside this call's range
     const bool               valid = kl < P.n;
@@ -158,58 +157,43 @@ __global__ void __launch_bounds__(BLOCK, 5) k_simulate(const __grid_constant__ C
     bool    acc = false;
     int64_t gap = 0;
     if (valid) {
-        if (from_table) {
-            acc = P.trk.accepted[kl] != 0;
-        } else {
-            acc = src.accepted(cfg, k);
-            gap = src.gap(cfg, k);
-        }
+        acc = src.accepted(cfg, k);
+        gap = src.gap(cfg, k);
     }
     const unsigned accmask = __ballot_sync(FULL, acc);
-    const int      evoff = __popc(accmask & lanemask_lt());  // accepted particles of this group before me
     int64_t        t_rel = gap;                              // inclusive scan: time relative to the group start
 #pragma unroll
     for (int s = 1; s < 32; s <<= 1) {
         int64_t o = __shfl_up_sync(FULL, t_rel, s);
         if (lane >= s) t_rel += o;
     }
-    W.evoff[lane] = (uint8_t)evoff;
 
     // ---- source state (main/hit.py:70-80, 104, 234-238) ----------------------------------------------
-    double E = 0, ax = 0, ay = 0, x = 0, y = 0, e0_self = 0;
-    if (!from_table) {
-        double e0_prev = 0;
-        if (valid) e0_self = src.eloss_only(cfg, k, 0);
-        e0_prev = __shfl_up_sync(FULL, e0_self, 1);
-        if (valid) {
-            if (k == 0)
-                e0_prev = e0_self;                      // event 0 starts from its own plane-0 loss
-            else if (lane == 0)
-                e0_prev = src.eloss_only(cfg, k - 1, 0);     // neighbour group: recomputed / injected look-back
-            double z[4];
-            src.start(k, z);
-            const bool first_event = (k == 0);
-            ax = cfg.angle_x + (first_event ? cfg.theta0_first : cfg.disp_x) * z[0];
-            ay = cfg.angle_y + (first_event ? cfg.theta0_first : cfg.disp_y) * z[1];
-            x = cfg.loc_x + cfg.sigma_x * z[2];
-            y = cfg.loc_y + cfg.sigma_y * z[3];
-            E = cfg.energy - e0_prev;
-        }
+    double E = 0, ax = 0, ay = 0, x = 0, y = 0, e0_self = 0, e0_prev = 0;
+    if (valid) e0_self = src.eloss_only(cfg, k, 0);
+    e0_prev = __shfl_up_sync(FULL, e0_self, 1);
+    if (valid) {
+        if (k == 0)
+            e0_prev = e0_self;                           // event 0 starts from its own plane-0 loss
+        else if (lane == 0)
+            e0_prev = src.eloss_only(cfg, k - 1, 0);     // neighbour group: recomputed / injected look-back
+        double z[4];
+        src.start(k, z);
+        const bool first_event = (k == 0);
+        ax = cfg.angle_x + (first_event ? cfg.theta0_first : cfg.disp_x) * z[0];
+        ay = cfg.angle_y + (first_event ? cfg.theta0_first : cfg.disp_y) * z[1];
+        x = cfg.loc_x + cfg.sigma_x * z[2];
+        y = cfg.loc_y + cfg.sigma_y * z[3];
+        E = cfg.energy - e0_prev;
     }
 
-    unsigned long long n_pairs = 0, n_inside = 0, n_pixels = 0;
-    unsigned           err = 0;
-
+    // ---- the track through all planes (main/hit.py:211-231)
+#pragma unroll 1
     for (int d = 0; d < D; ++d) {
         const PlaneK &pl = cfg.pl[d];
         double        eloss = 0;
-        // ---- track step (main/hit.py:211-231) ------------------------------------------------------
         if (valid) {
-            if (from_table) {
-                x = P.trk.x[kl * D + d];
-                y = P.trk.y[kl * D + d];
-                eloss = P.trk.eloss[(unsigned long long)d * P.n + kl];
-            } else if (d == 0) {
+            if (d == 0) {
                 eloss = e0_self;   // plane 0 is the start point: never propagated to, never bounds-checked (Q2)
             } else {
                 x = x + tan(ax) * pl.z;   // absolute z of the target plane (Q1)
@@ -241,7 +225,90 @@ __global__ void __launch_bounds__(BLOCK, 5) k_simulate(const __grid_constant__ C
                 if (d == 0) P.trk.accepted[kl] = acc ? 1 : 0;
             }
         }
-        if (!digitise) continue;
+        if (digitise) {
+            park[d * 96] = x;
+            park[d * 96 + 32] = y;
+            park[d * 96 + 64] = eloss;
+        }
+    }
+
+
+    const int64_t tsum = __shfl_sync(FULL, t_rel, 31);
+    if (lane == 0) {
+        unsigned long long *t = P.ws.table + group;
+        t[(unsigned long long)(D + 0) * P.n_groups] = (unsigned long long)__popc(accmask);
+        t[(unsigned long long)(D + 1) * P.n_groups] = (unsigned long long)tsum;
+        P.ws.accmask[group] = accmask;
+        if (!digitise) {
+            for (int d = 0; d < D; ++d) t[(unsigned long long)d * P.n_groups] = 0;
+            for (int c = D + 2; c < D + 5; ++c) t[(unsigned long long)c * P.n_groups] = 0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_digitise: one warp per group of 32 particles, plane by plane (main/device.py:132-168).  Inputs come from
+// k_tracks' park or, with PTB_TRACKS_FROM_TABLE, from the caller's hit_tables arrays exactly as
+// main/device.py:132-138 reads them.
+// ---------------------------------------------------------------------------------------------------
+template <class Src>
+__global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __grid_constant__ ConfigK cfg,
+                                                                    const __grid_constant__ KParams P, const Src src)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int                lane = threadIdx.x & 31;
+    const int                wib = threadIdx.x >> 5;
+    const unsigned long long group = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + wib;
+    if (group >= P.n_groups) return;  // whole warps leave; no block-wide barrier is used anywhere below
+
+    const int    D = cfg.n_planes;
+    const int    S = cfg.stage_hits;
+    const int    PC = cfg.pool_entries;
+    const bool   keep64 = (P.flags & PTB_KEEP_CHARGE64) != 0;
+    const bool   from_table = (P.flags & PTB_TRACKS_FROM_TABLE) != 0;
+    const size_t wbytes = warp_shared_bytes(S, PC, keep64);
+
+    unsigned char *wbase = smem_raw + wbytes * wib;
+    WarpShared    &W = *reinterpret_cast<WarpShared *>(wbase);
+    double        *pool_g = reinterpret_cast<double *>(wbase + sizeof(WarpShared));
+    double        *pool_e = pool_g + PC;
+    uint32_t      *st_cr = reinterpret_cast<uint32_t *>(pool_e + PC);
+    float         *st_q = reinterpret_cast<float *>(st_cr + S);
+    double        *st_q64 = reinterpret_cast<double *>(st_q + S);
+    uint8_t       *st_ev = reinterpret_cast<uint8_t *>(st_q + S) + (keep64 ? (size_t)S * 8 : 0);
+    const double  *park = P.ws.park + group * (unsigned long long)(D * 96) + lane;
+
+    const unsigned long long kl = group * 32 + lane;  // index inside this call's range
+    const bool               valid = kl < P.n;
+    const unsigned long long k = P.first + kl;        // global particle id
+
+    // trigger mask of the group: from k_tracks, or from the caller's table
+    unsigned accmask;
+    if (from_table)
+        accmask = __ballot_sync(FULL, valid && P.trk.accepted[kl] != 0);
+    else
+        accmask = P.ws.accmask[group];
+    const bool acc = (accmask >> lane) & 1u;
+    W.evoff[lane] = (uint8_t)__popc(accmask & lanemask_lt());   // accepted particles of this group before me
+
+    unsigned long long n_pairs = 0, n_inside = 0, n_pixels = 0;
+    unsigned           err = 0;
+
+#pragma unroll 1
+    for (int d = 0; d < D; ++d) {
+        const PlaneK &pl = cfg.pl[d];
+        double        x = 0, y = 0, eloss = 0;
+        if (from_table) {
+            if (valid) {
+                x = P.trk.x[kl * D + d];
+                y = P.trk.y[kl * D + d];
+                eloss = P.trk.eloss[(unsigned long long)d * P.n + kl];
+            }
+        } else {
+            x = park[d * 96];
+            y = park[d * 96 + 32];
+            eloss = park[d * 96 + 64];
+        }
 
         // ---- cluster descriptors, one lane per particle (main/device.py:137-140, 241-266) -----------
         int cnt = 0, nprof = 0;
@@ -466,6 +533,7 @@ __global__ void __launch_bounds__(BLOCK, 5) k_simulate(const __grid_constant__ C
         __syncwarp();
     }
 
+
     // ---- per-group counters for k_scan ---------------------------------------------------------------
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) {
@@ -474,13 +542,12 @@ __global__ void __launch_bounds__(BLOCK, 5) k_simulate(const __grid_constant__ C
         n_pixels += __shfl_xor_sync(FULL, n_pixels, s);
         err |= __shfl_xor_sync(FULL, err, s);
     }
-    const int64_t tsum = __shfl_sync(FULL, t_rel, 31);
     if (lane == 0) {
         unsigned long long *t = P.ws.table + group;
-        if (!digitise)
-            for (int d = 0; d < D; ++d) t[(unsigned long long)d * P.n_groups] = 0;
-        t[(unsigned long long)(D + 0) * P.n_groups] = (unsigned long long)__popc(accmask);
-        t[(unsigned long long)(D + 1) * P.n_groups] = (unsigned long long)tsum;
+        if (from_table) {
+            t[(unsigned long long)(D + 0) * P.n_groups] = (unsigned long long)__popc(accmask);
+            t[(unsigned long long)(D + 1) * P.n_groups] = 0;
+        }
         t[(unsigned long long)(D + 2) * P.n_groups] = n_pairs;
         t[(unsigned long long)(D + 3) * P.n_groups] = n_inside;
         t[(unsigned long long)(D + 4) * P.n_groups] = n_pixels;
@@ -716,7 +783,7 @@ struct PtbContext {
     int     fast_math;
     int     sm_count;
     int     timing;
-    std::vector<cudaEvent_t> ev;   // (start, stop) pairs of k_simulate launches, when timing is enabled
+    std::vector<cudaEvent_t> ev;   // (start, after k_tracks, after k_digitise) per ptb_simulate, when timing is enabled
     size_t  ev_used;
     char    err[512];
 };
@@ -768,9 +835,9 @@ int ptb_create(const PtbBeam *beam, const PtbDevice *dev, int32_t n_dev, const P
 
     ConfigK &c = h->cfg;
     c.n_planes = n_dev;
-    c.stage_hits = (opt && opt->stage_hits > 0) ? opt->stage_hits : 256;
+    c.stage_hits = (opt && opt->stage_hits > 0) ? opt->stage_hits : 128;
     c.stage_hits = (c.stage_hits + 3) / 4 * 4;
-    c.pool_entries = (opt && opt->pool_entries > 0) ? opt->pool_entries : 256;
+    c.pool_entries = (opt && opt->pool_entries > 0) ? opt->pool_entries : 192;
     c.pool_entries = (c.pool_entries + 1) / 2 * 2;
     h->fast_math = opt ? opt->fast_math : 0;
     c.energy = beam->energy;
@@ -879,37 +946,40 @@ int ptb_timing_enable(PtbHandle h, int32_t on)
     return PTB_OK;
 }
 
-int ptb_timing_read(PtbHandle h, double *simulate_ms, uint64_t *launches)
+int ptb_timing_read(PtbHandle h, double *tracks_ms, double *digitise_ms, uint64_t *calls)
 {
-    if (!h || !simulate_ms || !launches) return PTB_E_INVALID;
-    double sum = 0;
-    for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
-        cudaError_t e = cudaEventSynchronize(h->ev[i + 1]);
+    if (!h || !tracks_ms || !digitise_ms || !calls) return PTB_E_INVALID;
+    double st = 0, sd = 0;
+    for (size_t i = 0; i + 2 < h->ev_used; i += 3) {
+        cudaError_t e = cudaEventSynchronize(h->ev[i + 2]);
         if (e != cudaSuccess) return fail_cuda(h, e, "cudaEventSynchronize");
-        float ms = 0;
-        e = cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]);
+        float a = 0, b = 0;
+        e = cudaEventElapsedTime(&a, h->ev[i], h->ev[i + 1]);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&b, h->ev[i + 1], h->ev[i + 2]);
         if (e != cudaSuccess) return fail_cuda(h, e, "cudaEventElapsedTime");
-        sum += ms;
+        st += a;
+        sd += b;
     }
-    *simulate_ms = sum;
-    *launches = h->ev_used / 2;
+    *tracks_ms = st;
+    *digitise_ms = sd;
+    *calls = h->ev_used / 3;
     h->ev_used = 0;
     return PTB_OK;
 }
 
-// next (start, stop) event pair of the timing record, or nullptr when timing is off
+// next (start, mid, stop) event triple of the timing record, or nullptr when timing is off
 static cudaEvent_t *timing_pair(PtbHandle h)
 {
     if (!h->timing) return nullptr;
-    if (h->ev_used + 2 > h->ev.size()) {
-        for (int i = 0; i < 2; ++i) {
+    if (h->ev_used + 3 > h->ev.size()) {
+        for (int i = 0; i < 3; ++i) {
             cudaEvent_t e;
             if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
             h->ev.push_back(e);
         }
     }
     cudaEvent_t *p = &h->ev[h->ev_used];
-    h->ev_used += 2;
+    h->ev_used += 3;
     return p;
 }
 
@@ -1006,29 +1076,40 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
 
     const bool   keep64 = (flags & PTB_KEEP_CHARGE64) != 0;
     const size_t smem = warp_shared_bytes(c.stage_hits, c.pool_entries, keep64) * WARPS_PER_BLOCK;
-    const unsigned blocks = (unsigned)((P.n_groups + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-    if (smem > 227 * 1024) return fail(h, PTB_E_INVALID, "stage_hits too large for shared memory");
+    if (smem > 227 * 1024) return fail(h, PTB_E_INVALID, "stage_hits / pool_entries too large for shared memory");
     cudaEvent_t *tp = timing_pair(h);
     if (tp) cudaEventRecord(tp[0], st);
-    if (run->injected) {
-        InjectedSource src{*run->injected, run->first, run->n};
-        auto           kern = k_simulate<InjectedSource>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail_cuda(h, e, "cudaFuncSetAttribute");
-        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        kern<<<blocks, BLOCK, smem, st>>>(c, P, src);
-    } else {
-        PhiloxSource src{run->seed};
-        auto         kern = k_simulate<PhiloxSource>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail_cuda(h, e, "cudaFuncSetAttribute");
-        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        kern<<<blocks, BLOCK, smem, st>>>(c, P, src);
+    if (!(flags & PTB_TRACKS_FROM_TABLE)) {
+        const unsigned tb = (unsigned)((P.n_groups + TRACK_BLOCK / 32 - 1) / (TRACK_BLOCK / 32));
+        if (run->injected)
+            k_tracks<InjectedSource><<<tb, TRACK_BLOCK, 0, st>>>(c, P, InjectedSource{*run->injected, run->first, run->n});
+        else
+            k_tracks<PhiloxSource><<<tb, TRACK_BLOCK, 0, st>>>(c, P, PhiloxSource{run->seed});
+        ++g_launches;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return fail_cuda(h, e, "k_tracks launch");
     }
-    ++g_launches;
     if (tp) cudaEventRecord(tp[1], st);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return fail_cuda(h, e, "k_simulate launch");
+    if (flags & PTB_DIGITISE) {
+        const unsigned blocks = (unsigned)((P.n_groups + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+        if (run->injected) {
+            auto kern = k_digitise<InjectedSource>;
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return fail_cuda(h, e, "cudaFuncSetAttribute");
+            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            kern<<<blocks, BLOCK, smem, st>>>(c, P, InjectedSource{*run->injected, run->first, run->n});
+        } else {
+            auto kern = k_digitise<PhiloxSource>;
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return fail_cuda(h, e, "cudaFuncSetAttribute");
+            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            kern<<<blocks, BLOCK, smem, st>>>(c, P, PhiloxSource{run->seed});
+        }
+        ++g_launches;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return fail_cuda(h, e, "k_digitise launch");
+    }
+    if (tp) cudaEventRecord(tp[2], st);
 
     k_scan<<<D + 5, SCAN_THREADS, 0, st>>>(D, P.n_groups, flags, P.ws, run->bases_in, run->bases_out, run->totals);
     ++g_launches;

@@ -97,14 +97,14 @@ class Simulator:
     """One telescope set-up on one GPU."""
 
     def __init__(self, beam: dict, devices: list, materials: list, device=None, stage_hits: int = 0,
-                 fast_math: bool = False):
+                 pool_entries: int = 0, fast_math: bool = False):
         if not torch.cuda.is_available():
             raise PtbError("pytestbeam_b200 needs a CUDA device (sm_100a); there is no CPU path")
         self.lib = N.load()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.beam, self.devices, self.materials = dict(beam), list(devices), list(materials)
         self.D = len(devices)
-        self._opts = dict(stage_hits=int(stage_hits), fast_math=int(bool(fast_math)))
+        self._opts = dict(stage_hits=int(stage_hits), pool_entries=int(pool_entries), fast_math=int(bool(fast_math)))
         self._h = None
         self._create()
         self._hits_per_particle = None
@@ -113,7 +113,7 @@ class Simulator:
     def _create(self):
         self.close()
         h = C.c_void_p()
-        opt = N.PtbOptions(self._opts["stage_hits"], 0, self._opts["fast_math"], 0, 0.0)
+        opt = N.PtbOptions(self._opts["stage_hits"], self._opts["pool_entries"], self._opts["fast_math"], 0, 0.0)
         with torch.cuda.device(self.device):
             rc = self.lib.ptb_create(C.byref(N.pack_beam(self.beam)), N.pack_devices(self.devices, self.materials),
                                      self.D, C.byref(opt), C.byref(h))
@@ -264,14 +264,14 @@ class Simulator:
         raise PtbError("ptb_simulate kept overflowing its buffers")
 
     def timing(self, on: bool):
-        """Bracket every k_simulate launch with CUDA events on its stream (read back with timing_read)."""
+        """Bracket the k_tracks / k_digitise launches with CUDA events on their stream (see timing_read)."""
         self._check(self.lib.ptb_timing_enable(self._h, int(on)), "ptb_timing_enable")
 
     def timing_read(self):
-        """(summed k_simulate milliseconds, launches) since the last read; waits for the recorded events."""
-        ms, n = C.c_double(), C.c_uint64()
-        self._check(self.lib.ptb_timing_read(self._h, C.byref(ms), C.byref(n)), "ptb_timing_read")
-        return float(ms.value), int(n.value)
+        """(k_tracks ms, k_digitise ms, calls) summed since the last read; waits for the recorded events."""
+        a, b, n = C.c_double(), C.c_double(), C.c_uint64()
+        self._check(self.lib.ptb_timing_read(self._h, C.byref(a), C.byref(b), C.byref(n)), "ptb_timing_read")
+        return float(a.value), float(b.value), int(n.value)
 
     # -- helpers -------------------------------------------------------------------------------------
     def prefix(self, first, n, *, seed=0, injected: Injected | None = None):

@@ -21,7 +21,7 @@ PTB_DEV_SLAB_OVERFLOW = 2
 PTB_DEV_BOX_TOO_LARGE = 4
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libptb_b200.so")
+LIB_PATH = os.environ.get("PTB_LIB_PATH") or os.path.join(_HERE, "_lib", "libptb_b200.so")   # env: developer builds
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int64)
@@ -115,7 +115,7 @@ def load() -> C.CDLL:
     L.ptb_pack_hits.restype = C.c_int
     L.ptb_timing_enable.argtypes = [C.c_void_p, C.c_int32]
     L.ptb_timing_enable.restype = C.c_int
-    L.ptb_timing_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    L.ptb_timing_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.ptb_timing_read.restype = C.c_int
     L.ptb_launch_count.argtypes = []
     L.ptb_launch_count.restype = C.c_uint64

@@ -7,10 +7,11 @@ from pytestbeam_b200.engine import Simulator, _TOTALS_WORDS
 
 name = sys.argv[1] if len(sys.argv) > 1 else "c1"
 beam, devices, materials, names = cfg.flatten(getattr(cfg, name)(1000))
-sim = Simulator(beam, devices, materials)
+sim = Simulator(beam, devices, materials, stage_hits=int(os.environ.get("PTB_STAGE", 0)),
+                pool_entries=int(os.environ.get("PTB_POOL", 0)))
 hpp = sim.hits_per_particle()
 print("hits/particle", hpp.round(4), "total", hpp.sum().round(3), "stage", sim.stage_hits)
-for n in [1 << 20, 1 << 22, 10_000_000]:
+for n in [int(v) for v in os.environ.get("PTB_NS", "1048576,4194304,10000000").split(",")]:
     caps = sim.default_capacities(n)
     flags = N.PTB_DIGITISE | N.PTB_RECYCLE_SLABS
     slabs = sim.alloc_slabs(caps)
