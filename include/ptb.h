@@ -99,7 +99,8 @@ typedef struct PtbTrackTable {
     double  *energy, *angle_x, *angle_y, *x, *y, *z; /* [n*D] */
     int64_t *time_stamp;                              /* [n*D] */
     double  *eloss;                                   /* [D][n] after the acceptance zeroing */
-    uint8_t *accepted;                                /* [n] trigger mask (input with PTB_TRACKS_FROM_TABLE) */
+    uint8_t *accepted;                                /* [n] trigger mask; with PTB_TRACKS_FROM_TABLE an optional input
+                                                         (NULL = draw it from the variate source, main/device.py:56) */
 } PtbTrackTable;
 
 /* hit table of one plane as structure of arrays; rows in particle order, then column-major in the cluster */

@@ -98,14 +98,16 @@ __device__ __forceinline__ double u53_open(uint32_t a, uint32_t b)
     return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6) + 0.5) * (1.0 / 9007199254740992.0);
 }
 
-// Box-Muller pair in fp32 arithmetic, returned as doubles (sites that tolerate 24-bit normals)
+// Box-Muller pair in fp32 arithmetic, returned as doubles (sites that tolerate 24-bit normals: scattering
+// kicks, cluster radii, pixel noise).  Special-function-unit approximations throughout: lg2 / sin / cos are
+// good to ~2^-21 absolute on these ranges, far below what any of the consumers resolves.
 __device__ __forceinline__ void normal_pair_f32(uint32_t a, uint32_t b, double &n0, double &n1)
 {
     float u = fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // (0,1]
-    float v = fmaf((float)b, 4.6566128730773926e-10f, 2.3283064365386963e-10f);   // (0,2]
-    float r = sqrtf(-2.0f * logf(u));
+    float v = fmaf((float)b, 1.4629180792671596e-09f, 7.3145903963357980e-10f);   // (0,2pi]
+    float r = __fsqrt_rn(-1.3862943611198906f * __log2f(u));                       // sqrt(-2 ln u)
     float s, c;
-    sincospif(v, &s, &c);
+    __sincosf(v, &s, &c);
     n0 = (double)(r * c);
     n1 = (double)(r * s);
 }
@@ -191,9 +193,9 @@ struct PhiloxSource {
         if (p.lan_direct) {
             double z0, z1;
             normal_pair_f32(a, b, z0, z1);
-            double e = p.lan_loc + p.lan_scale * (double)(-2.0f * logf(fabsf((float)z0)));
+            double e = p.lan_loc + p.lan_scale * (double)(-1.3862943611198906f * __log2f(fabsf((float)z0)));
             if (e >= 0.0 && e <= 0.5) return e;
-            e = p.lan_loc + p.lan_scale * (double)(-2.0f * logf(fabsf((float)z1)));
+            e = p.lan_loc + p.lan_scale * (double)(-1.3862943611198906f * __log2f(fabsf((float)z1)));
             if (e >= 0.0 && e <= 0.5) return e;
             U4 w = philox_at(seed, k, SITE_PLANE + 4 * d + SUB_STEP, 1);
             a = w.x;

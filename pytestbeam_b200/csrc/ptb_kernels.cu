@@ -284,8 +284,8 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
 
     // trigger mask of the group: from k_tracks, or from the caller's table
     unsigned accmask;
-    if (from_table)
-        accmask = __ballot_sync(FULL, valid && P.trk.accepted[kl] != 0);
+    if (from_table)   // the caller's mask, or (when it passes none) the source's own trigger draw
+        accmask = __ballot_sync(FULL, valid && (P.trk.accepted ? P.trk.accepted[kl] != 0 : src.accepted(cfg, k)));
     else
         accmask = P.ws.accmask[group];
     const bool acc = (accmask >> lane) & 1u;
@@ -1001,7 +1001,7 @@ uint64_t ptb_launch_count(void) { return g_launches; }
 
 static bool injected_complete(const PtbInjected *v, uint32_t flags)
 {
-    if (flags & PTB_TRACKS_FROM_TABLE) return v->dig_z && v->dig_off;
+    if (flags & PTB_TRACKS_FROM_TABLE) return v->dig_z && v->dig_off;   /* accepted: table's, else v->accepted */
     bool ok = v->zstart && v->gap && v->zkick && v->eloss && v->accepted;
     if (flags & PTB_DIGITISE) ok = ok && v->dig_z && v->dig_off;
     return ok;
@@ -1041,12 +1041,14 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
         return fail(h, PTB_E_INVALID, "PTB_TRACKS_FROM_TABLE and PTB_WRITE_TRACKS are exclusive");
     if (flags & (PTB_TRACKS_FROM_TABLE | PTB_WRITE_TRACKS)) {
         const PtbTrackTable &t = run->tracks;
-        bool ok = t.x && t.y && t.eloss && t.accepted;
+        bool ok = t.x && t.y && t.eloss && (t.accepted || (flags & PTB_TRACKS_FROM_TABLE));
         if (flags & PTB_WRITE_TRACKS) ok = ok && t.energy && t.angle_x && t.angle_y && t.z && t.time_stamp;
         if (!ok) return fail(h, PTB_E_INVALID, "track table pointers missing");
     }
     if (run->injected && !injected_complete(run->injected, flags))
         return fail(h, PTB_E_INVALID, "injected variate tables incomplete for the requested flags");
+    if (run->injected && (flags & PTB_TRACKS_FROM_TABLE) && !run->tracks.accepted && !run->injected->accepted)
+        return fail(h, PTB_E_INVALID, "no trigger mask: neither the track table nor the injected tables carry one");
     unsigned long long cap[PTB_MAX_PLANES] = {0};
     if (flags & PTB_DIGITISE) {
         for (int d = 0; d < D; ++d) {
