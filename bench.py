@@ -156,7 +156,8 @@ def run_gpu(args):
     from pytestbeam_b200 import config as cfg
     from pytestbeam_b200 import native as N
     from pytestbeam_b200.engine import Simulator
-    from pytestbeam_b200.pipeline import ChunkPipeline, exclusive_prefix
+    from pytestbeam_b200.distributed import exchange_bases
+    from pytestbeam_b200.pipeline import ChunkPipeline
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -186,12 +187,8 @@ def run_gpu(args):
     def job(p, to_host):
         """The timed region: shard prefixes (N>1), then K chunks."""
         if world > 1:
-            acc, tsum = sim.prefix(first, n_rank, seed=seed)
-            mine = torch.tensor([acc, tsum], dtype=torch.int64, device=sim.device)
-            allv = [torch.zeros_like(mine) for _ in range(world)]
-            dist.all_gather(allv, mine)
-            base = exclusive_prefix(torch.stack(allv).cpu().numpy(), rank)
-            p.set_bases(int(base[0]), int(base[1]))
+            acc, tsum = sim.prefix(first, n_rank, seed=seed)          # this rank's own range only
+            p.set_bases(*exchange_bases(acc, tsum, device=sim.device))  # one all-gather of 2 int64 per rank
         else:
             p.set_bases(0, 0)
         if to_host:

@@ -1,0 +1,65 @@
+"""Host-side logic of the N>1 path on CPU: gloo, world_size 2 (shard ranges, prefix exchange, part-file merge)."""
+import os
+import socket
+
+import numpy as np
+import torch.multiprocessing as mp
+
+from pytestbeam_b200 import h5min
+from pytestbeam_b200.engine import HITS_DTYPE
+from pytestbeam_b200.pipeline import exclusive_prefix, shard_range
+
+
+def test_shard_ranges_tile_the_particles():
+    for n, w in [(10, 1), (10, 3), (1_000_000_007, 8), (5, 8)]:
+        pieces = [shard_range(n, r, w) for r in range(w)]
+        assert pieces[0][0] == 0 and sum(m for _, m in pieces) == n
+        for (a, m), (b, _) in zip(pieces[:-1], pieces[1:]):
+            assert a + m == b
+    vals = np.array([[3, 10], [4, 20], [5, 30]])
+    assert list(exclusive_prefix(vals, 0)) == [0, 0] and list(exclusive_prefix(vals, 2)) == [7, 30]
+
+
+def _worker(rank, size, port, folder, q):
+    import torch.distributed as dist
+    from pytestbeam_b200 import distributed as D
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    try:
+        # every rank "counted" accepted particles and a time sum for its own range
+        acc, tsum = 100 + rank, 1000 * (rank + 1)
+        ev, t = D.exchange_bases(acc, tsum)
+        rows = np.zeros(3 + rank, dtype=HITS_DTYPE)
+        rows["event_number"] = ev + 1 + np.arange(len(rows))
+        rows["column"], rows["row"], rows["charge"] = rank + 1, 7, 0.5
+        h5min.write_table(D.part_path(folder, "plane", rank), "Hits", rows)
+        dist.barrier()
+        if rank == 0:
+            D.merge_part_files(folder, ["plane"], size)
+        dist.barrier()
+        q.put((rank, ev, t))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_prefix_exchange_and_merge_world_size_2(tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    folder = str(tmp_path) + "/"
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, folder, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = dict((r, (ev, t)) for r, ev, t in (q.get(timeout=10) for _ in range(2)))
+    assert got[0] == (0, 0) and got[1] == (100, 1000)
+    merged = h5min.read_table(folder + "plane_dut.h5", "Hits")
+    assert len(merged) == 3 + 4
+    assert list(merged["column"]) == [1, 1, 1, 2, 2, 2, 2]                 # rank order = particle order
+    assert list(merged["event_number"]) == [1, 2, 3, 101, 102, 103, 104]
+    assert not os.path.exists(folder + "plane_dut.part000.h5")
