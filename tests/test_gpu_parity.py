@@ -159,3 +159,31 @@ def test_geometry_is_refused_like_the_oracle(torch_cuda):
     devices[0]["z_position"] = 5
     with pytest.raises(ValueError):
         Simulator(beam, devices, materials)
+
+
+def test_fine_pitch_planes_exercise_pool_rounds_and_stage_growth(torch_cuda):
+    """4 um pixels and a zero threshold: ~100 hits per particle on one plane.  The profile pool no longer holds a
+    whole group (it is served in rounds) and the shared-memory stage overflows until the host has grown it."""
+    from pytestbeam_b200 import config as cfg
+    from oracle import cpu_oracle as co
+    from pytestbeam_b200.engine import Simulator
+    n = 3000
+    setup = cfg.c1(n)
+    fine = setup["devices"]["mimosa26_p3"]
+    fine.update(column=5000, row=2500, column_pitch=4.0, row_pitch=4.0, threshold=0)
+    setup["devices"]["mimosa26_p5"].update(column=3000, row=3000, column_pitch=6.0, row_pitch=7.0, threshold=1)
+    beam, devices, materials, names = cfg.flatten(setup)
+    run = co.run(beam, devices, materials, n, 71, 72)
+    assert len(run.hits[2]) > 20 * n
+    sim = Simulator(beam, devices, materials)
+    first_stage = sim.stage_hits
+    res = sim.run(0, n, injected=H.injected_for(sim, run, 0, n), keep_charge64=True,
+                  capacities=[64 * n] * len(devices))
+    assert sim.stage_hits > first_stage                      # the overflow was reported and the stage regrown
+    _compare_hits(res, run, len(devices))
+    assert res.totals["pixels"] == run.census["pixels"]
+    # undersized slabs: the device reports the exact need and the host retries
+    res2 = sim.run(0, n, injected=H.injected_for(sim, run, 0, n), capacities=[100] * len(devices))
+    assert res2.totals["hits"] == res.totals["hits"]
+    for d in range(len(devices)):
+        assert res2.hits_numpy(d).tobytes() == res.hits_numpy(d).tobytes()
