@@ -22,6 +22,7 @@ struct PlaneK {
     double x_pos, x_neg, y_pos, y_neg;   // acceptance window, main/hit.py:56-59
     double eps, corr2;                   // thickness/X0 and (1+0.038 ln eps)^2, main/hit.py:294-296
     double pitch_c, pitch_r, delta_x, delta_y;
+    double rcp_pc, rcp_pr;               // RN(1/pitch), for div_rcp
     double half_nc, half_nr;             // number / 2 (true division), main/device.py:356,372
     double half_pc, half_pr;             // pitch / 2
     double thr_ke;                       // threshold * 1e-3, main/device.py:152
@@ -42,6 +43,7 @@ struct ConfigK {
     // charge-cloud constants, main/device.py:186-202
     double  diff2, qe, c3mu, t90, cden;
     double  sigma0;                      // cloud width for a vanishing deposit
+    double  rcp_3p6, rcp_cden;           // RN(1/3.6), RN(1/cden), for div_rcp
     PlaneK  pl[PTB_MAX_PLANES];
 };
 
@@ -268,11 +270,40 @@ struct InjectedSource {
 // physics
 // ---------------------------------------------------------------------------------------------------
 
+// a / b with y = RN(1/b) known in advance: q0 = RN(a*y), r = a - q0*b (exact in an FMA), q = RN(q0 + r*y).
+// Markstein's correction step: with a correctly rounded reciprocal the result is the correctly rounded quotient,
+// i.e. bit-identical to the IEEE division the reference executes (tests/test_division.py checks the recurrence in
+// exact rational arithmetic; the GPU parity tests check the implementation).  3 instructions instead of ~28.
+__host__ __device__ __forceinline__ double div_rcp(double a, double b, double y)
+{
+    const double q0 = a * y;
+    const double r = fma(-q0, b, a);
+    return fma(r, y, q0);
+}
+
+// tan for the flight step (main/hit.py:322-323).  Beam angles are of order 1e-4..1e-1 rad: below 2^-5 the odd
+// Taylor polynomial through x^13 is accurate to ~0.6 ulp (truncation 1e-24 relative), cheaper than the generic
+// routine's range reduction; larger angles take the library tan.
+__device__ __forceinline__ double tan_flight(double x)
+{
+    if (fabs(x) < 0.03125) {
+        const double t = x * x;
+        double       p = 21844.0 / 6081075.0;
+        p = fma(p, t, 1382.0 / 155925.0);
+        p = fma(p, t, 62.0 / 2835.0);
+        p = fma(p, t, 17.0 / 315.0);
+        p = fma(p, t, 2.0 / 15.0);
+        p = fma(p, t, 1.0 / 3.0);
+        return fma(x, t * p, x);
+    }
+    return tan(x);
+}
+
 // Highland width for electrons, main/hit.py:290-297 (the charge factor z=-1 only flips a sign that is squared)
 __host__ __device__ __forceinline__ double highland_theta0(double energy, double eps, double corr2)
 {
     double p = sqrt(energy * energy - 0.511 * 0.511);
-    double g = energy / 0.511;
+    double g = div_rcp(energy, 0.511, 1.0 / 0.511);
     double beta = sqrt(1.0 - 1.0 / (1.0 + g * g));
     double lead = 13.6 / (beta * p);
     return sqrt(lead * lead * eps * corr2);
@@ -292,16 +323,16 @@ __device__ __forceinline__ double cloud_sigma(const ConfigK &c, double eloss)
 {
     if (eloss == 0.0) return c.sigma0;   // misses deposit nothing; also keeps 0/x off the division slow path
     double ev = eloss * 1e6;
-    double q = c.qe * ev / 3.6;
-    double carg = c.c3mu * q * c.t90 / c.cden;
+    double q = div_rcp(c.qe * ev, 3.6, c.rcp_3p6);
+    double carg = div_rcp(c.c3mu * q * c.t90, c.cden, c.rcp_cden);
     double coul = 0.2 * pow_one_third(carg);
     return sqrt(c.diff2 + coul * coul) * 1e6;
 }
 
 // 1-based pixel index with truncation toward zero, main/device.py:356
-__device__ __forceinline__ int pixel_index(double pos, double delta, double pitch, double half_n)
+__device__ __forceinline__ int pixel_index(double pos, double delta, double pitch, double rcp_pitch, double half_n)
 {
-    double    t = (pos + delta) / pitch + half_n;
+    double    t = div_rcp(pos + delta, pitch, rcp_pitch) + half_n;
     long long i = __double2ll_rz(fmin(fmax(t, -1.0e9), 1.0e9)) + 1;
     return (int)i;
 }
@@ -314,13 +345,19 @@ __device__ __forceinline__ double pixel_centre(int idx, double delta, double pit
 
 #define PTB_SQRT_2PI 2.5066282746310002 /* sqrt(2*pi) rounded as numpy does: np.sqrt(2*np.pi) */
 
+// RN(1 / (2 rc^2)) for the clamped radius rc = 1/sqrt(2 pi), folded by the compiler in IEEE double
+#define PTB_RCP_2RC2_CLAMPED (1.0 / (2.0 * ((1.0 / PTB_SQRT_2PI) * (1.0 / PTB_SQRT_2PI))))
+
 // radius entering the Gaussian profile: clamped below 1 um, main/device.py:400-403
 __device__ __forceinline__ double profile_radius(double r) { return r < 1.0 ? 1.0 / PTB_SQRT_2PI : r; }
 
 // 1/(sigma*sqrt(2 pi)), first factor of main/device.py:378
 __device__ __forceinline__ double profile_norm(double rc) { return 1.0 / (rc * PTB_SQRT_2PI); }
 
-// exp(-(d^2)/(2 sigma^2)), second factor of main/device.py:378
-__device__ __forceinline__ double profile_shape(double d, double rc) { return exp(-(d * d) / (2.0 * (rc * rc))); }
+// exp(-(d^2)/(2 sigma^2)), second factor of main/device.py:378; y2 = RN(1/(2 sigma^2))
+__device__ __forceinline__ double profile_shape(double d, double rc, double y2)
+{
+    return exp(div_rcp(-(d * d), 2.0 * (rc * rc), y2));
+}
 
 }  // namespace ptb

@@ -106,6 +106,7 @@ static size_t carve_workspace(int D, unsigned long long n, const unsigned long l
 // shared memory of one warp: the per-particle cluster descriptors and the hit stage
 struct WarpShared {
     double   x[32], y[32], rx[32], ry[32], q[32], inx[32], iny[32], seedq[32];
+    double   yx[32], yy[32];   // RN(1/rx^2), RN(1/ry^2) for div_rcp
     int      clo[32], rlo[32], ncols[32], nrows[32];
     int      pprefix[32], qprefix[32], poff[32];   // work-list prefixes: profile entries, pixel quads; pool offset
     uint32_t seedcr[32];
@@ -196,8 +197,8 @@ __global__ void __launch_bounds__(TRACK_BLOCK) k_tracks(const __grid_constant__ 
             if (d == 0) {
                 eloss = e0_self;   // plane 0 is the start point: never propagated to, never bounds-checked (Q2)
             } else {
-                x = x + tan(ax) * pl.z;   // absolute z of the target plane (Q1)
-                y = y + tan(ay) * pl.z;
+                x = x + tan_flight(ax) * pl.z;   // absolute z of the target plane (Q1)
+                y = y + tan_flight(ay) * pl.z;
                 const double th = highland_theta0(E, pl.eps, pl.corr2);
                 double       zkx, zky;
                 src.step(cfg, k, d, zkx, zky, eloss);
@@ -319,20 +320,20 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
             src.dig(k, d, zrx, zry, zseed);
             const double rx = fabs(0.0 + sig * zrx);
             const double ry = fabs(0.0 + sig * zry);
-            const int    sc = pixel_index(x, pl.delta_x, pl.pitch_c, pl.half_nc);
-            const int    sr = pixel_index(y, pl.delta_y, pl.pitch_r, pl.half_nr);
+            const int    sc = pixel_index(x, pl.delta_x, pl.pitch_c, pl.rcp_pc, pl.half_nc);
+            const int    sr = pixel_index(y, pl.delta_y, pl.pitch_r, pl.rcp_pr, pl.half_nr);
             if (sc >= 1 && sc <= pl.ncol && sr >= 1 && sr <= pl.nrow) {
                 ++n_inside;
                 const double inx = profile_norm(profile_radius(rx));
                 const double iny = profile_norm(profile_radius(ry));
-                const double q = eloss == 0.0 ? 0.0 : eloss * 1e6 / 3.6;
+                const double q = eloss == 0.0 ? 0.0 : div_rcp(eloss * 1e6, 3.6, cfg.rcp_3p6);
                 const double noise = 0.0 + pl.noise_sigma * zseed;
                 // seed pixel: both profile factors are exp(-0) = 1; no pixel-area factor (Q9)
                 const double seedq = (q * (inx * iny) + noise) * 1e-3;
-                const int    c_hi = pixel_index(x + rx, pl.delta_x, pl.pitch_c, pl.half_nc);
-                const int    c_lo = pixel_index(x - rx, pl.delta_x, pl.pitch_c, pl.half_nc);
-                const int    r_hi = pixel_index(y + ry, pl.delta_y, pl.pitch_r, pl.half_nr);
-                const int    r_lo = pixel_index(y - ry, pl.delta_y, pl.pitch_r, pl.half_nr);
+                const int    c_hi = pixel_index(x + rx, pl.delta_x, pl.pitch_c, pl.rcp_pc, pl.half_nc);
+                const int    c_lo = pixel_index(x - rx, pl.delta_x, pl.pitch_c, pl.rcp_pc, pl.half_nc);
+                const int    r_hi = pixel_index(y + ry, pl.delta_y, pl.pitch_r, pl.rcp_pr, pl.half_nr);
+                const int    r_lo = pixel_index(y - ry, pl.delta_y, pl.pitch_r, pl.rcp_pr, pl.half_nr);
                 const long long nc = (long long)c_hi - c_lo + 1, nr = (long long)r_hi - r_lo + 1;
                 long long       box = (nc > 0 && nr > 0) ? nc * nr : 0;
                 if (box > (1ll << 20) || nc + nr > PC) {
@@ -345,6 +346,7 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
                 }
                 W.x[lane] = x; W.y[lane] = y; W.rx[lane] = rx; W.ry[lane] = ry;
                 W.q[lane] = q; W.inx[lane] = inx; W.iny[lane] = iny; W.seedq[lane] = seedq;
+                W.yx[lane] = 1.0 / (rx * rx); W.yy[lane] = 1.0 / (ry * ry);
                 W.clo[lane] = c_lo; W.rlo[lane] = r_lo; W.ncols[lane] = (int)nc; W.nrows[lane] = (int)nr;
                 W.seedcr[lane] = (uint32_t)sc | ((uint32_t)sr << 16);
             }
@@ -401,9 +403,12 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
                     const double pos = is_row ? W.y[own] : W.x[own];
                     const double r = is_row ? W.ry[own] : W.rx[own];
                     const double nrm = is_row ? W.iny[own] : W.inx[own];
+                    const double ye = is_row ? W.yy[own] : W.yx[own];
                     const double dd = ctr - pos;
-                    pool_g[t] = nrm * profile_shape(dd, profile_radius(r));
-                    pool_e[t] = (dd * dd) / (r * r);
+                    // 1/(2 rc^2): half of 1/r^2 (exact scaling) unless the radius is clamped (main/device.py:400-403)
+                    const double y2 = r < 1.0 ? PTB_RCP_2RC2_CLAMPED : 0.5 * ye;
+                    pool_g[t] = nrm * profile_shape(dd, profile_radius(r), y2);
+                    pool_e[t] = div_rcp(dd * dd, r * r, ye);
                 }
             }
             __syncwarp();
@@ -871,6 +876,8 @@ int ptb_create(const PtbBeam *beam, const PtbDevice *dev, int32_t n_dev, const P
         c.t90 = t;
         c.cden = 4 * M_PI * eps0 * epsr;
         c.sigma0 = sqrt(c.diff2 + 0.0) * 1e6;
+        c.rcp_3p6 = 1.0 / 3.6;
+        c.rcp_cden = 1.0 / c.cden;
     }
     double mean_prev = 0.0;   // mean loss in the previous plane; the reference indexes row -1 (all zero) for plane 0
     for (int d = 0; d < n_dev; ++d) {
@@ -888,6 +895,7 @@ int ptb_create(const PtbBeam *beam, const PtbDevice *dev, int32_t n_dev, const P
         p.delta_x = v.delta_x; p.delta_y = v.delta_y;
         p.half_nc = v.ncol / 2.0; p.half_nr = v.nrow / 2.0;
         p.half_pc = v.pitch_c / 2; p.half_pr = v.pitch_r / 2;
+        p.rcp_pc = 1.0 / v.pitch_c; p.rcp_pr = 1.0 / v.pitch_r;
         p.thr_ke = v.threshold_e * 1e-3;
         {
             double kb = 1.38 * 1e-23, qe = 1.602 * 1e-19, eps0 = 8.854 * 1e-12, epsr = 11.7, T = 300;
