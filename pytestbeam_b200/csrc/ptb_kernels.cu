@@ -667,14 +667,21 @@ __global__ void __launch_bounds__(256) k_gather(const __grid_constant__ GatherPa
     const PtbBases &B = *G.ws.bases_used;
     const int       D = G.D;
     if (G.flags & PTB_DIGITISE) {
+        // lane d fetches the segment descriptor of plane d: all table look-ups of the group are in flight at once
+        unsigned long long n_l = 0, src_l = 0, dst_l = 0;
+        if (lane < D) {
+            n_l = G.ws.table[(unsigned long long)lane * G.n_groups + group];
+            src_l = G.ws.table[(unsigned long long)(D + 5 + lane) * G.n_groups + group];
+            dst_l = B.hits[lane] + G.ws.prefix[(unsigned long long)lane * G.n_groups + group];
+        }
         const int64_t ev_base = B.event + (int64_t)G.ws.prefix[(unsigned long long)D * G.n_groups + group] + 1;
         const bool    keep64 = (G.flags & PTB_KEEP_CHARGE64) != 0;
         for (int d = 0; d < D; ++d) {
-            const unsigned long long n = G.ws.table[(unsigned long long)d * G.n_groups + group];
+            const unsigned long long n = __shfl_sync(FULL, n_l, d);
+            const unsigned long long src = __shfl_sync(FULL, src_l, d);
+            const unsigned long long dst = __shfl_sync(FULL, dst_l, d);
             if (n == 0) continue;
-            const unsigned long long src = G.ws.table[(unsigned long long)(D + 5 + d) * G.n_groups + group];
-            const unsigned long long dst = B.hits[d] + G.ws.prefix[(unsigned long long)d * G.n_groups + group];
-            const PtbHitSlab        &s = G.slabs[d];
+            const PtbHitSlab &s = G.slabs[d];
             if (dst + n > s.capacity || src + n > G.ws.cap[d]) {
                 if (lane == 0) atomicOr(&G.totals->error, PTB_DEV_SLAB_OVERFLOW);
                 continue;
