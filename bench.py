@@ -169,7 +169,9 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     K, W, chunk, seed = args.steps, args.warmup, args.chunk, args.seed
-    beam, devices, materials, _ = cfg.flatten(cfg.default_setup(chunk * K * world))
+    setup_fn = {"default": cfg.default_setup, "c3": cfg.c3, "c4": cfg.c4}[args.config]
+    workload = WORKLOAD if args.config == "default" else f"BASELINE config {args.config} (pytestbeam_b200/config.py), production RNG"
+    beam, devices, materials, _ = cfg.flatten(setup_fn(chunk * K * world))
     sim = Simulator(beam, devices, materials)
     D = sim.D
     lib = sim.lib
@@ -275,11 +277,11 @@ def run_gpu(args):
                 "hbm": {"achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
                         "bytes_per_electron": alg_bytes / chunk, "peak_source": hbm_src}}
         cpu_sample = args.cpu_sample or 1_000_000
-        cpu_val, cpu_hits = cpu_port_rate(cpu_sample, 1) if world == 1 else (None, None)
+        cpu_val, cpu_hits = cpu_port_rate(cpu_sample, 1) if (world == 1 and args.config == "default") else (None, None)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": WORKLOAD + f", {total_particles:.3g} electrons", "electrons_per_step": chunk,
+                "config": {"workload": workload + f", {total_particles:.3g} electrons", "electrons_per_step": chunk,
                            "planes": D, "hits_per_electron": hits_per_particle, "seed": seed,
                            "parallelism": f"index-range shards x{world}",
                            "l2": "no inputs; 1.2 GB of hit rows written per step (> 126 MB L2)"},
@@ -310,6 +312,8 @@ def main():
     ap.add_argument("--chunk", type=int, default=10_000_000)
     ap.add_argument("--seed", type=int, default=20261019)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="default", choices=["default", "c3", "c4"],
+                    help="telescope set-up (default = BASELINE configs 1/2/5; c3, c4 = the other two)")
     ap.add_argument("--cpu-sample", type=int, default=0)
     args = ap.parse_args()
     if args.impl == "reference":
