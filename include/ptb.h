@@ -22,7 +22,7 @@
  *   ptb_pack_hits   the structured-array rows handed to create_hit_file (main/device.py:317-327)
  *
  * Error convention: 0 on success, negative PTB_E_* otherwise; nothing is thrown across the ABI.
- * Conditions detected on the device (staging or slab overflow) are reported in PtbTotals.error, which
+ * Conditions detected on the device (slab overflow, oversized cluster box) are reported in PtbTotals.error, which
  * the caller reads after synchronising the stream.
  * One handle per GPU; a handle is not thread-safe, distinct handles are independent.
  */
@@ -45,7 +45,7 @@ extern "C" {
 #define PTB_E_NOMEM (-3)
 
 /* bits of PtbTotals.error (device-detected) */
-#define PTB_DEV_STAGE_OVERFLOW 1u /* one 32-particle group produced more hits on one plane than stage_hits */
+#define PTB_DEV_STAGE_OVERFLOW 1u /* reserved (a group that outgrows stage_hits is replayed straight into the slab) */
 #define PTB_DEV_SLAB_OVERFLOW 2u  /* a hit slab's capacity was exceeded; totals still hold the exact counts */
 #define PTB_DEV_BOX_TOO_LARGE 4u  /* a cluster bounding box exceeded 2^20 pixels */
 
@@ -72,8 +72,9 @@ typedef struct PtbDevice {
 } PtbDevice;
 
 typedef struct PtbOptions {
-    int32_t stage_hits;   /* hits one 32-particle group may stage per plane in shared memory; 0 = default (256) */
-    int32_t pool_entries; /* box columns + rows one round of a group may hold in shared memory; 0 = default (256) */
+    int32_t stage_hits;   /* hits one 32-particle group stages per plane in shared memory before falling back to a
+                             replay straight into the slab; 0 = default (128) */
+    int32_t pool_entries; /* box columns + rows one round of a group may hold in shared memory; 0 = default (192) */
     int32_t fast_math;    /* 0: IEEE operation order of the reference, no FMA contraction; 1: contracted build */
     int32_t _pad;
     double  trigger_accept; /* main/device.py:56 hard-codes 0.7; 0 = use that */

@@ -355,7 +355,14 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
 
         // The particles of the group are served in rounds so that the 1-D profiles of one round fit the
         // shared-memory pool (one round in all but pathological geometries).
-        int n_plane = 0;   // hits staged for this plane (warp-uniform)
+        // Pass 0 stages the hits in shared memory.  Should a group ever produce more hits on one plane than the
+        // stage holds, pass 0 still counts them all, the exact room is reserved, and pass 1 replays the plane (the
+        // variates are counter-based / injected, hence identical) writing straight into the scratch slab.
+        int                n_plane = 0;      // hits of this group on this plane (warp-uniform)
+        unsigned long long base = 0;         // start of the group's segment in the plane's scratch slab
+        bool               direct = false;
+        for (int pass = 0; pass < 2; ++pass) {
+        n_plane = 0;
         int o_begin = 0;
         while (true) {
             // inclusive prefix of the profile entries of lanes >= o_begin
@@ -494,13 +501,16 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     if (kmask & (1u << i)) {
-                        if (pos < S) {
+                        if (direct) {
+                            P.ws.s_cr[d][base + pos] = hcr[i];
+                            P.ws.s_q[d][base + pos] = (float)hq[i];
+                            P.ws.s_ev[d][base + pos] = (uint8_t)ev_off;
+                            if (keep64) P.ws.s_q64[d][base + pos] = hq[i];
+                        } else if (pos < S) {
                             st_cr[pos] = hcr[i];
                             st_q[pos] = (float)hq[i];
                             st_ev[pos] = (uint8_t)ev_off;
                             if (keep64) st_q64[pos] = hq[i];
-                        } else {
-                            err |= PTB_DEV_STAGE_OVERFLOW;
                         }
                         ++pos;
                     }
@@ -515,26 +525,30 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
             o_begin = o_end;
         }
         __syncwarp();
+        if (pass == 1) break;
 
-        // ---- reserve room in the plane's scratch slab and flush the stage ----------------------------
-        const int          n_out = min(n_plane, S);
-        unsigned long long base = 0;
+        // ---- reserve room in the plane's scratch slab; flush the stage, or replay into the slab ----------
         if (lane == 0) {
-            if (n_out > 0) base = atomicAdd(&P.ws.alloc[d * 16], (unsigned long long)n_out);
-            P.ws.table[(unsigned long long)d * P.n_groups + group] = (unsigned long long)n_out;
+            if (n_plane > 0) base = atomicAdd(&P.ws.alloc[d * 16], (unsigned long long)n_plane);
+            P.ws.table[(unsigned long long)d * P.n_groups + group] = (unsigned long long)n_plane;
             P.ws.table[(unsigned long long)(D + 5 + d) * P.n_groups + group] = base;
         }
         base = __shfl_sync(FULL, base, 0);
-        if (base + n_out > P.ws.cap[d]) {
-            err |= PTB_DEV_SLAB_OVERFLOW;
-        } else {
-            for (int i = lane; i < n_out; i += 32) {
+        if (base + n_plane > P.ws.cap[d]) {
+            err |= PTB_DEV_SLAB_OVERFLOW;      // totals stay exact; the host retries with slabs of that size
+            break;
+        }
+        if (n_plane <= S) {
+            for (int i = lane; i < n_plane; i += 32) {
                 P.ws.s_cr[d][base + i] = st_cr[i];
                 P.ws.s_q[d][base + i] = st_q[i];
                 P.ws.s_ev[d][base + i] = st_ev[i];
                 if (keep64) P.ws.s_q64[d][base + i] = st_q64[i];
             }
+            break;
         }
+        direct = true;
+        }   // pass
         __syncwarp();
     }
 
