@@ -125,6 +125,15 @@ __device__ __forceinline__ void normal_pair_f64(U4 w, double &n0, double &n1)
     n1 = r * s;
 }
 
+// ln Gamma(k+1) for the PTRS acceptance test: Stirling's series above 16 (truncation < 2e-12, against a
+// continuous uniform on the other side of the inequality), the library routine below
+__device__ __forceinline__ double log_gamma_kp1(double k)
+{
+    if (k < 16.0) return lgamma(k + 1.0);
+    const double z = k + 1.0, iz = 1.0 / z, iz2 = iz * iz;
+    return (z - 0.5) * log(z) - z + 0.9189385332046727 + iz * (1.0 / 12.0 - iz2 * (1.0 / 360.0 - iz2 * (1.0 / 1260.0)));
+}
+
 // ---------------------------------------------------------------------------------------------------
 // variate sources.  Both answer the same questions; the kernels are templated on the source so that the
 // deterministic (injected) and the production (Philox) mode run the very same physics code.
@@ -152,7 +161,7 @@ struct PhiloxSource {
                 if (us >= 0.07 && V <= cfg.p_vr) return (int64_t)kk;
                 if (kk < 0.0 || (us < 0.013 && V > us)) continue;
                 if (log(V) + cfg.p_log_invalpha - log(cfg.p_a / (us * us) + cfg.p_b) <=
-                    -lam + kk * cfg.p_loglam - lgamma(kk + 1.0))
+                    -lam + kk * cfg.p_loglam - log_gamma_kp1(kk))
                     return (int64_t)kk;
             }
         }

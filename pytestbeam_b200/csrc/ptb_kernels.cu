@@ -47,6 +47,7 @@ struct Workspace {
     PtbBases           *bases_used; // copy of bases_in taken by k_scan before bases_out is written
     double             *park;       // [n_groups][D][3][32] digitisation inputs handed from k_tracks to k_digitise
     unsigned           *accmask;    // [n_groups] trigger ballot of every group
+    unsigned long long *segsum;     // [(D+5) * SCAN_SEGMENTS] partial sums of the counter columns
     uint32_t           *s_cr[PTB_MAX_PLANES];
     float              *s_q[PTB_MAX_PLANES];
     uint8_t            *s_ev[PTB_MAX_PLANES];
@@ -87,6 +88,8 @@ static size_t carve_workspace(int D, unsigned long long n, const unsigned long l
     if (ws) ws->park = (double *)p;
     p = take(sizeof(unsigned) * ng);
     if (ws) ws->accmask = (unsigned *)p;
+    p = take(sizeof(unsigned long long) * (size_t)(D + 5) * 16);
+    if (ws) ws->segsum = (unsigned long long *)p;
     for (int d = 0; d < D; ++d) {
         unsigned long long c = (flags & PTB_DIGITISE) ? cap[d] : 0;
         p = take(4 * (size_t)c);
@@ -580,24 +583,62 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
 // ---------------------------------------------------------------------------------------------------
 constexpr int SCAN_THREADS = 1024;
 constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_SEGMENTS = 16;   // every counter column is scanned by this many blocks
 
+__device__ __forceinline__ void scan_segment_bounds(unsigned long long n_groups, int seg, unsigned long long &lo,
+                                                    unsigned long long &hi)
+{
+    const unsigned long long len = (n_groups + SCAN_SEGMENTS - 1) / SCAN_SEGMENTS;
+    lo = min(n_groups, len * (unsigned long long)seg);
+    hi = min(n_groups, lo + len);
+}
+
+// pass 1: sum of every segment of every column
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(unsigned long long n_groups, Workspace ws)
+{
+    __shared__ unsigned long long warp_sum[32];
+    const int                 c = blockIdx.x / SCAN_SEGMENTS, seg = blockIdx.x % SCAN_SEGMENTS;
+    const unsigned long long *col = ws.table + (unsigned long long)c * n_groups;
+    unsigned long long        lo, hi, sum = 0;
+    scan_segment_bounds(n_groups, seg, lo, hi);
+    for (unsigned long long i = lo + threadIdx.x; i < hi; i += SCAN_THREADS) sum += col[i];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(FULL, sum, s);
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        sum = warp_sum[threadIdx.x];
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(FULL, sum, s);
+        if (threadIdx.x == 0) ws.segsum[blockIdx.x] = sum;
+    }
+}
+
+// pass 2: block (c, seg) scans its segment of column c, seeded with the sums of the segments before it
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan(int D, unsigned long long n_groups, uint32_t flags, Workspace ws,
                                                        const PtbBases *bases_in, PtbBases *bases_out, PtbTotals *totals)
 {
     __shared__ unsigned long long warp_sum[32];
     __shared__ unsigned long long carry_s;
-    const int                     c = blockIdx.x;
+    const int                     c = blockIdx.x / SCAN_SEGMENTS, seg = blockIdx.x % SCAN_SEGMENTS;
     const unsigned long long     *col = ws.table + (unsigned long long)c * n_groups;
     unsigned long long           *out = (c < D + 2) ? ws.prefix + (unsigned long long)c * n_groups : nullptr;
     const int                     lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_s = 0;
+    unsigned long long            lo, hi;
+    scan_segment_bounds(n_groups, seg, lo, hi);
+    if (threadIdx.x == 0) {
+        unsigned long long before = 0;
+        for (int s2 = 0; s2 < seg; ++s2) before += ws.segsum[c * SCAN_SEGMENTS + s2];
+        carry_s = before;
+    }
     __syncthreads();
-    for (unsigned long long tile = 0; tile < n_groups; tile += (unsigned long long)SCAN_THREADS * SCAN_ITEMS) {
+    if (out == nullptr && seg != SCAN_SEGMENTS - 1) return;   // census columns only need their total
+    for (unsigned long long tile = lo; tile < hi; tile += (unsigned long long)SCAN_THREADS * SCAN_ITEMS) {
         const unsigned long long i0 = tile + (unsigned long long)threadIdx.x * SCAN_ITEMS;
         unsigned long long       v[SCAN_ITEMS], sum = 0;
 #pragma unroll
         for (int i = 0; i < SCAN_ITEMS; ++i) {
-            v[i] = (i0 + i < n_groups) ? col[i0 + i] : 0ull;
+            v[i] = (i0 + i < hi) ? col[i0 + i] : 0ull;
             sum += v[i];
         }
         unsigned long long incl = sum;
@@ -623,7 +664,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(int D, unsigned long long
         if (out) {
 #pragma unroll
             for (int i = 0; i < SCAN_ITEMS; ++i) {
-                if (i0 + i < n_groups) out[i0 + i] = excl;
+                if (i0 + i < hi) out[i0 + i] = excl;
                 excl += v[i];
             }
         }
@@ -631,7 +672,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(int D, unsigned long long
         if (threadIdx.x == SCAN_THREADS - 1) carry_s = carry + warp_sum[31];
         __syncthreads();
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && seg == SCAN_SEGMENTS - 1) {
         const unsigned long long total = carry_s;
         if (c < D) {
             const bool               recycle = (flags & PTB_RECYCLE_SLABS) != 0;
@@ -1142,8 +1183,10 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
     }
     if (tp) cudaEventRecord(tp[2], st);
 
-    k_scan<<<D + 5, SCAN_THREADS, 0, st>>>(D, P.n_groups, flags, P.ws, run->bases_in, run->bases_out, run->totals);
-    ++g_launches;
+    k_scan_sums<<<(D + 5) * SCAN_SEGMENTS, SCAN_THREADS, 0, st>>>(P.n_groups, P.ws);
+    k_scan<<<(D + 5) * SCAN_SEGMENTS, SCAN_THREADS, 0, st>>>(D, P.n_groups, flags, P.ws, run->bases_in, run->bases_out,
+                                                             run->totals);
+    g_launches += 2;
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(h, e, "k_scan launch");
 
