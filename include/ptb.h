@@ -74,7 +74,7 @@ typedef struct PtbDevice {
 typedef struct PtbOptions {
     int32_t stage_hits;   /* hits one 32-particle group stages per plane in shared memory before falling back to a
                              replay straight into the slab; 0 = default (128) */
-    int32_t pool_entries; /* box columns + rows one round of a group may hold in shared memory; 0 = default (192) */
+    int32_t pool_entries; /* box columns + rows one round of a group may hold in shared memory; 0 = default (128) */
     int32_t fast_math;    /* 0: IEEE operation order of the reference, no FMA contraction; 1: contracted build */
     int32_t _pad;
     double  trigger_accept; /* main/device.py:56 hard-codes 0.7; 0 = use that */

@@ -230,8 +230,8 @@ struct PhiloxSource {
         normal_pair_f32(w.x, w.y, zrx, zry);
         normal_pair_f32(w.z, w.w, zseed, spare);
     }
-    // noise normals of box pixels 4q .. 4q+3 of particle k on plane d: one Philox block
-    __device__ void pixel4(uint64_t k, int d, uint32_t q, int /*count*/, double z[4]) const
+    // noise normals of the q-th group of four candidate pixels of particle k on plane d: one Philox block
+    __device__ void pixel4(uint64_t k, int d, uint32_t q, const int * /*jf*/, int /*count*/, double z[4]) const
     {
         U4 w = philox_at(seed, k, SITE_PLANE + 4 * d + SUB_PIX, q);
         normal_pair_f32(w.x, w.y, z[0], z[1]);
@@ -267,11 +267,12 @@ struct InjectedSource {
         const double *p = v.dig_z + v.dig_off[(uint64_t)d * (n + 1) + (k - first)];
         zrx = p[0]; zry = p[1]; zseed = p[2];
     }
-    __device__ void pixel4(uint64_t k, int d, uint32_t q, int count, double z[4]) const
+    // jf[i]: index of the pixel in the reference's walk over its full bounding box = draw order
+    __device__ void pixel4(uint64_t k, int d, uint32_t /*q*/, const int *jf, int count, double z[4]) const
     {
-        const double *p = v.dig_z + v.dig_off[(uint64_t)d * (n + 1) + (k - first)] + 3 + 4 * (uint64_t)q;
+        const double *p = v.dig_z + v.dig_off[(uint64_t)d * (n + 1) + (k - first)] + 3;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) z[i] = i < count ? p[i] : 0.0;
+        for (int i = 0; i < 4; ++i) z[i] = i < count ? p[jf[i]] : 0.0;
     }
 };
 

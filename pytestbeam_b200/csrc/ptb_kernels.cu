@@ -110,7 +110,8 @@ static size_t carve_workspace(int D, unsigned long long n, const unsigned long l
 struct WarpShared {
     double   x[32], y[32], rx[32], ry[32], q[32], inx[32], iny[32], seedq[32];
     double   yx[32], yy[32];   // RN(1/rx^2), RN(1/ry^2) for div_rcp
-    int      clo[32], rlo[32], ncols[32], nrows[32];
+    int      clo[32], rlo[32], ncols[32], nrows[32];   // trimmed box: first column / row, extent
+    int      jbase[32], nrfull[32];                    // position of the trimmed box inside the reference's box
     int      pprefix[32], qprefix[32], poff[32];   // work-list prefixes: profile entries, pixel quads; pool offset
     uint32_t seedcr[32];
     uint8_t  evoff[32];
@@ -315,7 +316,10 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
         }
 
         // ---- cluster descriptors, one lane per particle (main/device.py:137-140, 241-266) -----------
-        int cnt = 0, nprof = 0;
+        int  cnt = 0;          // pixels of the reference's bounding box (census)
+        int  nprof = 0;        // columns + rows that can pass the ellipse test and lie on the matrix
+        int  cntT = 0;         // pixels of that trimmed box: the only ones that can become hits
+        bool inside = false;   // seed pixel on the matrix: the particle owns a work item even with an empty box
         if (valid && (acc || !pl.triggered)) {
             ++n_pairs;
             const double sig = cloud_sigma(cfg, eloss);
@@ -327,6 +331,7 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
             const int    sr = pixel_index(y, pl.delta_y, pl.pitch_r, pl.rcp_pr, pl.half_nr);
             if (sc >= 1 && sc <= pl.ncol && sr >= 1 && sr <= pl.nrow) {
                 ++n_inside;
+                inside = true;
                 const double inx = profile_norm(profile_radius(rx));
                 const double iny = profile_norm(profile_radius(ry));
                 const double q = eloss == 0.0 ? 0.0 : div_rcp(eloss * 1e6, 3.6, cfg.rcp_3p6);
@@ -339,18 +344,43 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
                 const int    r_lo = pixel_index(y - ry, pl.delta_y, pl.pitch_r, pl.rcp_pr, pl.half_nr);
                 const long long nc = (long long)c_hi - c_lo + 1, nr = (long long)r_hi - r_lo + 1;
                 long long       box = (nc > 0 && nr > 0) ? nc * nr : 0;
-                if (box > (1ll << 20) || nc + nr > PC) {
+                if (box > (1ll << 20)) {
                     err |= PTB_DEV_BOX_TOO_LARGE;
                     box = 0;
                 }
+                cnt = (int)box;
+                // A box pixel can only be kept if its column passes dx^2/rx^2 <= 1, its row dy^2/ry^2 <= 1 (both terms
+                // of the ellipse test are non-negative) and it lies on the matrix (main/device.py:290-295).  Each
+                // condition selects a contiguous index range, found by walking in from the box edges with the very
+                // expression the pixel test uses.
+                const double yx = 1.0 / (rx * rx), yy = 1.0 / (ry * ry);
+                int ca = 0, cb = -1, ra = 0, rb = -1;      // box-relative, inclusive
                 if (box > 0) {
-                    cnt = (int)box;
-                    nprof = (int)(nc + nr);
+                    ca = max(0, 1 - c_lo); cb = min((int)nc - 1, pl.ncol - c_lo);
+                    ra = max(0, 1 - r_lo); rb = min((int)nr - 1, pl.nrow - r_lo);
+                    auto term = [&](int idx, double delta, double pitch, double hn, double hp, double pos, double r,
+                                    double y_) {
+                        const double dd = pixel_centre(idx, delta, pitch, hn, hp) - pos;
+                        return div_rcp(dd * dd, r * r, y_);
+                    };
+                    while (ca <= cb && !(term(c_lo + ca, pl.delta_x, pl.pitch_c, pl.half_nc, pl.half_pc, x, rx, yx) <= 1.0)) ++ca;
+                    while (cb >= ca && !(term(c_lo + cb, pl.delta_x, pl.pitch_c, pl.half_nc, pl.half_pc, x, rx, yx) <= 1.0)) --cb;
+                    while (ra <= rb && !(term(r_lo + ra, pl.delta_y, pl.pitch_r, pl.half_nr, pl.half_pr, y, ry, yy) <= 1.0)) ++ra;
+                    while (rb >= ra && !(term(r_lo + rb, pl.delta_y, pl.pitch_r, pl.half_nr, pl.half_pr, y, ry, yy) <= 1.0)) --rb;
                 }
+                int ncT = max(cb - ca + 1, 0), nrT = max(rb - ra + 1, 0);
+                if (ncT == 0 || nrT == 0) ncT = nrT = 0;
+                if (ncT + nrT > PC) {
+                    err |= PTB_DEV_BOX_TOO_LARGE;
+                    ncT = nrT = 0;
+                }
+                cntT = ncT * nrT;
+                nprof = ncT + nrT;
                 W.x[lane] = x; W.y[lane] = y; W.rx[lane] = rx; W.ry[lane] = ry;
                 W.q[lane] = q; W.inx[lane] = inx; W.iny[lane] = iny; W.seedq[lane] = seedq;
-                W.yx[lane] = 1.0 / (rx * rx); W.yy[lane] = 1.0 / (ry * ry);
-                W.clo[lane] = c_lo; W.rlo[lane] = r_lo; W.ncols[lane] = (int)nc; W.nrows[lane] = (int)nr;
+                W.yx[lane] = yx; W.yy[lane] = yy;
+                W.clo[lane] = c_lo + ca; W.rlo[lane] = r_lo + ra; W.ncols[lane] = ncT; W.nrows[lane] = nrT;
+                W.jbase[lane] = ca * (int)nr + ra; W.nrfull[lane] = (int)nr;
                 W.seedcr[lane] = (uint32_t)sc | ((uint32_t)sr << 16);
             }
         }
@@ -379,7 +409,7 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
             const int      o_end = (fits == FULL) ? 32 : __ffs(~fits) - 1;  // first lane that does not fit
             const bool     mine = lane >= o_begin && lane < o_end;
             const int      my_prof = mine ? nprof : 0;
-            const int      my_quads = mine ? (cnt + 3) >> 2 : 0;
+            const int      my_quads = (mine && inside) ? max((cntT + 3) >> 2, 1) : 0;
             int            qin = my_quads;
 #pragma unroll
             for (int s = 1; s < 32; s <<= 1) {
@@ -443,16 +473,30 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
                 uint32_t  hcr[4];
                 if (has) {
                     const int    ncl = W.ncols[own], nrw = W.nrows[own];
-                    const int    box = ncl * nrw;
+                    const int    box = ncl * nrw;            // trimmed box: may be empty (seed fallback only)
                     const int    po = W.poff[own];
                     const double qtot = W.q[own];
-                    const bool   rpos = W.rx[own] > 0.0 && W.ry[own] > 0.0;
                     const int    clo = W.clo[own], rlo = W.rlo[own];
-                    double       zn[4];
-                    src.pixel4(P.first + group * 32 + own, d, (uint32_t)qi, min(4, box - 4 * qi), zn);
+                    const int    jbase = W.jbase[own], nrf = W.nrfull[own];
                     // column / row of the quad's first pixel; the following ones advance row-first
-                    int ci = (4 * qi) / nrw;
+                    int ci = (4 * qi) / max(nrw, 1);
                     int ri = 4 * qi - ci * nrw;
+                    // index of every pixel in the reference's (column-major) walk over its full box: the injected
+                    // noise variates are keyed by it
+                    int jf[4];
+                    {
+                        int c2 = ci, r2 = ri;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            jf[i] = jbase + c2 * nrf + r2;
+                            if (++r2 == nrw) {
+                                r2 = 0;
+                                ++c2;
+                            }
+                        }
+                    }
+                    double zn[4];
+                    src.pixel4(P.first + group * 32 + own, d, (uint32_t)qi, jf, min(4, box - 4 * qi), zn);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         if (4 * qi + i < box) {
@@ -460,9 +504,8 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
                             const double noise = 0.0 + pl.noise_sigma * zn[i];
                             const double signal = qtot * (pool_g[po + ci] * pool_g[po + ncl + ri]);
                             const double charge = (signal + noise) * 1e-3 * pl.pitch_c * pl.pitch_r;  // device.py:275-288
-                            const bool   keep = charge >= pl.thr_ke && rpos &&
-                                              pool_e[po + ci] + pool_e[po + ncl + ri] <= 1.0 && col >= 1 &&
-                                              col <= pl.ncol && row >= 1 && row <= pl.nrow;         // device.py:289-295
+                            // radius > 0 and the matrix bounds are implied by the trimmed box (device.py:289-295)
+                            const bool keep = charge >= pl.thr_ke && pool_e[po + ci] + pool_e[po + ncl + ri] <= 1.0;
                             hq[i] = charge;
                             hcr[i] = (uint32_t)col | ((uint32_t)row << 16);
                             if (keep) {
@@ -904,7 +947,7 @@ int ptb_create(const PtbBeam *beam, const PtbDevice *dev, int32_t n_dev, const P
     c.n_planes = n_dev;
     c.stage_hits = (opt && opt->stage_hits > 0) ? opt->stage_hits : 128;
     c.stage_hits = (c.stage_hits + 3) / 4 * 4;
-    c.pool_entries = (opt && opt->pool_entries > 0) ? opt->pool_entries : 192;
+    c.pool_entries = (opt && opt->pool_entries > 0) ? opt->pool_entries : 128;
     c.pool_entries = (c.pool_entries + 1) / 2 * 2;
     h->fast_math = opt ? opt->fast_math : 0;
     c.energy = beam->energy;
