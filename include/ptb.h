@@ -73,8 +73,9 @@ typedef struct PtbDevice {
 
 typedef struct PtbOptions {
     int32_t stage_hits;   /* hits one 32-particle group stages per plane in shared memory before falling back to a
-                             replay straight into the slab; 0 = default (128) */
-    int32_t pool_entries; /* box columns + rows one round of a group may hold in shared memory; 0 = default (128) */
+                             replay straight into the slab; 0 = default (128).  Compile-time variants: 128 and 8 */
+    int32_t pool_entries; /* box columns + rows one round of a group may hold in shared memory; 0 = default (128);
+                             goes with stage_hits: 128/128 (default) or 8/96 (drives the slow paths in the tests) */
     int32_t fast_math;    /* 0: IEEE operation order of the reference, no FMA contraction; 1: contracted build */
     int32_t _pad;
     double  trigger_accept; /* main/device.py:56 hard-codes 0.7; 0 = use that */

@@ -32,6 +32,10 @@ namespace ptb {
 constexpr int      WARPS_PER_BLOCK = 4;                 // k_digitise
 constexpr int      BLOCK = 32 * WARPS_PER_BLOCK;
 constexpr int      DIGI_MIN_BLOCKS = 7;
+// shared-memory sizing of k_digitise (compile-time).  The small variant exists so that the tests can drive the
+// replay-into-slab path and the multi-round pool path with ordinary geometries.
+constexpr int      STAGE_HITS = 128, POOL_ENTRIES = 128;
+constexpr int      SMALL_STAGE = 8, SMALL_POOL = 96;
 constexpr int      TRACK_BLOCK = 128;                   // k_tracks
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -118,7 +122,7 @@ struct WarpShared {
 };
 
 // bytes of one warp's region: descriptors, profile pool (2 doubles per column / row), hit stage
-__host__ __device__ inline size_t warp_shared_bytes(int stage, int pool, bool keep64)
+__host__ __device__ constexpr size_t warp_shared_bytes(int stage, int pool, bool keep64)
 {
     size_t b = sizeof(WarpShared);
     b += (size_t)pool * 16;               // profile value and ellipse term per box column / row
@@ -256,7 +260,10 @@ __global__ void __launch_bounds__(TRACK_BLOCK) k_tracks(const __grid_constant__ 
 // k_tracks' park or, with PTB_TRACKS_FROM_TABLE, from the caller's hit_tables arrays exactly as
 // main/device.py:132-138 reads them.
 // ---------------------------------------------------------------------------------------------------
-template <class Src>
+// S = hits a group stages per plane, PC = profile-pool entries, KEEP64 = also carry the f8 charge: compile-time, so
+// that every shared-memory address is base + immediate (as run-time values their re-derivation was 7 % of the
+// executed instructions).
+template <class Src, int S, int PC, bool KEEP64>
 __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __grid_constant__ ConfigK cfg,
                                                                     const __grid_constant__ KParams P, const Src src)
 {
@@ -267,11 +274,9 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
     if (group >= P.n_groups) return;  // whole warps leave; no block-wide barrier is used anywhere below
 
     const int    D = cfg.n_planes;
-    const int    S = cfg.stage_hits;
-    const int    PC = cfg.pool_entries;
-    const bool   keep64 = (P.flags & PTB_KEEP_CHARGE64) != 0;
-    const bool   from_table = (P.flags & PTB_TRACKS_FROM_TABLE) != 0;
-    const size_t wbytes = warp_shared_bytes(S, PC, keep64);
+    constexpr bool   keep64 = KEEP64;
+    const bool       from_table = (P.flags & PTB_TRACKS_FROM_TABLE) != 0;
+    constexpr size_t wbytes = warp_shared_bytes(S, PC, KEEP64);
 
     unsigned char *wbase = smem_raw + wbytes * wib;
     WarpShared    &W = *reinterpret_cast<WarpShared *>(wbase);
@@ -882,6 +887,20 @@ __global__ void __launch_bounds__(256) k_dfma(double *out, int iters, double a, 
 
 }  // namespace ptb
 
+template <class Src, int S, int PC, bool KEEP64>
+static cudaError_t launch_digitise(unsigned blocks, cudaStream_t st, const ptb::ConfigK &c, const ptb::KParams &P,
+                                   const Src &src)
+{
+    using namespace ptb;
+    constexpr size_t smem = warp_shared_bytes(S, PC, KEEP64) * WARPS_PER_BLOCK;
+    auto             kern = k_digitise<Src, S, PC, KEEP64>;
+    cudaError_t      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    kern<<<blocks, BLOCK, smem, st>>>(c, P, src);
+    return cudaGetLastError();
+}
+
 // =====================================================================================================
 // host side: handle, derived constants, C ABI
 // =====================================================================================================
@@ -945,10 +964,11 @@ int ptb_create(const PtbBeam *beam, const PtbDevice *dev, int32_t n_dev, const P
 
     ConfigK &c = h->cfg;
     c.n_planes = n_dev;
-    c.stage_hits = (opt && opt->stage_hits > 0) ? opt->stage_hits : 128;
-    c.stage_hits = (c.stage_hits + 3) / 4 * 4;
-    c.pool_entries = (opt && opt->pool_entries > 0) ? opt->pool_entries : 128;
-    c.pool_entries = (c.pool_entries + 1) / 2 * 2;
+    c.stage_hits = (opt && opt->stage_hits > 0) ? opt->stage_hits : STAGE_HITS;
+    c.pool_entries = (opt && opt->pool_entries > 0) ? opt->pool_entries : POOL_ENTRIES;
+    if (!((c.stage_hits == STAGE_HITS && c.pool_entries == POOL_ENTRIES) ||
+          (c.stage_hits == SMALL_STAGE && c.pool_entries == SMALL_POOL)))
+        return fail(h, PTB_E_INVALID, "stage_hits / pool_entries: built variants are 128/128 (default) and 8/96 (tests)");
     h->fast_math = opt ? opt->fast_math : 0;
     c.energy = beam->energy;
     c.loc_x = beam->loc_x; c.sigma_x = beam->sigma_x;
@@ -1189,9 +1209,7 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
     e = cudaMemsetAsync(run->totals, 0, sizeof(PtbTotals), st);
     if (e != cudaSuccess) return fail_cuda(h, e, "memset totals");
 
-    const bool   keep64 = (flags & PTB_KEEP_CHARGE64) != 0;
-    const size_t smem = warp_shared_bytes(c.stage_hits, c.pool_entries, keep64) * WARPS_PER_BLOCK;
-    if (smem > 227 * 1024) return fail(h, PTB_E_INVALID, "stage_hits / pool_entries too large for shared memory");
+    const bool keep64 = (flags & PTB_KEEP_CHARGE64) != 0;
     cudaEvent_t *tp = timing_pair(h);
     if (tp) cudaEventRecord(tp[0], st);
     if (!(flags & PTB_TRACKS_FROM_TABLE)) {
@@ -1207,21 +1225,25 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
     if (tp) cudaEventRecord(tp[1], st);
     if (flags & PTB_DIGITISE) {
         const unsigned blocks = (unsigned)((P.n_groups + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+        const bool     small = c.stage_hits == SMALL_STAGE;
         if (run->injected) {
-            auto kern = k_digitise<InjectedSource>;
-            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return fail_cuda(h, e, "cudaFuncSetAttribute");
-            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            kern<<<blocks, BLOCK, smem, st>>>(c, P, InjectedSource{*run->injected, run->first, run->n});
+            InjectedSource src{*run->injected, run->first, run->n};
+            if (small)
+                e = keep64 ? launch_digitise<InjectedSource, SMALL_STAGE, SMALL_POOL, true>(blocks, st, c, P, src)
+                           : launch_digitise<InjectedSource, SMALL_STAGE, SMALL_POOL, false>(blocks, st, c, P, src);
+            else
+                e = keep64 ? launch_digitise<InjectedSource, STAGE_HITS, POOL_ENTRIES, true>(blocks, st, c, P, src)
+                           : launch_digitise<InjectedSource, STAGE_HITS, POOL_ENTRIES, false>(blocks, st, c, P, src);
         } else {
-            auto kern = k_digitise<PhiloxSource>;
-            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return fail_cuda(h, e, "cudaFuncSetAttribute");
-            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            kern<<<blocks, BLOCK, smem, st>>>(c, P, PhiloxSource{run->seed});
+            PhiloxSource src{run->seed};
+            if (small)
+                e = keep64 ? launch_digitise<PhiloxSource, SMALL_STAGE, SMALL_POOL, true>(blocks, st, c, P, src)
+                           : launch_digitise<PhiloxSource, SMALL_STAGE, SMALL_POOL, false>(blocks, st, c, P, src);
+            else
+                e = keep64 ? launch_digitise<PhiloxSource, STAGE_HITS, POOL_ENTRIES, true>(blocks, st, c, P, src)
+                           : launch_digitise<PhiloxSource, STAGE_HITS, POOL_ENTRIES, false>(blocks, st, c, P, src);
         }
         ++g_launches;
-        e = cudaGetLastError();
         if (e != cudaSuccess) return fail_cuda(h, e, "k_digitise launch");
     }
     if (tp) cudaEventRecord(tp[2], st);

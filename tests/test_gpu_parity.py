@@ -181,7 +181,7 @@ def test_fine_pitch_planes_exercise_pool_rounds_and_stage_growth(torch_cuda):
                   capacities=[64 * n] * len(devices))
     assert len(run.hits[2]) / (n / 32) > 4 * sim.stage_hits   # far beyond what the stage holds per group
     _compare_hits(res, run, len(devices))
-    tiny = Simulator(beam, devices, materials, stage_hits=4, pool_entries=96)   # every plane replays / many rounds
+    tiny = Simulator(beam, devices, materials, stage_hits=8, pool_entries=96)   # every plane replays / many rounds
     res3 = tiny.run(0, n, injected=H.injected_for(tiny, run, 0, n), capacities=[64 * n] * len(devices))
     for d in range(len(devices)):
         assert res3.hits_numpy(d).tobytes() == res.hits_numpy(d).tobytes()
