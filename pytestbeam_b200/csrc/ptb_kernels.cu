@@ -368,10 +368,21 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
                         const double dd = pixel_centre(idx, delta, pitch, hn, hp) - pos;
                         return div_rcp(dd * dd, r * r, y_);
                     };
-                    while (ca <= cb && !(term(c_lo + ca, pl.delta_x, pl.pitch_c, pl.half_nc, pl.half_pc, x, rx, yx) <= 1.0)) ++ca;
-                    while (cb >= ca && !(term(c_lo + cb, pl.delta_x, pl.pitch_c, pl.half_nc, pl.half_pc, x, rx, yx) <= 1.0)) --cb;
-                    while (ra <= rb && !(term(r_lo + ra, pl.delta_y, pl.pitch_r, pl.half_nr, pl.half_pr, y, ry, yy) <= 1.0)) ++ra;
-                    while (rb >= ra && !(term(r_lo + rb, pl.delta_y, pl.pitch_r, pl.half_nr, pl.half_pr, y, ry, yy) <= 1.0)) --rb;
+                    // the box edges are the usual casualties: test the four of them straight-line first, then let
+                    // the loops finish whatever is left (matrix clipping, ties)
+                    const bool f0 = !(term(c_lo + ca, pl.delta_x, pl.pitch_c, pl.half_nc, pl.half_pc, x, rx, yx) <= 1.0);
+                    const bool f1 = !(term(c_lo + cb, pl.delta_x, pl.pitch_c, pl.half_nc, pl.half_pc, x, rx, yx) <= 1.0);
+                    const bool f2 = !(term(r_lo + ra, pl.delta_y, pl.pitch_r, pl.half_nr, pl.half_pr, y, ry, yy) <= 1.0);
+                    const bool f3 = !(term(r_lo + rb, pl.delta_y, pl.pitch_r, pl.half_nr, pl.half_pr, y, ry, yy) <= 1.0);
+                    ca += f0; cb -= f1; ra += f2; rb -= f3;
+                    if (f0)
+                        while (ca <= cb && !(term(c_lo + ca, pl.delta_x, pl.pitch_c, pl.half_nc, pl.half_pc, x, rx, yx) <= 1.0)) ++ca;
+                    if (f1)
+                        while (cb >= ca && !(term(c_lo + cb, pl.delta_x, pl.pitch_c, pl.half_nc, pl.half_pc, x, rx, yx) <= 1.0)) --cb;
+                    if (f2)
+                        while (ra <= rb && !(term(r_lo + ra, pl.delta_y, pl.pitch_r, pl.half_nr, pl.half_pr, y, ry, yy) <= 1.0)) ++ra;
+                    if (f3)
+                        while (rb >= ra && !(term(r_lo + rb, pl.delta_y, pl.pitch_r, pl.half_nr, pl.half_pr, y, ry, yy) <= 1.0)) --rb;
                 }
                 int ncT = max(cb - ca + 1, 0), nrT = max(rb - ra + 1, 0);
                 if (ncT == 0 || nrT == 0) ncT = nrT = 0;
