@@ -198,7 +198,10 @@ def run_gpu(args):
         p.run(first, K)
         return None
 
-    # warm-up: W untimed steps on both paths
+    # warm-up: W untimed steps on both paths (for N>1 including the prefix exchange, so that the NCCL communicator
+    # exists before the timed region)
+    if world > 1:
+        exchange_bases(*sim.prefix(first, min(n_rank, 1 << 20), seed=seed), device=sim.device)
     pipe.set_bases(0, 0)
     pipe.run(first, W)
     host_pipe.set_bases(0, 0)

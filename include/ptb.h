@@ -20,6 +20,7 @@
  *   PtbTrackTable   the 8-tuple returned by hit.tracks (main/hit.py:138)
  *   PtbHitSlab      the per-device hit table (main/device.py:20-28,66,156-163), as structure of arrays
  *   ptb_pack_hits   the structured-array rows handed to create_hit_file (main/device.py:317-327)
+ *   PTB_ZERO_RADIUS the calc_cluster_hits call of the threshold scan (main/threshold_scan.py:55-69)
  *
  * Error convention: 0 on success, negative PTB_E_* otherwise; nothing is thrown across the ABI.
  * Conditions detected on the device (slab overflow, oversized cluster box) are reported in PtbTotals.error, which
@@ -54,6 +55,8 @@ extern "C" {
 #define PTB_TRACKS_FROM_TABLE 2u /* do not generate tracks: read x, y, eloss from PtbRun.tracks (calc_position alone) */
 #define PTB_WRITE_TRACKS 4u      /* store the per-plane track records into PtbRun.tracks */
 #define PTB_KEEP_CHARGE64 8u     /* also store the f8 charge of every hit (PtbHitSlab.charge64) */
+#define PTB_ZERO_RADIUS 32u      /* charge injection (threshold scan, threshold_scan.py:55-69): the cluster radii are 0
+                                    instead of being drawn, so only the seed-pixel fallback of calc_cluster_hits fires */
 #define PTB_RECYCLE_SLABS 16u    /* rows start at 0 of each slab: ignore bases_in->hits and write bases_out->hits = 0 */
 
 /* beam block of setup.yml; lengths um, angles rad, energy MeV, rate Hz */
@@ -76,8 +79,6 @@ typedef struct PtbOptions {
                              replay straight into the slab; 0 = default (128).  Compile-time variants: 128 and 8 */
     int32_t pool_entries; /* box columns + rows one round of a group may hold in shared memory; 0 = default (128);
                              goes with stage_hits: 128/128 (default) or 8/96 (drives the slow paths in the tests) */
-    int32_t fast_math;    /* 0: IEEE operation order of the reference, no FMA contraction; 1: contracted build */
-    int32_t _pad;
     double  trigger_accept; /* main/device.py:56 hard-codes 0.7; 0 = use that */
 } PtbOptions;
 

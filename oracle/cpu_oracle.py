@@ -91,6 +91,8 @@ def lib():
         L.orc_digitise_plane.argtypes = [C.POINTER(OrcDevice), C.c_int32, C.c_int32, C.c_int64, dp, dp, dp,
                                          C.POINTER(C.c_uint8), C.c_void_p, dp]
         L.orc_digitise_plane.restype = C.POINTER(OrcDigi)
+        L.orc_digitise_plane_ex.argtypes = L.orc_digitise_plane.argtypes + [C.c_int32]
+        L.orc_digitise_plane_ex.restype = C.POINTER(OrcDigi)
         L.orc_digi_free.argtypes = [C.POINTER(OrcDigi)]
         L.orc_digi_free.restype = None
         _lib = L
@@ -246,13 +248,15 @@ def run_tracks(beam, devices, materials, n, zstart, gap, zkick, eloss_pre):
     return tuple(out) + (t,), eloss
 
 
-def run_digitise_plane(devices, materials, dut, n, x, y, eloss, accepted, mt: MT | None = None, inj=None):
+def run_digitise_plane(devices, materials, dut, n, x, y, eloss, accepted, mt: MT | None = None, inj=None,
+                       zero_radius=False):
     L = lib()
     od = pack_devices(devices, materials)
     acc = np.ascontiguousarray(accepted, dtype=np.uint8)
     injp = _dp(np.ascontiguousarray(inj, dtype=np.float64)) if inj is not None else None
-    r = L.orc_digitise_plane(od, len(devices), dut, n, _dp(x), _dp(y), _dp(eloss),
-                             acc.ctypes.data_as(C.POINTER(C.c_uint8)), mt.ptr if mt is not None else None, injp)
+    r = L.orc_digitise_plane_ex(od, len(devices), dut, n, _dp(x), _dp(y), _dp(eloss),
+                                acc.ctypes.data_as(C.POINTER(C.c_uint8)), mt.ptr if mt is not None else None, injp,
+                                int(bool(zero_radius)))
     rr = r.contents
     nh, nz = rr.n_hits, rr.n_z
     hits = np.zeros(nh, dtype=HITS_DTYPE)
@@ -297,3 +301,20 @@ def run(beam: dict, devices: list, materials: list, n: int | None = None, seed_i
         for k in census:
             census[k] += cs[k]
     return OracleRun(tracks, eloss, hits, q64s, var, census)
+
+
+def threshold_scan(inj_array, numb_inj, column_pitch, row_pitch, threshold, thickness, column_numb, row_numb, seed_numba,
+                   column=0, row=0):
+    """S-curve of main/threshold_scan.py:42-77 replayed on the CPU: (hit fractions, the normals drawn [bins,inj,2])."""
+    inj_array = np.asarray(inj_array, dtype=np.float64)
+    bins, numb_inj = len(inj_array), int(numb_inj)
+    n = bins * numb_inj
+    dev = [{"column": int(column_numb), "row": int(row_numb), "column_pitch": column_pitch, "row_pitch": row_pitch,
+            "thickness": thickness, "z_position": 0, "delta_x": column * column_pitch, "delta_y": row * row_pitch,
+            "threshold": threshold, "trigger": "untriggered", "material": "silicon"}]
+    mat = [{"rad_length": 93650, "Z": 14, "A": 24, "rho": 2.33}]
+    energy = np.repeat(inj_array * 1e-6 * 3.6, numb_inj).reshape(1, n)
+    hits, q64, z, off, census = run_digitise_plane(dev, mat, 0, n, np.zeros(n), np.zeros(n), energy,
+                                                   np.ones(n, np.uint8), mt=MT(seed_numba), zero_radius=True)
+    frac = np.bincount((hits["event_number"] - 1) // numb_inj, minlength=bins)[:bins] / numb_inj
+    return frac, z.reshape(bins, numb_inj, 2)

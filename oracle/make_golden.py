@@ -116,6 +116,30 @@ def helper_kats():
                                 "e": e.hex(), "rx": float(rx).hex(), "ry": float(ry).hex(),
                                 "col": [int(v) for v in c], "row": [int(v) for v in r],
                                 "q": [float(v).hex() for v in q]})
+    # threshold scan (main/threshold_scan.py:42-77): its module imports matplotlib / cmcrameri (absent here), so the
+    # loop of create_hits is replayed around the reference's own calc_cluster_hits, under a seeded Numba stream
+    @njit
+    def s_curve(seed, inj_array, numb_inj, pc, pr, thr, th, nc, nr, column, row):
+        np.random.seed(seed)
+        res = np.zeros(len(inj_array))
+        for j in range(len(inj_array)):
+            energy = inj_array[j] * 1e-6 * 3.6
+            hits = 0
+            for i in range(numb_inj):
+                c, r, q = device.calc_cluster_hits(pc, nc, column * pc, 0, pr, nr, row * pr, 0, 0, 0, thr * 1e-3, th,
+                                                   energy)
+                if len(q) > 0 and q[0] > 0:          # `charge > [0]` of threshold_scan.py:70 on the returned list
+                    hits += 1
+            res[j] = hits / numb_inj
+        return res
+
+    out["threshold_scan"] = []
+    for pc, pr, thr, th, nc, nr, lo, hi, bins, ninj, seed in [(50, 50, 1000, 300, 400, 384, 950, 1050, 40, 200, 5),
+                                                             (18.4, 18.4, 100, 50, 1152, 576, 60, 140, 32, 150, 6)]:
+        arr = np.arange(lo, hi, (hi - lo) / bins)
+        frac = s_curve(seed, arr, ninj, float(pc), float(pr), float(thr), float(th), nc, nr, 0, 0)
+        out["threshold_scan"].append({"geo": [pc, pr, thr, th, nc, nr], "low": lo, "high": hi, "bins": bins,
+                                      "inj": ninj, "seed": seed, "frac": [float(v) for v in frac]})
     return out
 
 

@@ -330,8 +330,9 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
             const double sig = cloud_sigma(cfg, eloss);
             double       zrx, zry, zseed;
             src.dig(k, d, zrx, zry, zseed);
-            const double rx = fabs(0.0 + sig * zrx);
-            const double ry = fabs(0.0 + sig * zry);
+            const bool   injected_charge = (P.flags & PTB_ZERO_RADIUS) != 0;   // threshold scan: radius 0
+            const double rx = injected_charge ? 0.0 : fabs(0.0 + sig * zrx);
+            const double ry = injected_charge ? 0.0 : fabs(0.0 + sig * zry);
             const int    sc = pixel_index(x, pl.delta_x, pl.pitch_c, pl.rcp_pc, pl.half_nc);
             const int    sr = pixel_index(y, pl.delta_y, pl.pitch_r, pl.rcp_pr, pl.half_nr);
             if (sc >= 1 && sc <= pl.ncol && sr >= 1 && sr <= pl.nrow) {
@@ -920,7 +921,6 @@ using namespace ptb;
 struct PtbContext {
     ConfigK cfg;
     int     device;
-    int     fast_math;
     int     sm_count;
     int     timing;
     std::vector<cudaEvent_t> ev;   // (start, after k_tracks, after k_digitise) per ptb_simulate, when timing is enabled
@@ -980,7 +980,6 @@ int ptb_create(const PtbBeam *beam, const PtbDevice *dev, int32_t n_dev, const P
     if (!((c.stage_hits == STAGE_HITS && c.pool_entries == POOL_ENTRIES) ||
           (c.stage_hits == SMALL_STAGE && c.pool_entries == SMALL_POOL)))
         return fail(h, PTB_E_INVALID, "stage_hits / pool_entries: built variants are 128/128 (default) and 8/96 (tests)");
-    h->fast_math = opt ? opt->fast_math : 0;
     c.energy = beam->energy;
     c.loc_x = beam->loc_x; c.sigma_x = beam->sigma_x;
     c.loc_y = beam->loc_y; c.sigma_y = beam->sigma_y;

@@ -97,14 +97,14 @@ class Simulator:
     """One telescope set-up on one GPU."""
 
     def __init__(self, beam: dict, devices: list, materials: list, device=None, stage_hits: int = 0,
-                 pool_entries: int = 0, fast_math: bool = False):
+                 pool_entries: int = 0):
         if not torch.cuda.is_available():
             raise PtbError("pytestbeam_b200 needs a CUDA device (sm_100a); there is no CPU path")
         self.lib = N.load()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.beam, self.devices, self.materials = dict(beam), list(devices), list(materials)
         self.D = len(devices)
-        self._opts = dict(stage_hits=int(stage_hits), pool_entries=int(pool_entries), fast_math=int(bool(fast_math)))
+        self._opts = dict(stage_hits=int(stage_hits), pool_entries=int(pool_entries))
         self._h = None
         self._create()
         self._hits_per_particle = None
@@ -113,7 +113,7 @@ class Simulator:
     def _create(self):
         self.close()
         h = C.c_void_p()
-        opt = N.PtbOptions(self._opts["stage_hits"], self._opts["pool_entries"], self._opts["fast_math"], 0, 0.0)
+        opt = N.PtbOptions(self._opts["stage_hits"], self._opts["pool_entries"], 0.0)
         with torch.cuda.device(self.device):
             rc = self.lib.ptb_create(C.byref(N.pack_beam(self.beam)), N.pack_devices(self.devices, self.materials),
                                      self.D, C.byref(opt), C.byref(h))
@@ -221,10 +221,10 @@ class Simulator:
                 "inside": int(u[35]), "pixels": int(u[36]), "error": int(u[37] & 0xFFFFFFFF)}
 
     def run(self, first, n, *, seed=0, injected=None, digitise=True, write_tracks=False, tracks_in=None,
-            keep_charge64=False, capacities=None, bases_in=None) -> RunResult:
+            keep_charge64=False, capacities=None, bases_in=None, zero_radius=False) -> RunResult:
         """Simulate particles [first, first+n), synchronise and return trimmed device buffers.
 
-        Retries with exact slab sizes / a larger shared-memory stage when the device reports an overflow.
+        Retries with exact slab sizes when the device reports a slab overflow (its totals stay exact).
         """
         first, n = int(first), int(n)
         flags = N.PTB_RECYCLE_SLABS   # every call of run() gets fresh slabs
@@ -236,6 +236,8 @@ class Simulator:
             flags |= N.PTB_WRITE_TRACKS
         if keep_charge64:
             flags |= N.PTB_KEEP_CHARGE64
+        if zero_radius:
+            flags |= N.PTB_ZERO_RADIUS
         if capacities is None:
             capacities = [4 * n + 4096] * self.D if digitise else [0] * self.D
         for attempt in range(8):
@@ -251,10 +253,6 @@ class Simulator:
             err = tot["error"]
             if err & N.PTB_DEV_BOX_TOO_LARGE:
                 raise PtbError("a cluster bounding box exceeded 2^20 pixels (check pitch / geometry)")
-            if err & N.PTB_DEV_STAGE_OVERFLOW:
-                self._opts["stage_hits"] = self.stage_hits * 2
-                self._create()
-                continue
             if err & N.PTB_DEV_SLAB_OVERFLOW:
                 capacities = [max(int(h), 1) for h in tot["hits"]]
                 continue

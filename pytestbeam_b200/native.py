@@ -15,6 +15,7 @@ PTB_TRACKS_FROM_TABLE = 2
 PTB_WRITE_TRACKS = 4
 PTB_KEEP_CHARGE64 = 8
 PTB_RECYCLE_SLABS = 16
+PTB_ZERO_RADIUS = 32
 
 PTB_DEV_STAGE_OVERFLOW = 1
 PTB_DEV_SLAB_OVERFLOW = 2
@@ -40,8 +41,7 @@ class PtbDevice(C.Structure):
 
 
 class PtbOptions(C.Structure):
-    _fields_ = [("stage_hits", C.c_int32), ("pool_entries", C.c_int32), ("fast_math", C.c_int32), ("_pad", C.c_int32),
-                ("trigger_accept", C.c_double)]
+    _fields_ = [("stage_hits", C.c_int32), ("pool_entries", C.c_int32), ("trigger_accept", C.c_double)]
 
 
 class PtbInjected(C.Structure):
