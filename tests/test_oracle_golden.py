@@ -126,3 +126,16 @@ def test_cluster_known_answers_f8(golden_dir):
         assert [float(v) for v in q64] == [fh(v) for v in c["q"]]
         n_hits += len(q64)
     assert n_hits > 30
+
+
+def test_threshold_scan_known_answers(golden_dir):
+    """S-curves replayed around the reference's own calc_cluster_hits (main/threshold_scan.py:42-77)."""
+    with open(os.path.join(golden_dir, "helpers.json")) as f:
+        kat = json.load(f)["threshold_scan"]
+    for t in kat:
+        pc, pr, thr, th, nc, nr = t["geo"]
+        arr = np.arange(t["low"], t["high"], (t["high"] - t["low"]) / t["bins"])
+        frac, z = co.threshold_scan(arr, t["inj"], pc, pr, thr, th, nc, nr, t["seed"])
+        assert np.array_equal(frac, np.array(t["frac"]))
+        assert z.shape == (t["bins"], t["inj"], 2)          # two normals per injection, as in the reference
+        assert 0 < frac.sum() < t["bins"]                  # a real S-curve: neither all 0 nor all 1
