@@ -21,6 +21,7 @@
  *   PtbHitSlab      the per-device hit table (main/device.py:20-28,66,156-163), as structure of arrays
  *   ptb_pack_hits   the structured-array rows handed to create_hit_file (main/device.py:317-327)
  *   PTB_ZERO_RADIUS the calc_cluster_hits call of the threshold scan (main/threshold_scan.py:55-69)
+ *   ptb_correlate   _eventloop_fast of the correlation plot (main/plotting.py:730-764)
  *
  * Error convention: 0 on success, negative PTB_E_* otherwise; nothing is thrown across the ABI.
  * Conditions detected on the device (slab overflow, oversized cluster box) are reported in PtbTotals.error, which
@@ -163,6 +164,19 @@ int ptb_prefix(PtbHandle h, uint64_t first, uint64_t n, uint64_t seed, const Ptb
                void *stream);
 
 int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream);
+
+/*
+ * Correlation histograms of two hit tables: the event loop of the reference's correlation plot (_eventloop_fast,
+ * main/plotting.py:730-764).  For every event number i in [ev_min, ev_max) each hit of table 1 with that number --
+ * plus the first hit of the following event, which the reference's loop also uses before it breaks -- is paired with
+ * the same set of table 2; x_hist[col1][col2] and y_hist[row1][row2] are incremented (int32, row-major with the given
+ * strides, zeroed by the caller, pairs outside the given extents are skipped).  Tables must be sorted by event
+ * number and hold the same set of event numbers (the reference filters them so, main/plotting.py:531-538).
+ */
+int ptb_correlate(const int64_t *ev1, const uint16_t *col1, const uint16_t *row1, uint64_t n1, const int64_t *ev2,
+                  const uint16_t *col2, const uint16_t *row2, uint64_t n2, int64_t ev_min, int64_t ev_max,
+                  int32_t *x_hist, int32_t x_dim0, int32_t x_dim1, int32_t *y_hist, int32_t y_dim0, int32_t y_dim1,
+                  void *stream);
 
 /* SoA slab rows [0, n) -> packed 18-byte records (event_number <i8, frame <u2 = 0, column <u2, row <u2, charge <f4) */
 int ptb_pack_hits(const PtbHitSlab *slab, uint64_t n, void *out_dev, void *stream);

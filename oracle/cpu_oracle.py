@@ -93,6 +93,10 @@ def lib():
         L.orc_digitise_plane.restype = C.POINTER(OrcDigi)
         L.orc_digitise_plane_ex.argtypes = L.orc_digitise_plane.argtypes + [C.c_int32]
         L.orc_digitise_plane_ex.restype = C.POINTER(OrcDigi)
+        u16p = C.POINTER(C.c_uint16)
+        L.orc_eventloop.argtypes = [ip, u16p, u16p, C.c_int64, ip, u16p, u16p, C.c_int64, C.POINTER(C.c_int32),
+                                    C.c_int64, C.POINTER(C.c_int32), C.c_int64]
+        L.orc_eventloop.restype = None
         L.orc_digi_free.argtypes = [C.POINTER(OrcDigi)]
         L.orc_digi_free.restype = None
         _lib = L
@@ -318,3 +322,36 @@ def threshold_scan(inj_array, numb_inj, column_pitch, row_pitch, threshold, thic
                                                    np.ones(n, np.uint8), mt=MT(seed_numba), zero_radius=True)
     frac = np.bincount((hits["event_number"] - 1) // numb_inj, minlength=bins)[:bins] / numb_inj
     return frac, z.reshape(bins, numb_inj, 2)
+
+
+def correlation_prepare(device_x, device_y, max_cols=(None, None), max_rows=(None, None), offset=0, event_size=None,
+                        event_numb_shift=0):
+    """The numpy pre-processing of plot_correlation (main/plotting.py:501-556): event window, event shift, keep only
+    events present in both tables, histogram shapes."""
+    device_x, device_y = np.copy(device_x), np.copy(device_y)
+    if event_size is not None:
+        device_x = device_x[(device_x["event_number"] <= offset + event_size) & (offset <= device_x["event_number"])]
+        device_y = device_y[(device_y["event_number"] <= offset + event_size) & (offset <= device_y["event_number"])]
+    device_y["event_number"] = device_y["event_number"] + event_numb_shift
+    device_x = device_x[np.isin(device_x["event_number"], device_y["event_number"])]
+    device_y = device_y[np.isin(device_y["event_number"], device_x["event_number"])]
+    max_cols, max_rows = list(max_cols), list(max_rows)
+    if max_cols[0] is None:
+        max_cols = [int(np.max(device_x["column"])) + 1, int(np.max(device_y["column"])) + 1]
+        max_rows = [int(np.max(device_x["row"])) + 1, int(np.max(device_y["row"])) + 1]
+    return device_x, device_y, max_cols, max_rows
+
+
+def correlation(device_x, device_y, **kw):
+    """(x_corr_hist, y_corr_hist) exactly as plot_correlation builds them before plotting."""
+    dx, dy, max_cols, max_rows = correlation_prepare(device_x, device_y, **kw)
+    xh = np.zeros(max_cols, dtype=np.int32)
+    yh = np.zeros(max_rows, dtype=np.int32)
+    c = lambda a, t: np.ascontiguousarray(a, dtype=t)   # noqa: E731
+    ev1, r1, c1 = c(dx["event_number"], np.int64), c(dx["row"], np.uint16), c(dx["column"], np.uint16)
+    ev2, r2, c2 = c(dy["event_number"], np.int64), c(dy["row"], np.uint16), c(dy["column"], np.uint16)
+    u16 = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint16))   # noqa: E731
+    lib().orc_eventloop(_ip(ev1), u16(r1), u16(c1), len(ev1), _ip(ev2), u16(r2), u16(c2), len(ev2),
+                        xh.ctypes.data_as(C.POINTER(C.c_int32)), xh.shape[1],
+                        yh.ctypes.data_as(C.POINTER(C.c_int32)), yh.shape[1])
+    return xh, yh

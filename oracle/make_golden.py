@@ -143,6 +143,51 @@ def helper_kats():
     return out
 
 
+def reference_eventloop():
+    """Compile the reference's own ``_eventloop_fast`` (main/plotting.py:730-764) without importing its module
+    (matplotlib / cmcrameri are absent): the function node is cut out of the parsed source and jitted as is."""
+    import ast
+    from numba import njit
+    path = os.path.join(reference_shim.reference_root(), "pytestbeam", "main", "plotting.py")
+    tree = ast.parse(open(path).read())
+    node = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "_eventloop_fast")
+    node.decorator_list = []
+    ns = {"np": np}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    return njit(nogil=True)(ns["_eventloop_fast"])
+
+
+def correlation_golden():
+    """Correlation histograms of the first and last device (plot_default, main/plotting.py:47-55) for the full-output
+    fixtures, computed with the reference's own event loop on the reference's own hit tables."""
+    from numba import int64
+    from numba.experimental import jitclass
+    from oracle import cpu_oracle as co
+
+    @jitclass([("n", int64)])
+    class Proxy:
+        def __init__(self):
+            self.n = 0
+
+        def update(self, k):
+            self.n += k
+
+    loop = reference_eventloop()
+    for name, n, a, b in FULL_CASES:
+        gold = np.load(os.path.join(GOLD, f"full_{name}_n{n}_s{a}_{b}.npz"))
+        names = list(gold["names"])
+        dx, dy, max_cols, max_rows = co.correlation_prepare(gold["hits_" + names[0]], gold["hits_" + names[-1]])
+        xh, yh = np.zeros(max_cols, dtype=np.int32), np.zeros(max_rows, dtype=np.int32)
+        xh, yh = loop(dx["event_number"], dx["row"], dx["column"], dy["event_number"], dy["row"], dy["column"], xh, yh,
+                      Proxy())
+        xi, yi = np.nonzero(xh), np.nonzero(yh)
+        path = os.path.join(GOLD, f"corr_{name}_n{n}_s{a}_{b}.npz")
+        np.savez_compressed(path, x_shape=np.array(xh.shape), y_shape=np.array(yh.shape),
+                            x_idx=np.stack(xi).astype(np.int32), x_val=xh[xi], y_idx=np.stack(yi).astype(np.int32),
+                            y_val=yh[yi])
+        print("wrote", path, int(xh.sum()), int(yh.sum()))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     for name, n, a, b in FULL_CASES:
@@ -169,6 +214,7 @@ def main():
     with open(os.path.join(GOLD, "helpers.json"), "w") as f:
         json.dump(helper_kats(), f, indent=1)
     print("wrote helpers.json")
+    correlation_golden()
 
 
 if __name__ == "__main__":

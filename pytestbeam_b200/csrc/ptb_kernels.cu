@@ -885,6 +885,40 @@ __global__ void __launch_bounds__(256) k_pack(PtbHitSlab s, unsigned long long n
 }
 
 // ---------------------------------------------------------------------------------------------------
+// k_correlate: one thread per event number; the hits of that event in both tables (plus the first hit of the next
+// event, as the reference's loop does) are found by binary search and their pairs counted with atomics
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long first_at_least(const int64_t *ev, unsigned long long n, int64_t v)
+{
+    unsigned long long lo = 0, hi = n;
+    while (lo < hi) {
+        const unsigned long long mid = (lo + hi) >> 1;
+        if (ev[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) k_correlate(const int64_t *ev1, const uint16_t *col1, const uint16_t *row1,
+                                                   unsigned long long n1, const int64_t *ev2, const uint16_t *col2,
+                                                   const uint16_t *row2, unsigned long long n2, int64_t ev_min,
+                                                   int64_t ev_max, int *xh, int xd0, int xd1, int *yh, int yd0, int yd1)
+{
+    for (int64_t i = ev_min + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ev_max;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long a0 = first_at_least(ev1, n1, i), a1 = first_at_least(ev1, n1, i + 1);
+        const unsigned long long b0 = first_at_least(ev2, n2, i), b1 = first_at_least(ev2, n2, i + 1);
+        for (unsigned long long a = a0; a <= a1 && a < n1; ++a) {
+            const int c1 = col1[a], r1 = row1[a];
+            for (unsigned long long b = b0; b <= b1 && b < n2; ++b) {
+                const int c2 = col2[b], r2 = row2[b];
+                if (c1 < xd0 && c2 < xd1) atomicAdd(&xh[(long long)c1 * xd1 + c2], 1);
+                if (r1 < yd0 && r2 < yd1) atomicAdd(&yh[(long long)r1 * yd1 + r2], 1);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // k_dfma: FP64 pipe probe for the roofline denominator
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_dfma(double *out, int iters, double a, double b)
@@ -1290,6 +1324,22 @@ int ptb_pack_hits(const PtbHitSlab *slab, uint64_t n, void *out_dev, void *strea
     if (n == 0) return PTB_OK;
     if (n > slab->capacity) return PTB_E_INVALID;
     k_pack<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*slab, n, (uint16_t *)out_dev);
+    ++g_launches;
+    return cudaGetLastError() == cudaSuccess ? PTB_OK : PTB_E_CUDA;
+}
+
+int ptb_correlate(const int64_t *ev1, const uint16_t *col1, const uint16_t *row1, uint64_t n1, const int64_t *ev2,
+                  const uint16_t *col2, const uint16_t *row2, uint64_t n2, int64_t ev_min, int64_t ev_max,
+                  int32_t *x_hist, int32_t x_dim0, int32_t x_dim1, int32_t *y_hist, int32_t y_dim0, int32_t y_dim1,
+                  void *stream)
+{
+    if (!ev1 || !col1 || !row1 || !ev2 || !col2 || !row2 || !x_hist || !y_hist) return PTB_E_INVALID;
+    if (x_dim0 < 1 || x_dim1 < 1 || y_dim0 < 1 || y_dim1 < 1) return PTB_E_INVALID;
+    if (n1 == 0 || n2 == 0 || ev_max <= ev_min) return PTB_OK;
+    const unsigned long long events = (unsigned long long)(ev_max - ev_min);
+    const unsigned           blocks = (unsigned)std::min<unsigned long long>((events + 255) / 256, 148ull * 16);
+    k_correlate<<<blocks, 256, 0, (cudaStream_t)stream>>>(ev1, col1, row1, n1, ev2, col2, row2, n2, ev_min, ev_max,
+                                                         x_hist, x_dim0, x_dim1, y_hist, y_dim0, y_dim1);
     ++g_launches;
     return cudaGetLastError() == cudaSuccess ? PTB_OK : PTB_E_CUDA;
 }

@@ -139,3 +139,17 @@ def test_threshold_scan_known_answers(golden_dir):
         assert np.array_equal(frac, np.array(t["frac"]))
         assert z.shape == (t["bins"], t["inj"], 2)          # two normals per injection, as in the reference
         assert 0 < frac.sum() < t["bins"]                  # a real S-curve: neither all 0 nor all 1
+
+
+@pytest.mark.parametrize("path", _cases(os.path.join(os.path.dirname(__file__), "golden"), "corr"))
+def test_correlation_event_loop_vs_reference(path):
+    """oracle orc_eventloop vs the reference's own _eventloop_fast (main/plotting.py:730-764) on its own hit tables."""
+    g = np.load(path)
+    full = np.load(path.replace("corr_", "full_"))
+    names = list(full["names"])
+    xh, yh = co.correlation(full["hits_" + names[0]], full["hits_" + names[-1]])
+    xr = np.zeros(tuple(g["x_shape"]), np.int32)
+    xr[tuple(g["x_idx"])] = g["x_val"]
+    yr = np.zeros(tuple(g["y_shape"]), np.int32)
+    yr[tuple(g["y_idx"])] = g["y_val"]
+    assert np.array_equal(xh, xr) and np.array_equal(yh, yr)
