@@ -776,11 +776,27 @@ struct GatherParams {
 
 __global__ void __launch_bounds__(256) k_gather(const __grid_constant__ GatherParams G)
 {
+    // per-plane pointers in shared memory: lanes of one warp address different planes at the same time
+    __shared__ const uint32_t *s_cr[PTB_MAX_PLANES];
+    __shared__ const float    *s_q[PTB_MAX_PLANES];
+    __shared__ const uint8_t  *s_ev[PTB_MAX_PLANES];
+    __shared__ const double   *s_q64[PTB_MAX_PLANES];
+    __shared__ int64_t        *d_event[PTB_MAX_PLANES];
+    __shared__ uint16_t       *d_col[PTB_MAX_PLANES], *d_row[PTB_MAX_PLANES];
+    __shared__ float          *d_charge[PTB_MAX_PLANES];
+    __shared__ double         *d_q64[PTB_MAX_PLANES];
+    const int D = G.D;
+    if (threadIdx.x < D) {
+        const int d = threadIdx.x;
+        s_cr[d] = G.ws.s_cr[d]; s_q[d] = G.ws.s_q[d]; s_ev[d] = G.ws.s_ev[d]; s_q64[d] = G.ws.s_q64[d];
+        d_event[d] = G.slabs[d].event; d_col[d] = G.slabs[d].col; d_row[d] = G.slabs[d].row;
+        d_charge[d] = G.slabs[d].charge; d_q64[d] = G.slabs[d].charge64;
+    }
+    __syncthreads();
     const int                lane = threadIdx.x & 31;
     const unsigned long long group = (unsigned long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (group >= G.n_groups) return;
     const PtbBases &B = *G.ws.bases_used;
-    const int       D = G.D;
     if (G.flags & PTB_DIGITISE) {
         // lane d fetches the segment descriptor of plane d: all table look-ups of the group are in flight at once
         unsigned long long n_l = 0, src_l = 0, dst_l = 0;
@@ -788,26 +804,38 @@ __global__ void __launch_bounds__(256) k_gather(const __grid_constant__ GatherPa
             n_l = G.ws.table[(unsigned long long)lane * G.n_groups + group];
             src_l = G.ws.table[(unsigned long long)(D + 5 + lane) * G.n_groups + group];
             dst_l = B.hits[lane] + G.ws.prefix[(unsigned long long)lane * G.n_groups + group];
+            if (n_l != 0 && (dst_l + n_l > G.slabs[lane].capacity || src_l + n_l > G.ws.cap[lane])) {
+                atomicOr(&G.totals->error, PTB_DEV_SLAB_OVERFLOW);
+                n_l = 0;
+            }
         }
         const int64_t ev_base = B.event + (int64_t)G.ws.prefix[(unsigned long long)D * G.n_groups + group] + 1;
         const bool    keep64 = (G.flags & PTB_KEEP_CHARGE64) != 0;
-        for (int d = 0; d < D; ++d) {
-            const unsigned long long n = __shfl_sync(FULL, n_l, d);
-            const unsigned long long src = __shfl_sync(FULL, src_l, d);
-            const unsigned long long dst = __shfl_sync(FULL, dst_l, d);
-            if (n == 0) continue;
-            const PtbHitSlab &s = G.slabs[d];
-            if (dst + n > s.capacity || src + n > G.ws.cap[d]) {
-                if (lane == 0) atomicOr(&G.totals->error, PTB_DEV_SLAB_OVERFLOW);
-                continue;
-            }
-            for (unsigned long long i = lane; i < n; i += 32) {
-                const uint32_t cr = G.ws.s_cr[d][src + i];
-                s.event[dst + i] = ev_base + (int64_t)G.ws.s_ev[d][src + i];
-                s.col[dst + i] = (uint16_t)(cr & 0xffffu);
-                s.row[dst + i] = (uint16_t)(cr >> 16);
-                s.charge[dst + i] = G.ws.s_q[d][src + i];
-                if (keep64) s.charge64[dst + i] = G.ws.s_q64[d][src + i];
+        // the group's segments of all planes form one work list, walked 32 rows at a time: every step is a full
+        // warp of independent loads, whatever the sizes of the individual segments
+        int cum = (int)n_l;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            int o = __shfl_up_sync(FULL, cum, s);
+            if (lane >= s) cum += o;
+        }
+        const int total = __shfl_sync(FULL, cum, 31);
+        for (int w0 = 0; w0 < total; w0 += 32) {
+            const int w = w0 + lane;
+            int       d = 0;
+            for (int p = 0; p < D; ++p) d += (__shfl_sync(FULL, cum, p) <= w) ? 1 : 0;   // plane of row w
+            d = min(d, D - 1);
+            const int                before = __shfl_sync(FULL, cum, max(d - 1, 0));   // all lanes take part
+            const int                first = d ? before : 0;
+            const unsigned long long src = __shfl_sync(FULL, src_l, d), dst = __shfl_sync(FULL, dst_l, d);
+            if (w < total) {
+                const unsigned long long i = (unsigned long long)(w - first);
+                const uint32_t           cr = s_cr[d][src + i];
+                d_event[d][dst + i] = ev_base + (int64_t)s_ev[d][src + i];
+                d_col[d][dst + i] = (uint16_t)(cr & 0xffffu);
+                d_row[d][dst + i] = (uint16_t)(cr >> 16);
+                d_charge[d][dst + i] = s_q[d][src + i];
+                if (keep64) d_q64[d][dst + i] = s_q64[d][src + i];
             }
         }
     }
