@@ -85,7 +85,7 @@ typedef struct PtbOptions {
 
 /*
  * Deterministic mode: every random variate of particles [first, first+n) pre-drawn by the caller
- * (device pointers, indexed by k - first).  Layout = oracle/cpu_oracle.py:Variates.
+ * (device pointers, indexed by k - first).
  */
 typedef struct PtbInjected {
     const double  *zstart;   /* [n][4]  standard normals for (angle_x, angle_y, x, y) at the source */

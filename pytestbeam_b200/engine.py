@@ -42,7 +42,7 @@ class Injected:
     @staticmethod
     def from_numpy(device, first: int, n: int, *, zstart=None, gap=None, zkick=None, eloss=None, accepted=None,
                    dig_z=None, dig_off=None):
-        """Slice whole-run variate tables (numpy, layout of ``oracle.cpu_oracle.Variates``) to a particle range.
+        """Slice whole-run variate tables (numpy; layout documented at PtbInjected in include/ptb.h) to a particle range.
 
         ``dig_z`` / ``dig_off`` are per-plane lists: normals in consumption order and their CSR offsets [N+1].
         """

@@ -220,3 +220,44 @@ def test_one_million_electrons_deterministic_in_chunks(torch_cuda):
         rows += len(w)
     print(f"\n1e6 electrons: {rows} hit rows, IDs identical, {charge_diff} f4 charges off by one ulp")
     assert rows > 7_000_000 and charge_diff <= rows * 1e-4
+
+
+@pytest.mark.parametrize("n_planes", [1, 2, 16, 32])
+def test_plane_count_extremes(torch_cuda, n_planes):
+    """One plane (nothing to propagate to), two, and the maximum the ABI supports (PTB_MAX_PLANES = 32)."""
+    from pytestbeam_b200 import config as cfg
+    from oracle import cpu_oracle as co
+    from pytestbeam_b200.engine import Simulator
+    n = 3000
+    setup = cfg.default_setup(n)
+    base = setup["devices"]["mimosa26_p2"]
+    devs = {}
+    for i in range(n_planes):
+        d = dict(base)
+        d["z_position"] = 0 if i == 0 else 10000 * i + 37 * (i % 3)
+        d["delta_x"], d["delta_y"] = 50 * (i % 5) - 100, 30 * (i % 4)
+        d["trigger"] = "triggered" if i % 3 == 2 else "untriggered"
+        if i % 7 == 6:
+            d.update(column=400, row=384, column_pitch=50, row_pitch=50, thickness=300, threshold=1000)
+        devs[f"plane{i}"] = d
+    setup["devices"] = devs
+    beam, devices, materials, names = cfg.flatten(setup)
+    run = co.run(beam, devices, materials, n, 91, 92)
+    sim = Simulator(beam, devices, materials)
+    res = sim.run(0, n, injected=H.injected_for(sim, run, 0, n), write_tracks=True, keep_charge64=True)
+    assert H.rel_err(res.tracks["x"].cpu().numpy(), run.tracks[3]) < 1e-6
+    assert np.array_equal(res.tracks["time_stamp"].cpu().numpy(), run.tracks[6])
+    _compare_hits(res, run, n_planes)
+    prod = sim.run(0, 20000, seed=3)
+    assert prod.totals["error"] == 0 and sum(prod.totals["hits"]) > 0
+
+
+def test_too_many_planes_is_refused(torch_cuda):
+    from pytestbeam_b200 import config as cfg
+    from pytestbeam_b200.engine import Simulator
+    setup = cfg.default_setup(10)
+    base = setup["devices"]["mimosa26_p2"]
+    setup["devices"] = {f"p{i}": dict(base, z_position=1000 * i) for i in range(33)}
+    beam, devices, materials, names = cfg.flatten(setup)
+    with pytest.raises(ValueError):
+        Simulator(beam, devices, materials)
