@@ -136,7 +136,10 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sample * workers / value * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "hits_per_s": hits,
-            "config": {"workload": WORKLOAD, "electrons_per_step": sample * workers, "planes": 7},
+            "config": {"workload": WORKLOAD + f", {args.chunk * args.steps * args.gpus:.3g} electrons",
+                       "electrons_per_step": sample * workers, "planes": 7,
+                       "note": "each step is a bounded sample of the workload: the CPU port needs ~0.3 us per electron "
+                               "and core"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
                              "sample": f"{workers} processes x {sample} electrons per step, distinct seeds; the "
                                        "reference itself is single-threaded Python+Numba and cannot travel"},

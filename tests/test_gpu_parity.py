@@ -261,3 +261,24 @@ def test_too_many_planes_is_refused(torch_cuda):
     beam, devices, materials, names = cfg.flatten(setup)
     with pytest.raises(ValueError):
         Simulator(beam, devices, materials)
+
+
+def test_tilted_offset_beam_low_energy(torch_cuda):
+    """Non-zero beam angles, offsets, unequal widths and dispersions, 40 MeV: exercises every beam scalar, the
+    large-angle branch of the flight tangent and big scattering kicks."""
+    from pytestbeam_b200 import config as cfg
+    from oracle import cpu_oracle as co
+    from pytestbeam_b200.engine import Simulator
+    n = 20000
+    setup = cfg.c4(n)
+    setup["beam"].update(energy=40.0, sigma_x=3000, sigma_y=4000, loc_x=500, loc_y=-300, x_disp=2e-4, y_disp=5e-5,
+                         x_angle=1e-3, y_angle=-2e-3, particle_rate=3.3e7)
+    beam, devices, materials, names = cfg.flatten(setup)
+    run = co.run(beam, devices, materials, n, 111, 112)
+    sim = Simulator(beam, devices, materials)
+    res = sim.run(0, n, injected=H.injected_for(sim, run, 0, n), write_tracks=True, keep_charge64=True)
+    for i, k in enumerate(TRACK_KEYS):
+        assert H.rel_err(res.tracks[k].cpu().numpy(), run.tracks[i]) < 1e-6, k
+    assert np.array_equal(res.tracks["time_stamp"].cpu().numpy(), run.tracks[6])
+    assert np.abs(run.tracks[1]).max() > 0.03125        # some angles beyond the polynomial's range
+    _compare_hits(res, run, sim.D)
