@@ -1,6 +1,6 @@
 // libptb_b200 -- kernels and C ABI (include/ptb.h).
 //
-// One call of ptb_simulate runs four kernels on the caller's stream:
+// One call of ptb_simulate runs these kernels on the caller's stream:
 //
 //   k_tracks    one lane per particle, one warp per group of 32 consecutive particles: beam draw, plane-by-
 //               plane propagation, Highland kick, Landau loss, acceptance test.  Hands the per-plane
@@ -8,11 +8,13 @@
 //   k_digitise  one warp per group, warp-cooperative: the 32 particles' pixel boxes are flattened into work
 //               lists that the lanes walk 32 items at a time (first the separable per-column / per-row
 //               profiles, then four pixels per lane), and hits are compacted in reference order (particle,
-//               column, row) with warp scans into a shared-memory stage.  After every plane the group
+//               column, row) with warp scans into a shared-memory stage.  Only the box pixels that can pass
+//               the ellipse test and lie on the matrix are evaluated.  After every plane the group
 //               reserves room in that plane's scratch slab with one atomic and flushes the stage with
 //               coalesced stores.  (Two kernels rather than one: fused, the code no longer fits the
 //               instruction cache and ran 26 % slower -- profiles/.)
-//   k_scan      exclusive prefix over the per-group counters (hits per plane, accepted events, time).
+//   k_scan_sums, k_scan   exclusive prefix over the per-group counters (hits per plane, accepted events,
+//               time), 16 blocks per counter column.
 //   k_gather    copies each group's scratch segment to its final, particle-ordered position in the
 //               structure-of-arrays hit slab and stamps the event numbers.
 //
@@ -38,6 +40,7 @@ constexpr int      STAGE_HITS = 128, POOL_ENTRIES = 128;
 constexpr int      SMALL_STAGE = 8, SMALL_POOL = 96;
 constexpr int      TRACK_BLOCK = 128;                   // k_tracks
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int      SCAN_SEGMENTS = 16;                  // every counter column is scanned by this many blocks
 
 static unsigned long long g_launches = 0;
 
@@ -88,11 +91,12 @@ static size_t carve_workspace(int D, unsigned long long n, const unsigned long l
     if (ws) ws->prefix = (unsigned long long *)p;
     p = take(sizeof(PtbBases));
     if (ws) ws->bases_used = (PtbBases *)p;
-    p = take((flags & PTB_DIGITISE) ? sizeof(double) * 96 * (size_t)D * ng : 0);
+    const bool parked = (flags & PTB_DIGITISE) && !(flags & PTB_TRACKS_FROM_TABLE);
+    p = take(parked ? sizeof(double) * 96 * (size_t)D * ng : 0);
     if (ws) ws->park = (double *)p;
     p = take(sizeof(unsigned) * ng);
     if (ws) ws->accmask = (unsigned *)p;
-    p = take(sizeof(unsigned long long) * (size_t)(D + 5) * 16);
+    p = take(sizeof(unsigned long long) * (size_t)(D + 5) * SCAN_SEGMENTS);
     if (ws) ws->segsum = (unsigned long long *)p;
     for (int d = 0; d < D; ++d) {
         unsigned long long c = (flags & PTB_DIGITISE) ? cap[d] : 0;
@@ -643,7 +647,6 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
 // ---------------------------------------------------------------------------------------------------
 constexpr int SCAN_THREADS = 1024;
 constexpr int SCAN_ITEMS = 4;
-constexpr int SCAN_SEGMENTS = 16;   // every counter column is scanned by this many blocks
 
 __device__ __forceinline__ void scan_segment_bounds(unsigned long long n_groups, int seg, unsigned long long &lo,
                                                     unsigned long long &hi)
