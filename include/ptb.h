@@ -2,7 +2,8 @@
  * ptb.h -- C ABI of libptb_b200: the per-particle Monte Carlo hot path of pytestbeam as sm_100a CUDA
  * kernels.  Plain pointers and sizes only; no torch, no C++ types.  Every entry point is
  * stream-ordered and non-blocking; the caller owns all device buffers (hit slabs, track tables,
- * injected variates, workspace); the library owns only the handle (host memory).
+ * injected variates, workspace); the library owns only the handle (host memory plus one small device table of the
+ * Poisson gap law).
  *
  * What each entry point replaces in the reference (rpartzsch/pytestbeam has no FFI layer; the boundary
  * is two Python calls and the two Numba kernels behind them -- SURVEY.md section 8b):

@@ -33,6 +33,12 @@ struct PlaneK {
     int32_t lan_direct;                  // 1: the window holds essentially all of the Moyal law: sample -ln(Z^2) directly
 };
 
+struct AliasEntry {
+    double  prob;    // probability of keeping the drawn column
+    int32_t alias;   // the column's alias otherwise
+    int32_t _pad;
+};
+
 struct ConfigK {
     int32_t n_planes, stage_hits, pool_entries, _pad0;
     double  energy, loc_x, sigma_x, loc_y, sigma_y, disp_x, disp_y, angle_x, angle_y;
@@ -40,6 +46,11 @@ struct ConfigK {
     double  accept_p;                    // main/device.py:56
     // Poisson gap, main/hit.py:33,239
     double  lam, p_loglam, p_b, p_a, p_log_invalpha, p_vr, p_explam;
+    // Walker alias table of the Poisson law on [alias_kmin, alias_kmin + alias_n) (device memory owned by the
+    // handle; null when the law is too wide for a table and the rejection samplers are used instead)
+    const struct AliasEntry *alias;
+    long long                alias_kmin;
+    int32_t                  alias_n, _pad1;
     // charge-cloud constants, main/device.py:186-202
     double  diff2, qe, c3mu, t90, cden;
     double  sigma0;                      // cloud width for a vanishing deposit
@@ -113,18 +124,6 @@ __device__ __forceinline__ void normal_pair_f32(uint32_t a, uint32_t b, double &
     n0 = (double)(r * c);
     n1 = (double)(r * s);
 }
-// Box-Muller pair in fp64 (beam profile: sigma of millimetres against a pitch of micrometres)
-__device__ __forceinline__ void normal_pair_f64(U4 w, double &n0, double &n1)
-{
-    double u = u53_open(w.x, w.y);
-    double v = u53_closed_open(w.z, w.w);
-    double r = sqrt(-2.0 * log(u));
-    double s, c;
-    sincospi(2.0 * v, &s, &c);
-    n0 = r * c;
-    n1 = r * s;
-}
-
 // ln Gamma(k+1) for the PTRS acceptance test: Stirling's series above 16 (truncation < 2e-12, against a
 // continuous uniform on the other side of the inequality), the library routine below
 __device__ __forceinline__ double log_gamma_kp1(double k)
@@ -150,6 +149,13 @@ struct PhiloxSource {
     // generator that the reference draws from, main/hit.py:239)
     __device__ int64_t gap(const ConfigK &cfg, uint64_t k) const
     {
+        if (cfg.alias) {
+            // alias method: exact for the tabulated law (the table spans the mean +- 10 sigma), one Philox block
+            U4               w = philox_at(seed, k, SITE_EVENT, 1);
+            const int        col = min((int)(u53_closed_open(w.x, w.y) * (double)cfg.alias_n), cfg.alias_n - 1);
+            const AliasEntry e = cfg.alias[col];
+            return cfg.alias_kmin + (u53_closed_open(w.z, w.w) < e.prob ? col : e.alias);
+        }
         const double lam = cfg.lam;
         if (lam >= 10.0) {
             for (uint32_t it = 1;; ++it) {
@@ -178,10 +184,19 @@ struct PhiloxSource {
             ++n;
         }
     }
+    // one Philox block: the two angle normals from the fp32 generator (dispersion of 1e-4 rad), the two position
+    // normals from a double-precision Box-Muller on 32-bit uniforms (millimetre beam against micrometre pixels)
     __device__ void start(uint64_t k, double z[4]) const
     {
-        normal_pair_f64(philox_at(seed, k, SITE_START, 0), z[0], z[1]);
-        normal_pair_f64(philox_at(seed, k, SITE_START, 1), z[2], z[3]);
+        U4 w = philox_at(seed, k, SITE_START, 0);
+        normal_pair_f32(w.x, w.y, z[0], z[1]);
+        const double u = ((double)w.z + 0.5) * 2.3283064365386963e-10;   // (0,1)
+        const double v = (double)w.w * 4.656612873077393e-10;            // [0,2)
+        const double r = sqrt(-2.0 * log(u));
+        double       sn, cs;
+        sincospi(v, &sn, &cs);
+        z[2] = r * cs;
+        z[3] = r * sn;
     }
     // scattering kicks and the Landau loss of plane d come out of one Philox block
     __device__ void step(const ConfigK &cfg, uint64_t k, int d, double &zkx, double &zky, double &eloss) const

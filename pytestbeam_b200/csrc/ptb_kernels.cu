@@ -985,6 +985,7 @@ using namespace ptb;
 
 struct PtbContext {
     ConfigK cfg;
+    void   *alias_dev;   // device copy of the Poisson alias table (cfg.alias points at it)
     int     device;
     int     sm_count;
     int     timing;
@@ -1024,6 +1025,7 @@ int ptb_create(const PtbBeam *beam, const PtbDevice *dev, int32_t n_dev, const P
     if (!h) return PTB_E_NOMEM;
     memset(&h->cfg, 0, sizeof(h->cfg));
     h->timing = 0;
+    h->alias_dev = nullptr;
     h->ev_used = 0;
     h->err[0] = 0;
     *out = h;
@@ -1135,6 +1137,50 @@ int ptb_create(const PtbBeam *beam, const PtbDevice *dev, int32_t n_dev, const P
 
     cudaError_t e = cudaGetDevice(&h->device);
     if (e != cudaSuccess) return fail_cuda(h, e, "cudaGetDevice");
+    // Poisson gap as a Walker alias table over mean +- 10 sigma (tail mass < 1e-22), when that is a sane size
+    {
+        const double sd = sqrt(c.lam);
+        const double klo = floor(fmax(0.0, c.lam - 10.0 * sd - 10.0)), khi = ceil(c.lam + 10.0 * sd + 10.0);
+        const double span = khi - klo + 1.0;
+        if (c.lam > 0.0 && span <= (double)(1 << 20)) {
+            const int           m = (int)span;
+            std::vector<double> pmf(m);
+            double              sum = 0;
+            for (int i = 0; i < m; ++i) {
+                const double k = klo + i;
+                pmf[i] = exp(k * log(c.lam) - c.lam - lgamma(k + 1.0));
+                sum += pmf[i];
+            }
+            std::vector<AliasEntry> tab(m);
+            std::vector<int>        small, large;
+            std::vector<double>     scaled(m);
+            for (int i = 0; i < m; ++i) {
+                scaled[i] = pmf[i] / sum * m;
+                (scaled[i] < 1.0 ? small : large).push_back(i);
+            }
+            while (!small.empty() && !large.empty()) {
+                const int s_ = small.back(), l_ = large.back();
+                small.pop_back();
+                tab[s_].prob = scaled[s_];
+                tab[s_].alias = l_;
+                tab[s_]._pad = 0;
+                scaled[l_] = (scaled[l_] + scaled[s_]) - 1.0;
+                if (scaled[l_] < 1.0) {
+                    large.pop_back();
+                    small.push_back(l_);
+                }
+            }
+            for (int i : large) tab[i] = AliasEntry{1.0, i, 0};
+            for (int i : small) tab[i] = AliasEntry{1.0, i, 0};
+            e = cudaMalloc(&h->alias_dev, sizeof(AliasEntry) * m);
+            if (e != cudaSuccess) return fail_cuda(h, e, "cudaMalloc(alias table)");
+            e = cudaMemcpy(h->alias_dev, tab.data(), sizeof(AliasEntry) * m, cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) return fail_cuda(h, e, "cudaMemcpy(alias table)");
+            c.alias = (const AliasEntry *)h->alias_dev;
+            c.alias_n = m;
+            c.alias_kmin = (long long)klo;
+        }
+    }
     e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
     if (e != cudaSuccess) return fail_cuda(h, e, "cudaDeviceGetAttribute");
     return PTB_OK;
@@ -1144,6 +1190,7 @@ void ptb_destroy(PtbHandle h)
 {
     if (!h) return;
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+    if (h->alias_dev) cudaFree(h->alias_dev);
     delete h;
 }
 
