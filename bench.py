@@ -265,11 +265,13 @@ def run_gpu(args):
         F_all = flops_per_particle(tot, chunk, D)
         F = digitise_flops_per_particle(tot, chunk)    # the share of SURVEY 8(d)'s count that k_digitise executes
         alg_bytes = 18.0 * sum(tot["hits"])            # 18 B per hit row, nothing read
-        traffic = None
+        traffic, ncu = None, None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
                 tj = json.load(f)
             traffic = tj["dram_bytes_per_launch"] * (chunk / tj["chunk"])
+            ncu = {k: tj[k] for k in ("issue_active_pct", "lanes_active_per_instruction", "pipe_pct") if k in tj}
+            ncu["note"] = "from the committed ncu capture (profiles/), not measured in this run"
         except Exception:
             pass
         ach_tf = F * chunk / (launch_ms * 1e-3) / 1e12
@@ -279,7 +281,8 @@ def run_gpu(args):
                 "peak_source": "in-job DFMA probe (ptb_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
                 "flops_per_electron": F, "flops_per_electron_whole_path": F_all, "launch_ms": launch_ms,
                 "k_tracks_launch_ms": tracks_launch_ms, "launches_timed": sim_launches,
-                "share_of_step": launch_ms / (ms / K), "traffic": traffic,
+                "share_of_step": launch_ms / (ms / K), "traffic": traffic, "ncu": ncu,
+                "binding": "instruction issue (78 % of issue slots busy, FP64 pipe 22 %): see profiles/README.md",
                 "hbm": {"achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
                         "bytes_per_electron": alg_bytes / chunk, "peak_source": hbm_src}}
         cpu_sample = args.cpu_sample or 1_000_000
@@ -302,7 +305,9 @@ def run_gpu(args):
         if cpu_val is not None:
             line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": f"{cpu_sample} electrons, default telescope, single thread "
-                                              "(oracle/ C + numpy port of the reference's sequential loops)",
+                                              "(oracle/ C + numpy port of the reference's sequential loops; the "
+                                              "reference itself, Python+Numba, ran 6.4-7.2e4 electrons/s on one core "
+                                              "in the build container and cannot travel to this box)",
                                     "hits_per_s": cpu_hits}
         print(json.dumps(line), flush=True)
     if world > 1:
