@@ -4,6 +4,8 @@ by two-sample KS / chi-square tests at p > 0.01 (BASELINE.json north_star, mode 
 The oracle's energy-loss table is drawn from the reference's UN-bootstrapped accept/reject pool
 (main/hit.py:347-356), because the reference's own bootstrap (main/hit.py:359) fails a KS test against
 itself; everything else in the oracle run is the reference's algorithm unchanged."""
+import os
+
 import numpy as np
 import pytest
 from scipy import stats
@@ -80,7 +82,7 @@ def _first_rows(hits):
 
 @pytest.mark.parametrize("name,seed", [("c1", 2024), ("c3", 2025), ("c4", 2026)])
 def test_distributions_match_oracle(name, seed):
-    n = 100_000
+    n = int(os.environ.get("PTB_KS_N", 100_000))      # the suite runs 1e5; larger values for one-off checks
     beam, devices, materials, names = H.setup(name, n)
     D = len(devices)
     table = _pool_table(beam, devices, materials, n, seed + 7)
