@@ -148,3 +148,30 @@ def test_distributions_match_oracle(name, seed):
     # 0.01/len(report), and at most 3 % of the tests below 0.01
     assert all(p > P_MIN / len(report) for _, p in report), bad
     assert len(bad) <= max(1, int(0.03 * len(report))), bad
+
+
+def test_source_draws_follow_their_exact_laws():
+    """One-sample tests of the production generator against the laws the reference draws from (main/hit.py:235-239,
+    main/device.py:56): beam position / angle normals, Poisson gaps, trigger acceptance.  N = 4e6."""
+    from pytestbeam_b200 import config as cfg
+    n = 4_000_000
+    beam, devices, materials, names = cfg.flatten(cfg.c1(n))
+    sim = _sim((beam, devices, materials, names))
+    D = sim.D
+    r = sim.run(0, n, seed=2026, digitise=False, write_tracks=True)
+    col = lambda k: r.tracks[k].cpu().numpy().reshape(n, D)[1:, 0]      # noqa: E731  (event 0 is special, Q3)
+    p = {"x": stats.kstest(col("x") / beam["sigma_x"], "norm").pvalue,
+         "y": stats.kstest(col("y") / beam["sigma_y"], "norm").pvalue,
+         "angle_x": stats.kstest(col("angle_x") / beam["x_disp"], "norm").pvalue,
+         "angle_y": stats.kstest(col("angle_y") / beam["y_disp"], "norm").pvalue}
+    gaps = np.diff(r.tracks["time_stamp"].cpu().numpy().reshape(n, D)[:, 0])
+    lam = 1 / beam["particle_rate"] * 1e9
+    edges = stats.poisson.ppf(np.linspace(0, 1, 41)[1:-1], lam)
+    obs = np.bincount(np.searchsorted(edges, gaps, side="left"), minlength=40)
+    expect = np.diff(np.concatenate([[0], stats.poisson.cdf(edges, lam), [1]])) * len(gaps)
+    p["gap"] = stats.chisquare(obs, expect).pvalue
+    acc = r.tracks["accepted"].cpu().numpy().astype(np.float64)
+    p["accepted"] = 2 * stats.norm.sf(abs(acc.mean() - 0.7) / np.sqrt(0.21 / n))
+    print(p)
+    assert all(v > 0.01 / len(p) for v in p.values()), p          # Bonferroni over the six laws
+    assert sum(v < 0.01 for v in p.values()) <= 1, p
