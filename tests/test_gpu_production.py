@@ -175,3 +175,33 @@ def test_source_draws_follow_their_exact_laws():
     print(p)
     assert all(v > 0.01 / len(p) for v in p.values()), p          # Bonferroni over the six laws
     assert sum(v < 0.01 for v in p.values()) <= 1, p
+
+
+@pytest.mark.parametrize("rate,lam", [(0.1, 1e10), (2e8, 5.0), (1e8, 10.0), (4e7, 25.0)])
+def test_poisson_gap_samplers(rate, lam):
+    """Gap laws across the samplers: alias table (lam = 5, 10, 25) and, when the law is too wide for a table
+    (lam = 1e10), Hoermann's PTRS -- mean, variance and a chi-square against the exact pmf."""
+    from pytestbeam_b200 import config as cfg
+    n = 400_000
+    setup = cfg.c1(n)
+    setup["beam"]["particle_rate"] = rate
+    beam, devices, materials, names = cfg.flatten(setup)
+    sim = _sim((beam, devices, materials, names))
+    r = sim.run(0, n, seed=77, digitise=False, write_tracks=True)
+    t = r.tracks["time_stamp"].cpu().numpy().reshape(n, sim.D)[:, 0]
+    gaps = np.diff(t).astype(np.float64)
+    assert abs(gaps.mean() / lam - 1) < 6 / np.sqrt(lam * n)
+    assert abs(gaps.var() / lam - 1) < 6 * np.sqrt(2 / n) + 3 / lam
+    if lam < 1e6:
+        m = int(gaps.max()) + 1
+        obs = np.bincount(gaps.astype(np.int64), minlength=m)
+        expect = stats.poisson.pmf(np.arange(m), lam) * len(gaps)
+        keep = expect > 10
+        obs_k = np.append(obs[keep], obs[~keep].sum())
+        exp_k = np.append(expect[keep], len(gaps) - expect[keep].sum())
+        assert stats.chisquare(obs_k, exp_k).pvalue > 1e-3
+    else:
+        z = (gaps - lam) / np.sqrt(lam)
+        assert stats.kstest(z, "norm").pvalue > 1e-3        # Poisson(1e10) is normal to 1e-5
+    acc, tsum = sim.prefix(0, n, seed=77)
+    assert tsum == int(t[-1])
