@@ -58,11 +58,39 @@ def run_job(job: Job, log) -> None:
                  "main.plotting.plot_default")
 
 
+def run_job_sharded(job: Job, log) -> None:
+    """One process per GPU (torchrun): every rank simulates its index range, rank 0 merges the part files."""
+    import torch
+    import torch.distributed as dist
+
+    from . import distributed
+    from .main.hit import _seed_of
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    try:
+        if job.folder.endswith("/"):
+            os.makedirs(job.folder, exist_ok=True)
+        seed = torch.tensor([_seed_of(job.beam) & (2**63 - 1)], dtype=torch.int64, device=torch.device("cuda", local))
+        dist.broadcast(seed, 0)                       # an unseeded run still needs one seed for all ranks
+        if job.saving_tracks and dist.get_rank() == 0:
+            log.info("saving_tracks is ignored in sharded runs (the track table is a single-process feature)")
+        info = distributed.run_sharded(job.beam, job.devices, job.materials, job.names, job.folder, int(seed.item()), log)
+        log.info("rank %d: electrons [%d, %d), %d hit rows" % (info["rank"], info["first"], info["first"] + info["n"],
+                                                              sum(info["hits"])))
+    finally:
+        dist.destroy_process_group()
+
+
 def main(workdir: str = ".") -> None:
     logging.basicConfig(level=logging.INFO, format="%(asctime)s %(name)s %(levelname)s %(message)s")
     log = logging.getLogger("pytestbeam")
     log.info("Preparing simulation")
-    run_job(load_job(workdir), log)
+    job = load_job(workdir)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        run_job_sharded(job, log)
+    else:
+        run_job(job, log)
 
 
 if __name__ == "__main__":
