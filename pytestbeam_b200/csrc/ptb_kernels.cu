@@ -33,7 +33,13 @@ namespace ptb {
 
 constexpr int      WARPS_PER_BLOCK = 4;                 // k_digitise
 constexpr int      BLOCK = 32 * WARPS_PER_BLOCK;
-constexpr int      DIGI_MIN_BLOCKS = 7;
+#ifndef PTB_DIGI_MIN_BLOCKS
+#define PTB_DIGI_MIN_BLOCKS 7
+#endif
+#ifndef PTB_TRACK_MIN_BLOCKS
+#define PTB_TRACK_MIN_BLOCKS 7
+#endif
+constexpr int      DIGI_MIN_BLOCKS = PTB_DIGI_MIN_BLOCKS;
 // shared-memory sizing of k_digitise (compile-time).  The small variant exists so that the tests can drive the
 // replay-into-slab path and the multi-round pool path with ordinary geometries.
 constexpr int      STAGE_HITS = 128, POOL_ENTRIES = 128;
@@ -118,7 +124,8 @@ static size_t carve_workspace(int D, unsigned long long n, const unsigned long l
 struct WarpShared {
     double   x[32], y[32], rx[32], ry[32], q[32], inx[32], iny[32], seedq[32];
     double   yx[32], yy[32];   // RN(1/rx^2), RN(1/ry^2) for div_rcp
-    int      clo[32], rlo[32], ncols[32], nrows[32];   // trimmed box: first column / row, extent
+    int      clo[32], rlo[32];                         // trimmed box: first column / row ...
+    uint8_t  ncols[32], nrows[32];                     // ... and extent (ncols + nrows <= pool entries <= 128)
     int      jbase[32], nrfull[32];                    // position of the trimmed box inside the reference's box
     int      pprefix[32], qprefix[32], poff[32];   // work-list prefixes: profile entries, pixel quads; pool offset
     uint32_t seedcr[32];
@@ -150,7 +157,7 @@ __device__ __forceinline__ unsigned lanemask_lt()
 // ("park", [D][3][32] doubles, coalesced), the trigger ballot, and the group's accepted / time counters.
 // ---------------------------------------------------------------------------------------------------
 template <class Src>
-__global__ void __launch_bounds__(TRACK_BLOCK) k_tracks(const __grid_constant__ ConfigK cfg,
+__global__ void __launch_bounds__(TRACK_BLOCK, PTB_TRACK_MIN_BLOCKS) k_tracks(const __grid_constant__ ConfigK cfg,
                                                        const __grid_constant__ KParams P, const Src src)
 {
     const int                lane = threadIdx.x & 31;
@@ -400,7 +407,7 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
                 W.x[lane] = x; W.y[lane] = y; W.rx[lane] = rx; W.ry[lane] = ry;
                 W.q[lane] = q; W.inx[lane] = inx; W.iny[lane] = iny; W.seedq[lane] = seedq;
                 W.yx[lane] = yx; W.yy[lane] = yy;
-                W.clo[lane] = c_lo + ca; W.rlo[lane] = r_lo + ra; W.ncols[lane] = ncT; W.nrows[lane] = nrT;
+                W.clo[lane] = c_lo + ca; W.rlo[lane] = r_lo + ra; W.ncols[lane] = (uint8_t)ncT; W.nrows[lane] = (uint8_t)nrT;
                 W.jbase[lane] = ca * (int)nr + ra; W.nrfull[lane] = (int)nr;
                 W.seedcr[lane] = (uint32_t)sc | ((uint32_t)sr << 16);
             }

@@ -33,6 +33,30 @@ def test_struct_sizes_match_header_layout():
     assert ctypes.sizeof(native.PtbRun) == 32 + 8 + 72 + 48 * 32 + 8 * 5
 
 
+def test_struct_layout_agrees_with_a_c_compiler(tmp_path):
+    """sizeof / offsetof of every struct as gcc sees include/ptb.h (plain C) against the ctypes mirror."""
+    import subprocess
+    structs = {"PtbBeam": native.PtbBeam, "PtbDevice": native.PtbDevice, "PtbOptions": native.PtbOptions,
+               "PtbInjected": native.PtbInjected, "PtbTrackTable": native.PtbTrackTable,
+               "PtbHitSlab": native.PtbHitSlab, "PtbBases": native.PtbBases, "PtbTotals": native.PtbTotals,
+               "PtbRun": native.PtbRun}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "ptb.h"', 'int main(void) {']
+    for name, st in structs.items():
+        lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
+        for field, _ in st._fields_:
+            lines.append(f'  printf("{name}.{field} %zu\\n", offsetof({name}, {field}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    seen = dict(ln.split() for ln in subprocess.check_output([str(exe)], text=True).splitlines())
+    for name, st in structs.items():
+        assert int(seen[name]) == ctypes.sizeof(st), name
+        for field, _ in st._fields_:
+            assert int(seen[f"{name}.{field}"]) == getattr(st, field).offset, f"{name}.{field}"
+
+
 def test_launch_counter_starts_at_zero_without_gpu_work():
     lib = native.load()
     assert lib.ptb_launch_count() >= 0
