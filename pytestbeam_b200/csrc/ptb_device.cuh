@@ -21,6 +21,7 @@ struct PlaneK {
     double z;
     double x_pos, x_neg, y_pos, y_neg;   // acceptance window, main/hit.py:56-59
     double eps, corr2;                   // thickness/X0 and (1+0.038 ln eps)^2, main/hit.py:294-296
+    double hl_c;                         // 13.6 * sqrt(eps * corr2): energy-independent factor of the Highland width
     double pitch_c, pitch_r, delta_x, delta_y;
     double rcp_pc, rcp_pr;               // RN(1/pitch), for div_rcp
     double half_nc, half_nr;             // number / 2 (true division), main/device.py:356,372
@@ -334,6 +335,20 @@ __host__ __device__ __forceinline__ double highland_theta0(double energy, double
     return sqrt(lead * lead * eps * corr2);
 }
 
+// The same width on the device, regrouped so that it costs one reciprocal square root instead of three square
+// roots, a division and a reciprocal: with g = E/0.511, beta = g/sqrt(1+g^2) and lead > 0,
+//     theta0 = 13.6 sqrt(eps corr2) / (beta p) = hl_c * (1+g^2) * rsqrt((1+g^2) * g^2 * (E^2 - 0.511^2)).
+// Agrees with the reference's operation order to <= 3 ulp (7e-16 relative; tests/test_highland.py), i.e. 1e-19 rad
+// on a kick: far below anything the pixel indices resolve.  NaN below the electron mass, as the reference (Q17).
+__device__ __forceinline__ double highland_theta0_dev(double energy, double hl_c)
+{
+    const double g = div_rcp(energy, 0.511, 1.0 / 0.511);
+    const double g2 = g * g;
+    const double num = 1.0 + g2;
+    const double den = g2 * (energy * energy - 0.511 * 0.511);
+    return hl_c * num * rsqrt(num * den);
+}
+
 // width of the collected charge cloud in um, main/device.py:186-202.  np.cbrt under Numba is pow(x, 1/3).
 // pow(x, 1.0/3.0) for x > 0, i.e. with the exponent rounded to double as the reference evaluates it:
 // x^(1/3 + delta) = cbrt(x) * (1 + delta ln x), delta = double(1/3) - 1/3 = -1.85e-17 (the correction is a fraction
@@ -341,7 +356,8 @@ __host__ __device__ __forceinline__ double highland_theta0(double energy, double
 __device__ __forceinline__ double pow_one_third(double x)
 {
     const double c = cbrt(x);
-    return fma(c, -1.850371707708594e-17 * (double)logf((float)x), c);
+    // ln x to ~1e-6 relative is ample for a correction of a few ulp: lg2 on the special-function unit
+    return fma(c, -1.850371707708594e-17 * (double)(0.6931471805599453f * __log2f((float)x)), c);
 }
 
 __device__ __forceinline__ double cloud_sigma(const ConfigK &c, double eloss)
@@ -357,9 +373,9 @@ __device__ __forceinline__ double cloud_sigma(const ConfigK &c, double eloss)
 // 1-based pixel index with truncation toward zero, main/device.py:356
 __device__ __forceinline__ int pixel_index(double pos, double delta, double pitch, double rcp_pitch, double half_n)
 {
-    double    t = div_rcp(pos + delta, pitch, rcp_pitch) + half_n;
-    long long i = __double2ll_rz(fmin(fmax(t, -1.0e9), 1.0e9)) + 1;
-    return (int)i;
+    const double t = div_rcp(pos + delta, pitch, rcp_pitch) + half_n;
+    // the conversion saturates (NaN -> 0); a saturated index wraps to INT_MIN and fails every matrix test
+    return (int)((unsigned)__double2int_rz(t) + 1u);
 }
 
 // centre of pixel idx, main/device.py:372

@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(TRACK_BLOCK, PTB_TRACK_MIN_BLOCKS) k_tracks(co
             } else {
                 x = x + tan_flight(ax) * pl.z;   // absolute z of the target plane (Q1)
                 y = y + tan_flight(ay) * pl.z;
-                const double th = highland_theta0(E, pl.eps, pl.corr2);
+                const double th = highland_theta0_dev(E, pl.hl_c);
                 double       zkx, zky;
                 src.step(cfg, k, d, zkx, zky, eloss);
                 double kx = 0.0 + th * zkx;
@@ -1100,6 +1100,7 @@ int ptb_create(const PtbBeam *beam, const PtbDevice *dev, int32_t n_dev, const P
         p.eps = v.thickness / v.rad_length;
         double corr = 1 + 0.038 * log(p.eps);
         p.corr2 = corr * corr;
+        p.hl_c = 13.6 * sqrt(p.eps * p.corr2);
         p.pitch_c = v.pitch_c; p.pitch_r = v.pitch_r;
         p.delta_x = v.delta_x; p.delta_y = v.delta_y;
         p.half_nc = v.ncol / 2.0; p.half_nr = v.nrow / 2.0;
