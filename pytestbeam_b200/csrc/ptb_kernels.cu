@@ -367,9 +367,10 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
                 }
                 cnt = (int)box;
                 // A box pixel can only be kept if its column passes dx^2/rx^2 <= 1, its row dy^2/ry^2 <= 1 (both terms
-                // of the ellipse test are non-negative) and it lies on the matrix (main/device.py:290-295).  Each
-                // condition selects a contiguous index range, found by walking in from the box edges with the very
-                // expression the pixel test uses.
+                // of the ellipse test are non-negative) and it lies on the matrix (main/device.py:290-295).  The box
+                // is clipped to the matrix, and its edge columns / rows -- the usual casualties, their centres lie up
+                // to half a pitch outside x +- rx -- are dropped when they fail the very expression the pixel test
+                // uses.  Whatever else fails is still rejected by the full test in phase B.
                 const double yx = 1.0 / (rx * rx), yy = 1.0 / (ry * ry);
                 int ca = 0, cb = -1, ra = 0, rb = -1;      // box-relative, inclusive
                 if (box > 0) {
@@ -380,21 +381,11 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
                         const double dd = pixel_centre(idx, delta, pitch, hn, hp) - pos;
                         return div_rcp(dd * dd, r * r, y_);
                     };
-                    // the box edges are the usual casualties: test the four of them straight-line first, then let
-                    // the loops finish whatever is left (matrix clipping, ties)
                     const bool f0 = !(term(c_lo + ca, pl.delta_x, pl.pitch_c, pl.half_nc, pl.half_pc, x, rx, yx) <= 1.0);
                     const bool f1 = !(term(c_lo + cb, pl.delta_x, pl.pitch_c, pl.half_nc, pl.half_pc, x, rx, yx) <= 1.0);
                     const bool f2 = !(term(r_lo + ra, pl.delta_y, pl.pitch_r, pl.half_nr, pl.half_pr, y, ry, yy) <= 1.0);
                     const bool f3 = !(term(r_lo + rb, pl.delta_y, pl.pitch_r, pl.half_nr, pl.half_pr, y, ry, yy) <= 1.0);
                     ca += f0; cb -= f1; ra += f2; rb -= f3;
-                    if (f0)
-                        while (ca <= cb && !(term(c_lo + ca, pl.delta_x, pl.pitch_c, pl.half_nc, pl.half_pc, x, rx, yx) <= 1.0)) ++ca;
-                    if (f1)
-                        while (cb >= ca && !(term(c_lo + cb, pl.delta_x, pl.pitch_c, pl.half_nc, pl.half_pc, x, rx, yx) <= 1.0)) --cb;
-                    if (f2)
-                        while (ra <= rb && !(term(r_lo + ra, pl.delta_y, pl.pitch_r, pl.half_nr, pl.half_pr, y, ry, yy) <= 1.0)) ++ra;
-                    if (f3)
-                        while (rb >= ra && !(term(r_lo + rb, pl.delta_y, pl.pitch_r, pl.half_nr, pl.half_pr, y, ry, yy) <= 1.0)) --rb;
                 }
                 int ncT = max(cb - ca + 1, 0), nrT = max(rb - ra + 1, 0);
                 if (ncT == 0 || nrT == 0) ncT = nrT = 0;
@@ -532,7 +523,8 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
                             const double noise = 0.0 + pl.noise_sigma * zn[i];
                             const double signal = qtot * (pool_g[po + ci] * pool_g[po + ncl + ri]);
                             const double charge = (signal + noise) * 1e-3 * pl.pitch_c * pl.pitch_r;  // device.py:275-288
-                            // radius > 0 and the matrix bounds are implied by the trimmed box (device.py:289-295)
+                            // the matrix bounds are implied by the clipped box; a zero radius makes the ellipse terms
+                            // NaN or inf, which fail the comparison as rx > 0 and ry > 0 would (device.py:289-295)
                             const bool keep = charge >= pl.thr_ke && pool_e[po + ci] + pool_e[po + ncl + ri] <= 1.0;
                             hq[i] = charge;
                             hcr[i] = (uint32_t)col | ((uint32_t)row << 16);
