@@ -48,7 +48,7 @@ extern "C" {
 #define PTB_E_NOMEM (-3)
 
 /* bits of PtbTotals.error (device-detected) */
-#define PTB_DEV_STAGE_OVERFLOW 1u /* reserved (a group that outgrows stage_hits is replayed straight into the slab) */
+#define PTB_DEV_SCRATCH_OVERFLOW 1u /* the workspace's scratch rows of a plane ran out; PtbTotals.reserved is exact */
 #define PTB_DEV_SLAB_OVERFLOW 2u  /* a hit slab's capacity was exceeded; totals still hold the exact counts */
 #define PTB_DEV_BOX_TOO_LARGE 4u  /* a cluster bounding box exceeded 2^20 pixels */
 
@@ -77,10 +77,9 @@ typedef struct PtbDevice {
 } PtbDevice;
 
 typedef struct PtbOptions {
-    int32_t stage_hits;   /* hits one 32-particle group stages per plane in shared memory before falling back to a
-                             replay straight into the slab; 0 = default (128).  Compile-time variants: 128 and 8 */
-    int32_t pool_entries; /* box columns + rows one round of a group may hold in shared memory; 0 = default (128);
-                             goes with stage_hits: 128/128 (default) or 8/96 (drives the slow paths in the tests) */
+    int32_t pool_entries; /* box columns + rows one round of a 32-particle group may hold in shared memory; 0 = default
+                             (128).  Compile-time variants: 128 and 96 (drives the multi-round path in the tests) */
+    int32_t _pad;
     double  trigger_accept; /* main/device.py:56 hard-codes 0.7; 0 = use that */
 } PtbOptions;
 
@@ -132,7 +131,12 @@ typedef struct PtbTotals {
     int64_t  time_sum;
     uint64_t pairs, inside, pixels; /* census: digitised (particle,plane) pairs, seed-in-matrix pairs, pixel evaluations */
     uint32_t error, _pad;
+    uint64_t reserved[PTB_MAX_PLANES]; /* scratch rows the call needs per plane (>= hits: every 32-particle group
+                                          reserves room for all pixels that can still become hits) */
 } PtbTotals;
+
+/* scratch rows per plane when the caller names none: twice the slab capacity (measured need: 1.6-1.9 x the hits) */
+#define PTB_DEFAULT_SCRATCH_ROWS(capacity) (2ull * (capacity) + 4096ull)
 
 typedef struct PtbRun {
     uint64_t first, n;   /* global particle index range */
@@ -144,8 +148,10 @@ typedef struct PtbRun {
     const PtbBases    *bases_in;   /* device; NULL = all zero */
     PtbBases          *bases_out;  /* device; bases_in + this call's totals; may alias bases_in; may be NULL */
     PtbTotals         *totals;     /* device; required */
-    void              *workspace;  /* device; ptb_workspace_bytes(handle, n, capacities) bytes */
+    void              *workspace;  /* device; ptb_workspace_bytes(handle, n, capacities, scratch_rows, flags) bytes */
     size_t             workspace_bytes;
+    uint64_t           scratch_rows[PTB_MAX_PLANES]; /* rows of the workspace's scratch slab per plane; 0 = the default
+                                                        rule.  On PTB_DEV_SCRATCH_OVERFLOW retry with totals.reserved */
 } PtbRun;
 
 typedef struct PtbContext *PtbHandle;
@@ -155,10 +161,10 @@ int         ptb_create(const PtbBeam *beam, const PtbDevice *devices, int32_t n_
 void        ptb_destroy(PtbHandle h);
 const char *ptb_last_error(PtbHandle h);
 int32_t     ptb_n_planes(PtbHandle h);
-int32_t     ptb_stage_hits(PtbHandle h);
 
-/* bytes of workspace ptb_simulate needs for n particles and the given slab capacities */
-size_t ptb_workspace_bytes(PtbHandle h, uint64_t n, const uint64_t *capacity /*[n_planes]*/, uint32_t flags);
+/* bytes of workspace ptb_simulate needs for n particles, the given slab capacities and scratch rows (NULL = default) */
+size_t ptb_workspace_bytes(PtbHandle h, uint64_t n, const uint64_t *capacity /*[n_planes]*/,
+                           const uint64_t *scratch_rows /*[n_planes] or NULL*/, uint32_t flags);
 
 /* out_dev[0] += accepted particles in [first, first+n); out_dev[1] += sum of their Poisson gaps */
 int ptb_prefix(PtbHandle h, uint64_t first, uint64_t n, uint64_t seed, const PtbInjected *inj, int64_t *out_dev,

@@ -41,7 +41,7 @@ struct AliasEntry {
 };
 
 struct ConfigK {
-    int32_t n_planes, stage_hits, pool_entries, _pad0;
+    int32_t n_planes, pool_entries;
     double  energy, loc_x, sigma_x, loc_y, sigma_y, disp_x, disp_y, angle_x, angle_y;
     double  theta0_first;                // Highland width of plane 0 at beam energy: event 0 only, main/hit.py:75-80
     double  accept_p;                    // main/device.py:56

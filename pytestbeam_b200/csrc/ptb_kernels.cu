@@ -8,11 +8,11 @@
 //   k_digitise  one warp per group, warp-cooperative: the 32 particles' pixel boxes are flattened into work
 //               lists that the lanes walk 32 items at a time (first the separable per-column / per-row
 //               profiles, then four pixels per lane), and hits are compacted in reference order (particle,
-//               column, row) with warp scans into a shared-memory stage.  Only the box pixels that can pass
-//               the ellipse test and lie on the matrix are evaluated.  After every plane the group
-//               reserves room in that plane's scratch slab with one atomic and flushes the stage with
-//               coalesced stores.  (Two kernels rather than one: fused, the code no longer fits the
-//               instruction cache and ran 26 % slower -- profiles/.)
+//               column, row) with warp scans.  Only the box pixels that can pass the ellipse test and lie on the
+//               matrix are evaluated.  Before the pixels of a plane are evaluated the group reserves room for
+//               all of them (an upper bound on its hits) in that plane's scratch slab with one atomic, so
+//               that the kept pixels go straight to their place in the segment.  (Two kernels rather than
+//               one: fused, the code no longer fits the instruction cache and ran 26 % slower -- profiles/.)
 //   k_scan_sums, k_scan   exclusive prefix over the per-group counters (hits per plane, accepted events,
 //               time), 16 blocks per counter column.
 //   k_gather    copies each group's scratch segment to its final, particle-ordered position in the
@@ -41,9 +41,9 @@ constexpr int      BLOCK = 32 * WARPS_PER_BLOCK;
 #endif
 constexpr int      DIGI_MIN_BLOCKS = PTB_DIGI_MIN_BLOCKS;
 // shared-memory sizing of k_digitise (compile-time).  The small variant exists so that the tests can drive the
-// replay-into-slab path and the multi-round pool path with ordinary geometries.
-constexpr int      STAGE_HITS = 128, POOL_ENTRIES = 128;
-constexpr int      SMALL_STAGE = 8, SMALL_POOL = 96;
+// multi-round pool path with ordinary geometries.
+constexpr int      POOL_ENTRIES = 128;
+constexpr int      SMALL_POOL = 96;
 constexpr int      TRACK_BLOCK = 128;                   // k_tracks
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int      SCAN_SEGMENTS = 16;                  // every counter column is scanned by this many blocks
@@ -61,11 +61,11 @@ struct Workspace {
     double             *park;       // [n_groups][D][3][32] digitisation inputs handed from k_tracks to k_digitise
     unsigned           *accmask;    // [n_groups] trigger ballot of every group
     unsigned long long *segsum;     // [(D+5) * SCAN_SEGMENTS] partial sums of the counter columns
-    uint32_t           *s_cr[PTB_MAX_PLANES];
-    float              *s_q[PTB_MAX_PLANES];
-    uint8_t            *s_ev[PTB_MAX_PLANES];
+    // scratch slab of every plane: segments in arbitrary (atomic) order, rows inside a segment in reference order
+    uint2              *s_hit[PTB_MAX_PLANES];   // packed (col | row << 16), f32 charge bits
+    uint8_t            *s_ev[PTB_MAX_PLANES];    // accepted particles of the group before the hit's particle
     double             *s_q64[PTB_MAX_PLANES];
-    unsigned long long  cap[PTB_MAX_PLANES];
+    unsigned long long  cap[PTB_MAX_PLANES];     // rows
 };
 
 struct KParams {
@@ -78,8 +78,8 @@ struct KParams {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static size_t carve_workspace(int D, unsigned long long n, const unsigned long long *cap, uint32_t flags, char *base,
-                              Workspace *ws)
+static size_t carve_workspace(int D, unsigned long long n, const unsigned long long *scratch_rows, uint32_t flags,
+                              char *base, Workspace *ws)
 {
     unsigned long long ng = (n + 31) / 32;
     size_t             off = 0;
@@ -105,11 +105,9 @@ static size_t carve_workspace(int D, unsigned long long n, const unsigned long l
     p = take(sizeof(unsigned long long) * (size_t)(D + 5) * SCAN_SEGMENTS);
     if (ws) ws->segsum = (unsigned long long *)p;
     for (int d = 0; d < D; ++d) {
-        unsigned long long c = (flags & PTB_DIGITISE) ? cap[d] : 0;
-        p = take(4 * (size_t)c);
-        if (ws) ws->s_cr[d] = (uint32_t *)p;
-        p = take(4 * (size_t)c);
-        if (ws) ws->s_q[d] = (float *)p;
+        unsigned long long c = (flags & PTB_DIGITISE) ? scratch_rows[d] : 0;
+        p = take(8 * (size_t)c);
+        if (ws) ws->s_hit[d] = (uint2 *)p;
         p = take((size_t)c);
         if (ws) ws->s_ev[d] = (uint8_t *)p;
         p = take((flags & PTB_KEEP_CHARGE64) ? 8 * (size_t)c : 0);
@@ -120,7 +118,7 @@ static size_t carve_workspace(int D, unsigned long long n, const unsigned long l
 }
 
 
-// shared memory of one warp: the per-particle cluster descriptors and the hit stage
+// shared memory of one warp: the per-particle cluster descriptors
 struct WarpShared {
     double   x[32], y[32], rx[32], ry[32], q[32], inx[32], iny[32], seedq[32];
     double   yx[32], yy[32];   // RN(1/rx^2), RN(1/ry^2) for div_rcp
@@ -132,14 +130,11 @@ struct WarpShared {
     uint8_t  evoff[32];
 };
 
-// bytes of one warp's region: descriptors, profile pool (2 doubles per column / row), hit stage
-__host__ __device__ constexpr size_t warp_shared_bytes(int stage, int pool, bool keep64)
+// bytes of one warp's region: descriptors, profile pool (2 doubles per column / row)
+__host__ __device__ constexpr size_t warp_shared_bytes(int pool)
 {
     size_t b = sizeof(WarpShared);
     b += (size_t)pool * 16;               // profile value and ellipse term per box column / row
-    b += (size_t)stage * (4 + 4);         // packed (col,row), f32 charge
-    b += keep64 ? (size_t)stage * 8 : 0;  // f64 charge
-    b += (size_t)stage;                   // event offset within the group
     return (b + 15) / 16 * 16;
 }
 
@@ -271,10 +266,9 @@ __global__ void __launch_bounds__(TRACK_BLOCK, PTB_TRACK_MIN_BLOCKS) k_tracks(co
 // k_tracks' park or, with PTB_TRACKS_FROM_TABLE, from the caller's hit_tables arrays exactly as
 // main/device.py:132-138 reads them.
 // ---------------------------------------------------------------------------------------------------
-// S = hits a group stages per plane, PC = profile-pool entries, KEEP64 = also carry the f8 charge: compile-time, so
-// that every shared-memory address is base + immediate (as run-time values their re-derivation was 7 % of the
-// executed instructions).
-template <class Src, int S, int PC, bool KEEP64>
+// PC = profile-pool entries, KEEP64 = also carry the f8 charge: compile-time, so that every shared-memory address
+// is base + immediate (as run-time values their re-derivation was 7 % of the executed instructions).
+template <class Src, int PC, bool KEEP64>
 __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __grid_constant__ ConfigK cfg,
                                                                     const __grid_constant__ KParams P, const Src src)
 {
@@ -287,16 +281,12 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
     const int    D = cfg.n_planes;
     constexpr bool   keep64 = KEEP64;
     const bool       from_table = (P.flags & PTB_TRACKS_FROM_TABLE) != 0;
-    constexpr size_t wbytes = warp_shared_bytes(S, PC, KEEP64);
+    constexpr size_t wbytes = warp_shared_bytes(PC);
 
     unsigned char *wbase = smem_raw + wbytes * wib;
     WarpShared    &W = *reinterpret_cast<WarpShared *>(wbase);
     double        *pool_g = reinterpret_cast<double *>(wbase + sizeof(WarpShared));
     double        *pool_e = pool_g + PC;
-    uint32_t      *st_cr = reinterpret_cast<uint32_t *>(pool_e + PC);
-    float         *st_q = reinterpret_cast<float *>(st_cr + S);
-    double        *st_q64 = reinterpret_cast<double *>(st_q + S);
-    uint8_t       *st_ev = reinterpret_cast<uint8_t *>(st_q + S) + (keep64 ? (size_t)S * 8 : 0);
     const double  *park = P.ws.park + group * (unsigned long long)(D * 96) + lane;
 
     const unsigned long long kl = group * 32 + lane;  // index inside this call's range
@@ -405,17 +395,23 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
         }
         n_pixels += (unsigned)cnt;
 
+        // ---- room for every pixel that can become a hit (all trimmed-box pixels, or the seed fallback), reserved
+        //      in the plane's scratch slab before the pixels are evaluated: the kept ones go straight to their place
+        //      in the segment, and the atomic's latency hides behind phase A.  The segment's unused tail stays a hole
+        //      (k_gather copies the first n_plane rows).
+        const int          ub = __reduce_add_sync(FULL, inside ? max(cntT, 1) : 0);
+        unsigned long long base = 0;         // start of the group's segment in the plane's scratch slab
+        if (lane == 0 && ub > 0) base = atomicAdd(&P.ws.alloc[d * 16], (unsigned long long)ub);
+        uint2   *seg_hit = P.ws.s_hit[d];    // become the group's segment once the reservation has come back
+        uint8_t *seg_ev = P.ws.s_ev[d];
+        double  *seg_q64 = P.ws.s_q64[d];
+        bool     room = true;
+
         // The particles of the group are served in rounds so that the 1-D profiles of one round fit the
         // shared-memory pool (one round in all but pathological geometries).
-        // Pass 0 stages the hits in shared memory.  Should a group ever produce more hits on one plane than the
-        // stage holds, pass 0 still counts them all, the exact room is reserved, and pass 1 replays the plane (the
-        // variates are counter-based / injected, hence identical) writing straight into the scratch slab.
-        int                n_plane = 0;      // hits of this group on this plane (warp-uniform)
-        unsigned long long base = 0;         // start of the group's segment in the plane's scratch slab
-        bool               direct = false;
-        for (int pass = 0; pass < 2; ++pass) {
-        n_plane = 0;
+        int n_plane = 0;      // hits of this group on this plane (warp-uniform)
         int o_begin = 0;
+        bool first_round = true;
         while (true) {
             // inclusive prefix of the profile entries of lanes >= o_begin
             int pin = (lane >= o_begin) ? nprof : 0;
@@ -471,6 +467,14 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
                 }
             }
             __syncwarp();
+            if (first_round) {
+                base = __shfl_sync(FULL, base, 0);
+                room = base + (unsigned long long)ub <= P.ws.cap[d];   // else: count only, the host retries
+                seg_hit += base;
+                seg_ev += base;
+                if (keep64) seg_q64 += base;
+                first_round = false;
+            }
 
             // ---- phase B: pixels in (particle, column, row) order, four per lane and step -----------------
             int carry_owner = -1;   // particle whose pixels straddle the previous step, and its kept count
@@ -562,23 +566,16 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
                 }
                 const unsigned fbmask = __ballot_sync(FULL, fb);
                 // position = hits of earlier steps + kept pixels of lower lanes + fallbacks of lower lanes
-                int       pos = n_plane + (kin - kq) + __popc(fbmask & lanemask_lt());
-                const int ev_off = W.evoff[own];
+                const unsigned pos = (unsigned)(n_plane + (kin - kq) + __popc(fbmask & lanemask_lt()));
+                const unsigned wmask = room ? kmask : 0u;
+                const unsigned ev_off = W.evoff[own];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    if (kmask & (1u << i)) {
-                        if (direct) {
-                            P.ws.s_cr[d][base + pos] = hcr[i];
-                            P.ws.s_q[d][base + pos] = (float)hq[i];
-                            P.ws.s_ev[d][base + pos] = (uint8_t)ev_off;
-                            if (keep64) P.ws.s_q64[d][base + pos] = hq[i];
-                        } else if (pos < S) {
-                            st_cr[pos] = hcr[i];
-                            st_q[pos] = (float)hq[i];
-                            st_ev[pos] = (uint8_t)ev_off;
-                            if (keep64) st_q64[pos] = hq[i];
-                        }
-                        ++pos;
+                    if (wmask & (1u << i)) {
+                        const unsigned at = pos + __popc(kmask & ((1u << i) - 1u));
+                        seg_hit[at] = make_uint2(hcr[i], __float_as_uint((float)hq[i]));
+                        seg_ev[at] = (uint8_t)ev_off;
+                        if (keep64) seg_q64[at] = hq[i];
                     }
                 }
                 n_plane += __shfl_sync(FULL, kin, 31) + __popc(fbmask);
@@ -591,31 +588,11 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
             o_begin = o_end;
         }
         __syncwarp();
-        if (pass == 1) break;
-
-        // ---- reserve room in the plane's scratch slab; flush the stage, or replay into the slab ----------
         if (lane == 0) {
-            if (n_plane > 0) base = atomicAdd(&P.ws.alloc[d * 16], (unsigned long long)n_plane);
             P.ws.table[(unsigned long long)d * P.n_groups + group] = (unsigned long long)n_plane;
             P.ws.table[(unsigned long long)(D + 5 + d) * P.n_groups + group] = base;
         }
-        base = __shfl_sync(FULL, base, 0);
-        if (base + n_plane > P.ws.cap[d]) {
-            err |= PTB_DEV_SLAB_OVERFLOW;      // totals stay exact; the host retries with slabs of that size
-            break;
-        }
-        if (n_plane <= S) {
-            for (int i = lane; i < n_plane; i += 32) {
-                P.ws.s_cr[d][base + i] = st_cr[i];
-                P.ws.s_q[d][base + i] = st_q[i];
-                P.ws.s_ev[d][base + i] = st_ev[i];
-                if (keep64) P.ws.s_q64[d][base + i] = st_q64[i];
-            }
-            break;
-        }
-        direct = true;
-        }   // pass
-        __syncwarp();
+        if (!room) err |= PTB_DEV_SCRATCH_OVERFLOW;   // totals stay exact; the host retries with the reported sizes
     }
 
 
@@ -741,6 +718,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(int D, unsigned long long
             const unsigned long long b = (bases_in && !recycle) ? bases_in->hits[c] : 0ull;
             ws.bases_used->hits[c] = b;
             totals->hits[c] = total;
+            totals->reserved[c] = ws.alloc[c * 16];   // scratch rows the groups asked for (k_digitise has finished)
             if (bases_out) bases_out->hits[c] = recycle ? 0ull : b + total;
         } else if (c == D) {
             const int64_t b = bases_in ? bases_in->event : 0;
@@ -779,8 +757,7 @@ struct GatherParams {
 __global__ void __launch_bounds__(256) k_gather(const __grid_constant__ GatherParams G)
 {
     // per-plane pointers in shared memory: lanes of one warp address different planes at the same time
-    __shared__ const uint32_t *s_cr[PTB_MAX_PLANES];
-    __shared__ const float    *s_q[PTB_MAX_PLANES];
+    __shared__ const uint2    *s_hit[PTB_MAX_PLANES];
     __shared__ const uint8_t  *s_ev[PTB_MAX_PLANES];
     __shared__ const double   *s_q64[PTB_MAX_PLANES];
     __shared__ int64_t        *d_event[PTB_MAX_PLANES];
@@ -790,7 +767,7 @@ __global__ void __launch_bounds__(256) k_gather(const __grid_constant__ GatherPa
     const int D = G.D;
     if (threadIdx.x < D) {
         const int d = threadIdx.x;
-        s_cr[d] = G.ws.s_cr[d]; s_q[d] = G.ws.s_q[d]; s_ev[d] = G.ws.s_ev[d]; s_q64[d] = G.ws.s_q64[d];
+        s_hit[d] = G.ws.s_hit[d]; s_ev[d] = G.ws.s_ev[d]; s_q64[d] = G.ws.s_q64[d];
         d_event[d] = G.slabs[d].event; d_col[d] = G.slabs[d].col; d_row[d] = G.slabs[d].row;
         d_charge[d] = G.slabs[d].charge; d_q64[d] = G.slabs[d].charge64;
     }
@@ -807,7 +784,8 @@ __global__ void __launch_bounds__(256) k_gather(const __grid_constant__ GatherPa
             src_l = G.ws.table[(unsigned long long)(D + 5 + lane) * G.n_groups + group];
             dst_l = B.hits[lane] + G.ws.prefix[(unsigned long long)lane * G.n_groups + group];
             if (n_l != 0 && (dst_l + n_l > G.slabs[lane].capacity || src_l + n_l > G.ws.cap[lane])) {
-                atomicOr(&G.totals->error, PTB_DEV_SLAB_OVERFLOW);
+                atomicOr(&G.totals->error, dst_l + n_l > G.slabs[lane].capacity ? PTB_DEV_SLAB_OVERFLOW
+                                                                                : PTB_DEV_SCRATCH_OVERFLOW);
                 n_l = 0;
             }
         }
@@ -832,11 +810,11 @@ __global__ void __launch_bounds__(256) k_gather(const __grid_constant__ GatherPa
             const unsigned long long src = __shfl_sync(FULL, src_l, d), dst = __shfl_sync(FULL, dst_l, d);
             if (w < total) {
                 const unsigned long long i = (unsigned long long)(w - first);
-                const uint32_t           cr = s_cr[d][src + i];
+                const uint2              hit = s_hit[d][src + i];
                 d_event[d][dst + i] = ev_base + (int64_t)s_ev[d][src + i];
-                d_col[d][dst + i] = (uint16_t)(cr & 0xffffu);
-                d_row[d][dst + i] = (uint16_t)(cr >> 16);
-                d_charge[d][dst + i] = s_q[d][src + i];
+                d_col[d][dst + i] = (uint16_t)(hit.x & 0xffffu);
+                d_row[d][dst + i] = (uint16_t)(hit.x >> 16);
+                d_charge[d][dst + i] = __uint_as_float(hit.y);
                 if (keep64) d_q64[d][dst + i] = s_q64[d][src + i];
             }
         }
@@ -963,13 +941,13 @@ __global__ void __launch_bounds__(256) k_dfma(double *out, int iters, double a, 
 
 }  // namespace ptb
 
-template <class Src, int S, int PC, bool KEEP64>
+template <class Src, int PC, bool KEEP64>
 static cudaError_t launch_digitise(unsigned blocks, cudaStream_t st, const ptb::ConfigK &c, const ptb::KParams &P,
                                    const Src &src)
 {
     using namespace ptb;
-    constexpr size_t smem = warp_shared_bytes(S, PC, KEEP64) * WARPS_PER_BLOCK;
-    auto             kern = k_digitise<Src, S, PC, KEEP64>;
+    constexpr size_t smem = warp_shared_bytes(PC) * WARPS_PER_BLOCK;
+    auto             kern = k_digitise<Src, PC, KEEP64>;
     cudaError_t      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -1041,11 +1019,9 @@ int ptb_create(const PtbBeam *beam, const PtbDevice *dev, int32_t n_dev, const P
 
     ConfigK &c = h->cfg;
     c.n_planes = n_dev;
-    c.stage_hits = (opt && opt->stage_hits > 0) ? opt->stage_hits : STAGE_HITS;
     c.pool_entries = (opt && opt->pool_entries > 0) ? opt->pool_entries : POOL_ENTRIES;
-    if (!((c.stage_hits == STAGE_HITS && c.pool_entries == POOL_ENTRIES) ||
-          (c.stage_hits == SMALL_STAGE && c.pool_entries == SMALL_POOL)))
-        return fail(h, PTB_E_INVALID, "stage_hits / pool_entries: built variants are 128/128 (default) and 8/96 (tests)");
+    if (c.pool_entries != POOL_ENTRIES && c.pool_entries != SMALL_POOL)
+        return fail(h, PTB_E_INVALID, "pool_entries: built variants are 128 (default) and 96 (tests)");
     c.energy = beam->energy;
     c.loc_x = beam->loc_x; c.sigma_x = beam->sigma_x;
     c.loc_y = beam->loc_y; c.sigma_y = beam->sigma_y;
@@ -1242,14 +1218,20 @@ const char *ptb_last_error(PtbHandle h) { return h ? h->err : "null handle"; }
 
 int32_t ptb_n_planes(PtbHandle h) { return h ? h->cfg.n_planes : 0; }
 
-int32_t ptb_stage_hits(PtbHandle h) { return h ? h->cfg.stage_hits : 0; }
+// rows of a plane's scratch slab: the caller's figure, or the default rule of include/ptb.h
+static unsigned long long scratch_rows_of(uint64_t capacity, uint64_t given)
+{
+    return given ? given : PTB_DEFAULT_SCRATCH_ROWS(capacity);
+}
 
-size_t ptb_workspace_bytes(PtbHandle h, uint64_t n, const uint64_t *capacity, uint32_t flags)
+size_t ptb_workspace_bytes(PtbHandle h, uint64_t n, const uint64_t *capacity, const uint64_t *scratch_rows,
+                           uint32_t flags)
 {
     if (!h) return 0;
-    unsigned long long cap[PTB_MAX_PLANES] = {0};
-    for (int d = 0; d < h->cfg.n_planes; ++d) cap[d] = capacity ? capacity[d] : 0;
-    return carve_workspace(h->cfg.n_planes, n, cap, flags, nullptr, nullptr);
+    unsigned long long rows[PTB_MAX_PLANES] = {0};
+    for (int d = 0; d < h->cfg.n_planes; ++d)
+        rows[d] = scratch_rows_of(capacity ? capacity[d] : 0, scratch_rows ? scratch_rows[d] : 0);
+    return carve_workspace(h->cfg.n_planes, n, rows, flags, nullptr, nullptr);
 }
 
 uint64_t ptb_launch_count(void) { return g_launches; }
@@ -1304,13 +1286,13 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
         return fail(h, PTB_E_INVALID, "injected variate tables incomplete for the requested flags");
     if (run->injected && (flags & PTB_TRACKS_FROM_TABLE) && !run->tracks.accepted && !run->injected->accepted)
         return fail(h, PTB_E_INVALID, "no trigger mask: neither the track table nor the injected tables carry one");
-    unsigned long long cap[PTB_MAX_PLANES] = {0};
+    unsigned long long cap[PTB_MAX_PLANES] = {0};   // rows of every plane's scratch slab
     if (flags & PTB_DIGITISE) {
         for (int d = 0; d < D; ++d) {
             const PtbHitSlab &s = run->slabs[d];
             if (!s.event || !s.col || !s.row || !s.charge || ((flags & PTB_KEEP_CHARGE64) && !s.charge64))
                 return fail(h, PTB_E_INVALID, "hit slab pointers missing");
-            cap[d] = s.capacity;
+            cap[d] = scratch_rows_of(s.capacity, run->scratch_rows[d]);
         }
     }
     KParams P;
@@ -1347,23 +1329,23 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
     if (tp) cudaEventRecord(tp[1], st);
     if (flags & PTB_DIGITISE) {
         const unsigned blocks = (unsigned)((P.n_groups + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-        const bool     small = c.stage_hits == SMALL_STAGE;
+        const bool     small = c.pool_entries == SMALL_POOL;
         if (run->injected) {
             InjectedSource src{*run->injected, run->first, run->n};
             if (small)
-                e = keep64 ? launch_digitise<InjectedSource, SMALL_STAGE, SMALL_POOL, true>(blocks, st, c, P, src)
-                           : launch_digitise<InjectedSource, SMALL_STAGE, SMALL_POOL, false>(blocks, st, c, P, src);
+                e = keep64 ? launch_digitise<InjectedSource, SMALL_POOL, true>(blocks, st, c, P, src)
+                           : launch_digitise<InjectedSource, SMALL_POOL, false>(blocks, st, c, P, src);
             else
-                e = keep64 ? launch_digitise<InjectedSource, STAGE_HITS, POOL_ENTRIES, true>(blocks, st, c, P, src)
-                           : launch_digitise<InjectedSource, STAGE_HITS, POOL_ENTRIES, false>(blocks, st, c, P, src);
+                e = keep64 ? launch_digitise<InjectedSource, POOL_ENTRIES, true>(blocks, st, c, P, src)
+                           : launch_digitise<InjectedSource, POOL_ENTRIES, false>(blocks, st, c, P, src);
         } else {
             PhiloxSource src{run->seed};
             if (small)
-                e = keep64 ? launch_digitise<PhiloxSource, SMALL_STAGE, SMALL_POOL, true>(blocks, st, c, P, src)
-                           : launch_digitise<PhiloxSource, SMALL_STAGE, SMALL_POOL, false>(blocks, st, c, P, src);
+                e = keep64 ? launch_digitise<PhiloxSource, SMALL_POOL, true>(blocks, st, c, P, src)
+                           : launch_digitise<PhiloxSource, SMALL_POOL, false>(blocks, st, c, P, src);
             else
-                e = keep64 ? launch_digitise<PhiloxSource, STAGE_HITS, POOL_ENTRIES, true>(blocks, st, c, P, src)
-                           : launch_digitise<PhiloxSource, STAGE_HITS, POOL_ENTRIES, false>(blocks, st, c, P, src);
+                e = keep64 ? launch_digitise<PhiloxSource, POOL_ENTRIES, true>(blocks, st, c, P, src)
+                           : launch_digitise<PhiloxSource, POOL_ENTRIES, false>(blocks, st, c, P, src);
         }
         ++g_launches;
         if (e != cudaSuccess) return fail_cuda(h, e, "k_digitise launch");

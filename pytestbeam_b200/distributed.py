@@ -73,7 +73,8 @@ def run_sharded(beam: dict, devices: list, materials: list, names: list, folder:
     hits = [0] * len(devices)
     for c0 in range(lo, lo + n, chunk):
         m = min(chunk, lo + n - c0)
-        r = sim.run(c0, m, seed=seed, bases_in=bases, capacities=sim.default_capacities(m))
+        r = sim.run(c0, m, seed=seed, bases_in=bases, capacities=sim.default_capacities(m),
+                        scratch_rows=sim.default_scratch_rows(m))
         bases = r.bases_out
         for d in range(len(devices)):
             parts[d].append(_packed_rows(sim, r.slabs[d]))

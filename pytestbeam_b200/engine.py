@@ -96,24 +96,23 @@ class RunResult:
 class Simulator:
     """One telescope set-up on one GPU."""
 
-    def __init__(self, beam: dict, devices: list, materials: list, device=None, stage_hits: int = 0,
-                 pool_entries: int = 0):
+    def __init__(self, beam: dict, devices: list, materials: list, device=None, pool_entries: int = 0):
         if not torch.cuda.is_available():
             raise PtbError("pytestbeam_b200 needs a CUDA device (sm_100a); there is no CPU path")
         self.lib = N.load()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.beam, self.devices, self.materials = dict(beam), list(devices), list(materials)
         self.D = len(devices)
-        self._opts = dict(stage_hits=int(stage_hits), pool_entries=int(pool_entries))
+        self._opts = dict(pool_entries=int(pool_entries))
         self._h = None
         self._create()
-        self._hits_per_particle = None
+        self._hits_per_particle = self._rows_per_particle = None
 
     # -- handle ------------------------------------------------------------------------------------
     def _create(self):
         self.close()
         h = C.c_void_p()
-        opt = N.PtbOptions(self._opts["stage_hits"], self._opts["pool_entries"], 0.0)
+        opt = N.PtbOptions(self._opts["pool_entries"], 0, 0.0)
         with torch.cuda.device(self.device):
             rc = self.lib.ptb_create(C.byref(N.pack_beam(self.beam)), N.pack_devices(self.devices, self.materials),
                                      self.D, C.byref(opt), C.byref(h))
@@ -134,10 +133,6 @@ class Simulator:
             self.close()
         except Exception:
             pass
-
-    @property
-    def stage_hits(self) -> int:
-        return int(self.lib.ptb_stage_hits(self._h))
 
     def _check(self, rc, what):
         if rc != 0:
@@ -164,9 +159,10 @@ class Simulator:
                 "z": f8(n * D), "time_stamp": torch.empty(n * D, dtype=torch.int64, device=self.device),
                 "eloss": f8(D * n), "accepted": torch.empty(n, dtype=torch.uint8, device=self.device)}
 
-    def workspace_bytes(self, n, capacities, flags) -> int:
+    def workspace_bytes(self, n, capacities, flags, scratch_rows=None) -> int:
         caps = (C.c_uint64 * self.D)(*[int(c) for c in capacities])
-        return int(self.lib.ptb_workspace_bytes(self._h, int(n), caps, int(flags)))
+        rows = (C.c_uint64 * self.D)(*[int(c) for c in scratch_rows]) if scratch_rows is not None else None
+        return int(self.lib.ptb_workspace_bytes(self._h, int(n), caps, rows, int(flags)))
 
     def new_bases(self) -> torch.Tensor:
         return torch.zeros(_BASES_WORDS, dtype=torch.int64, device=self.device)
@@ -176,15 +172,25 @@ class Simulator:
         if self._hits_per_particle is None:
             r = self.run(0, pilot, seed=seed, capacities=[pilot * 64] * self.D)
             self._hits_per_particle = np.array(r.totals["hits"], dtype=np.float64) / pilot
+            self._rows_per_particle = np.array(r.totals["reserved"], dtype=np.float64) / pilot
         return self._hits_per_particle
 
+    @staticmethod
+    def _with_margin(n, per_particle):
+        return [int(n * h * 1.05 + 8 * np.sqrt(n * max(h, 1e-3) * 30) + 4096) for h in per_particle]
+
     def default_capacities(self, n: int):
-        hpp = self.hits_per_particle()
-        return [int(n * h * 1.05 + 8 * np.sqrt(n * max(h, 1e-3) * 30) + 4096) for h in hpp]
+        """Slab rows per plane for n particles: the pilot's hits per particle plus a margin."""
+        return self._with_margin(n, self.hits_per_particle())
+
+    def default_scratch_rows(self, n: int):
+        """Scratch rows per plane for n particles (PtbRun.scratch_rows): the pilot's reserved rows plus a margin."""
+        self.hits_per_particle()
+        return self._with_margin(n, self._rows_per_particle)
 
     # -- one call of ptb_simulate --------------------------------------------------------------------
     def launch(self, first, n, *, seed=0, injected: Injected | None = None, flags=N.PTB_DIGITISE, slabs=None,
-               tracks=None, bases_in=None, bases_out=None, totals=None, workspace=None):
+               tracks=None, bases_in=None, bases_out=None, totals=None, workspace=None, scratch_rows=None):
         """Enqueue one ptb_simulate call on the current stream (no synchronisation)."""
         run = N.PtbRun()
         run.first, run.n, run.seed, run.flags = int(first), int(n), int(seed) & (2**64 - 1), int(flags)
@@ -209,6 +215,9 @@ class Simulator:
         run.totals = totals.data_ptr()
         run.workspace = workspace.data_ptr()
         run.workspace_bytes = workspace.numel()
+        if scratch_rows is not None:
+            for d, r in enumerate(scratch_rows):
+                run.scratch_rows[d] = int(r)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
             self._check(self.lib.ptb_simulate(self._h, C.byref(run), C.c_void_p(stream)), "ptb_simulate")
@@ -218,13 +227,14 @@ class Simulator:
         a = t.cpu().numpy()
         u = a.view(np.uint64)
         return {"hits": [int(v) for v in u[:D]], "accepted": int(u[32]), "time_sum": int(a[33]), "pairs": int(u[34]),
-                "inside": int(u[35]), "pixels": int(u[36]), "error": int(u[37] & 0xFFFFFFFF)}
+                "inside": int(u[35]), "pixels": int(u[36]), "error": int(u[37] & 0xFFFFFFFF),
+                "reserved": [int(v) for v in u[38:38 + D]]}
 
     def run(self, first, n, *, seed=0, injected=None, digitise=True, write_tracks=False, tracks_in=None,
-            keep_charge64=False, capacities=None, bases_in=None, zero_radius=False) -> RunResult:
+            keep_charge64=False, capacities=None, bases_in=None, zero_radius=False, scratch_rows=None) -> RunResult:
         """Simulate particles [first, first+n), synchronise and return trimmed device buffers.
 
-        Retries with exact slab sizes when the device reports a slab overflow (its totals stay exact).
+        Retries with exact slab / scratch sizes when the device reports an overflow (its totals stay exact).
         """
         first, n = int(first), int(n)
         flags = N.PTB_RECYCLE_SLABS   # every call of run() gets fresh slabs
@@ -245,16 +255,18 @@ class Simulator:
             tracks = tracks_in if tracks_in is not None else (self.alloc_tracks(n) if write_tracks else None)
             totals = torch.zeros(_TOTALS_WORDS, dtype=torch.int64, device=self.device)
             bases_out = self.new_bases()
-            ws = torch.empty(self.workspace_bytes(n, capacities, flags), dtype=torch.uint8, device=self.device)
+            ws = torch.empty(self.workspace_bytes(n, capacities, flags, scratch_rows), dtype=torch.uint8,
+                             device=self.device)
             self.launch(first, n, seed=seed, injected=injected, flags=flags, slabs=slabs, tracks=tracks,
-                        bases_in=bases_in, bases_out=bases_out, totals=totals, workspace=ws)
+                        bases_in=bases_in, bases_out=bases_out, totals=totals, workspace=ws, scratch_rows=scratch_rows)
             torch.cuda.synchronize(self.device)
             tot = self.decode_totals(totals, self.D)
             err = tot["error"]
             if err & N.PTB_DEV_BOX_TOO_LARGE:
                 raise PtbError("a cluster bounding box exceeded 2^20 pixels (check pitch / geometry)")
-            if err & N.PTB_DEV_SLAB_OVERFLOW:
+            if err & (N.PTB_DEV_SLAB_OVERFLOW | N.PTB_DEV_SCRATCH_OVERFLOW):
                 capacities = [max(int(h), 1) for h in tot["hits"]]
+                scratch_rows = [max(int(r), 1) for r in tot["reserved"]]
                 continue
             if digitise:
                 slabs = [{k: v[:tot["hits"][d]] for k, v in s.items()} for d, s in enumerate(slabs)]

@@ -39,7 +39,8 @@ def device_hits(beam: dict, devices: list, hit_data, log=None) -> list:
         bases = None
         for lo in range(0, n, CHUNK):
             m = min(CHUNK, n - lo)
-            r = sim.run(lo, m, seed=seed, bases_in=bases, capacities=sim.default_capacities(m))
+            r = sim.run(lo, m, seed=seed, bases_in=bases, capacities=sim.default_capacities(m),
+                        scratch_rows=sim.default_scratch_rows(m))
             bases = r.bases_out
             for d in range(D):
                 parts[d].append(_packed_rows(sim, r.slabs[d]))
@@ -70,7 +71,8 @@ def device_hits_from_arrays(sim: Simulator, x, y, eloss, seed: int, accepted=Non
                "eloss": torch.from_numpy(np.ascontiguousarray(eloss[:, lo:lo + m], dtype=np.float64)).to(dev)}
         if accepted is not None:
             tin["accepted"] = torch.from_numpy(np.ascontiguousarray(accepted[lo:lo + m], dtype=np.uint8)).to(dev)
-        r = sim.run(lo, m, seed=seed, tracks_in=tin, bases_in=bases, capacities=sim.default_capacities(m))
+        r = sim.run(lo, m, seed=seed, tracks_in=tin, bases_in=bases, capacities=sim.default_capacities(m),
+                        scratch_rows=sim.default_scratch_rows(m))
         bases = r.bases_out
         for d in range(D):
             parts[d].append(_packed_rows(sim, r.slabs[d]))

@@ -17,7 +17,7 @@ PTB_KEEP_CHARGE64 = 8
 PTB_RECYCLE_SLABS = 16
 PTB_ZERO_RADIUS = 32
 
-PTB_DEV_STAGE_OVERFLOW = 1
+PTB_DEV_SCRATCH_OVERFLOW = 1
 PTB_DEV_SLAB_OVERFLOW = 2
 PTB_DEV_BOX_TOO_LARGE = 4
 
@@ -41,7 +41,7 @@ class PtbDevice(C.Structure):
 
 
 class PtbOptions(C.Structure):
-    _fields_ = [("stage_hits", C.c_int32), ("pool_entries", C.c_int32), ("trigger_accept", C.c_double)]
+    _fields_ = [("pool_entries", C.c_int32), ("_pad", C.c_int32), ("trigger_accept", C.c_double)]
 
 
 class PtbInjected(C.Structure):
@@ -67,21 +67,27 @@ class PtbBases(C.Structure):
 class PtbTotals(C.Structure):
     _fields_ = [("hits", C.c_uint64 * PTB_MAX_PLANES), ("accepted", C.c_uint64), ("time_sum", C.c_int64),
                 ("pairs", C.c_uint64), ("inside", C.c_uint64), ("pixels", C.c_uint64), ("error", C.c_uint32),
-                ("_pad", C.c_uint32)]
+                ("_pad", C.c_uint32), ("reserved", C.c_uint64 * PTB_MAX_PLANES)]
 
 
 class PtbRun(C.Structure):
     _fields_ = [("first", C.c_uint64), ("n", C.c_uint64), ("seed", C.c_uint64), ("flags", C.c_uint32),
                 ("_pad", C.c_uint32), ("injected", C.POINTER(PtbInjected)), ("tracks", PtbTrackTable),
                 ("slabs", PtbHitSlab * PTB_MAX_PLANES), ("bases_in", C.c_void_p), ("bases_out", C.c_void_p),
-                ("totals", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+                ("totals", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+                ("scratch_rows", C.c_uint64 * PTB_MAX_PLANES)]
 
 
-EXPORTS = ("ptb_create", "ptb_destroy", "ptb_last_error", "ptb_n_planes", "ptb_stage_hits", "ptb_workspace_bytes",
+EXPORTS = ("ptb_create", "ptb_destroy", "ptb_last_error", "ptb_n_planes", "ptb_workspace_bytes",
            "ptb_prefix", "ptb_simulate", "ptb_pack_hits", "ptb_launch_count", "ptb_measure_fp64_peak",
            "ptb_timing_enable", "ptb_timing_read", "ptb_correlate")
 
 _lib = None
+
+
+def default_scratch_rows(capacity: int) -> int:
+    """PTB_DEFAULT_SCRATCH_ROWS of include/ptb.h."""
+    return 2 * int(capacity) + 4096
 
 
 def load() -> C.CDLL:
@@ -102,9 +108,8 @@ def load() -> C.CDLL:
     L.ptb_last_error.restype = C.c_char_p
     L.ptb_n_planes.argtypes = [C.c_void_p]
     L.ptb_n_planes.restype = C.c_int32
-    L.ptb_stage_hits.argtypes = [C.c_void_p]
-    L.ptb_stage_hits.restype = C.c_int32
-    L.ptb_workspace_bytes.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint32]
+    L.ptb_workspace_bytes.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                      C.c_uint32]
     L.ptb_workspace_bytes.restype = C.c_size_t
     L.ptb_prefix.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(PtbInjected), C.c_void_p,
                              C.c_void_p]

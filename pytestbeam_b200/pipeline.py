@@ -16,15 +16,17 @@ from .engine import _TOTALS_WORDS, PtbError, Simulator
 
 class ChunkPipeline:
     def __init__(self, sim: Simulator, chunk: int, *, n_buffers: int = 2, capacities=None, host: bool = False,
-                 seed: int = 0):
+                 seed: int = 0, scratch_rows=None):
         self.sim, self.chunk, self.seed = sim, int(chunk), int(seed)
         self.flags = N.PTB_DIGITISE | N.PTB_RECYCLE_SLABS
         self.caps = list(capacities) if capacities is not None else sim.default_capacities(self.chunk)
+        self.rows = list(scratch_rows) if scratch_rows is not None else sim.default_scratch_rows(self.chunk)
         dev = sim.device
         self.sets = []
         for _ in range(n_buffers):
             s = {"slabs": sim.alloc_slabs(self.caps),
-                 "ws": torch.empty(sim.workspace_bytes(self.chunk, self.caps, self.flags), dtype=torch.uint8, device=dev),
+                 "ws": torch.empty(sim.workspace_bytes(self.chunk, self.caps, self.flags, self.rows),
+                                   dtype=torch.uint8, device=dev),
                  "totals": torch.zeros(_TOTALS_WORDS, dtype=torch.int64, device=dev),
                  "done": torch.cuda.Event(), "copied": torch.cuda.Event()}
             if host:
@@ -43,7 +45,7 @@ class ChunkPipeline:
 
     def _launch(self, s, first, n):
         self.sim.launch(first, n, seed=self.seed, flags=self.flags, slabs=s["slabs"], bases_in=self.bases,
-                        bases_out=self.bases, totals=s["totals"], workspace=s["ws"])
+                        bases_out=self.bases, totals=s["totals"], workspace=s["ws"], scratch_rows=self.rows)
 
     # -- device-resident -------------------------------------------------------------------------------
     def run(self, first: int, n_chunks: int):

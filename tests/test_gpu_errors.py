@@ -54,7 +54,7 @@ def test_unsupported_options_and_geometry():
     from pytestbeam_b200.engine import Simulator
     beam, devices, materials, names = cfg.flatten(cfg.c1(100))
     with pytest.raises(ValueError, match="variants"):
-        Simulator(beam, devices, materials, stage_hits=77)
+        Simulator(beam, devices, materials, pool_entries=77)
     bad = [dict(d) for d in devices]
     bad[3]["z_position"] = bad[2]["z_position"]
     with pytest.raises(ValueError, match="z_position"):

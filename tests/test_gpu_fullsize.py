@@ -23,7 +23,7 @@ def _sums(sim, n_total, chunk, seed):
         m = min(chunk, n_total - first)
         s = pipe.sets[0]
         sim.launch(first, m, seed=seed, flags=pipe.flags, slabs=s["slabs"], bases_in=pipe.bases, bases_out=pipe.bases,
-                   totals=s["totals"], workspace=s["ws"])
+                   totals=s["totals"], workspace=s["ws"], scratch_rows=pipe.rows)
         tot = Simulator.decode_totals(s["totals"], D)
         assert tot["error"] == 0
         acc["accepted"] += tot["accepted"]

@@ -161,10 +161,9 @@ def test_geometry_is_refused_like_the_oracle(torch_cuda):
         Simulator(beam, devices, materials)
 
 
-def test_fine_pitch_planes_exercise_pool_rounds_and_stage_growth(torch_cuda):
+def test_fine_pitch_planes_exercise_pool_rounds_and_overflow_retries(torch_cuda):
     """4 um pixels and a zero threshold: ~100 hits per particle on one plane.  The profile pool no longer holds a
-    whole group (it is served in rounds) and the shared-memory stage is outgrown (the plane is replayed straight
-    into the scratch slab)."""
+    whole group (it is served in rounds), and undersized slabs / scratch rows are reported with the exact need."""
     from pytestbeam_b200 import config as cfg
     from oracle import cpu_oracle as co
     from pytestbeam_b200.engine import Simulator
@@ -179,18 +178,25 @@ def test_fine_pitch_planes_exercise_pool_rounds_and_stage_growth(torch_cuda):
     sim = Simulator(beam, devices, materials)
     res = sim.run(0, n, injected=H.injected_for(sim, run, 0, n), keep_charge64=True,
                   capacities=[64 * n] * len(devices))
-    assert len(run.hits[2]) / (n / 32) > 4 * sim.stage_hits   # far beyond what the stage holds per group
+    assert len(run.hits[2]) / (n / 32) > 512   # hundreds of hits per group and plane
     _compare_hits(res, run, len(devices))
-    tiny = Simulator(beam, devices, materials, stage_hits=8, pool_entries=96)   # every plane replays / many rounds
+    assert all(r >= h for r, h in zip(res.totals["reserved"], res.totals["hits"]))
+    tiny = Simulator(beam, devices, materials, pool_entries=96)   # more rounds per group
     res3 = tiny.run(0, n, injected=H.injected_for(tiny, run, 0, n), capacities=[64 * n] * len(devices))
     for d in range(len(devices)):
         assert res3.hits_numpy(d).tobytes() == res.hits_numpy(d).tobytes()
     assert res.totals["pixels"] == run.census["pixels"]
-    # undersized slabs: the device reports the exact need and the host retries
+    # undersized slabs (and with them the default scratch rows): the device reports the exact need, the host retries
     res2 = sim.run(0, n, injected=H.injected_for(sim, run, 0, n), capacities=[100] * len(devices))
-    assert res2.totals["hits"] == res.totals["hits"]
+    assert res2.totals["hits"] == res.totals["hits"] and res2.totals["reserved"] == res.totals["reserved"]
     for d in range(len(devices)):
         assert res2.hits_numpy(d).tobytes() == res.hits_numpy(d).tobytes()
+    # ample slabs, scratch rows one short of the need on every plane: same retry, same tables
+    short = [max(r - 1, 1) for r in res.totals["reserved"]]
+    res4 = sim.run(0, n, injected=H.injected_for(sim, run, 0, n), capacities=[64 * n] * len(devices),
+                   scratch_rows=short)
+    for d in range(len(devices)):
+        assert res4.hits_numpy(d).tobytes() == res.hits_numpy(d).tobytes()
 
 
 def test_one_million_electrons_deterministic_in_chunks(torch_cuda):

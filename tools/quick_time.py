@@ -7,25 +7,24 @@ from pytestbeam_b200.engine import Simulator, _TOTALS_WORDS
 
 name = sys.argv[1] if len(sys.argv) > 1 else "c1"
 beam, devices, materials, names = cfg.flatten(getattr(cfg, name)(1000))
-sim = Simulator(beam, devices, materials, stage_hits=int(os.environ.get("PTB_STAGE", 0)),
-                pool_entries=int(os.environ.get("PTB_POOL", 0)))
+sim = Simulator(beam, devices, materials, pool_entries=int(os.environ.get("PTB_POOL", 0)))
 hpp = sim.hits_per_particle()
-print("hits/particle", hpp.round(4), "total", hpp.sum().round(3), "stage", sim.stage_hits)
+print("hits/particle", hpp.round(4), "total", hpp.sum().round(3))
 for n in [int(v) for v in os.environ.get("PTB_NS", "1048576,4194304,10000000").split(",")]:
-    caps = sim.default_capacities(n)
+    caps, rows = sim.default_capacities(n), sim.default_scratch_rows(n)
     flags = N.PTB_DIGITISE | N.PTB_RECYCLE_SLABS
     slabs = sim.alloc_slabs(caps)
-    ws = torch.empty(sim.workspace_bytes(n, caps, flags), dtype=torch.uint8, device=sim.device)
+    ws = torch.empty(sim.workspace_bytes(n, caps, flags, rows), dtype=torch.uint8, device=sim.device)
     totals = torch.zeros(_TOTALS_WORDS, dtype=torch.int64, device=sim.device)
     bases = sim.new_bases()
     for it in range(2):
-        sim.launch(0, n, seed=7, flags=flags, slabs=slabs, bases_in=bases, bases_out=bases, totals=totals, workspace=ws)
+        sim.launch(0, n, seed=7, flags=flags, slabs=slabs, bases_in=bases, bases_out=bases, totals=totals, workspace=ws, scratch_rows=rows)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 3
     e0.record()
     for it in range(reps):
-        sim.launch(it * n, n, seed=7, flags=flags, slabs=slabs, bases_in=bases, bases_out=bases, totals=totals, workspace=ws)
+        sim.launch(it * n, n, seed=7, flags=flags, slabs=slabs, bases_in=bases, bases_out=bases, totals=totals, workspace=ws, scratch_rows=rows)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps

@@ -7,22 +7,22 @@ from pytestbeam_b200.engine import Simulator, _TOTALS_WORDS
 
 n = 4_194_304
 beam, devices, materials, names = cfg.flatten(cfg.c1(1000))
-sim = Simulator(beam, devices, materials, stage_hits=int(os.environ.get("PTB_STAGE", 0)), pool_entries=int(os.environ.get("PTB_POOL", 0)))
-caps = [int(n * 1.4) + 4096] * sim.D
+sim = Simulator(beam, devices, materials, pool_entries=int(os.environ.get("PTB_POOL", 0)))
+caps, rows = [int(n * 1.4) + 4096] * sim.D, sim.default_scratch_rows(n)
 slabs = sim.alloc_slabs(caps)
 tracks = sim.alloc_tracks(n)
 totals = torch.zeros(_TOTALS_WORDS, dtype=torch.int64, device=sim.device)
 bases = sim.new_bases()
 allflags = N.PTB_DIGITISE | N.PTB_RECYCLE_SLABS | N.PTB_WRITE_TRACKS
-ws = torch.empty(sim.workspace_bytes(n, caps, allflags), dtype=torch.uint8, device=sim.device)
+ws = torch.empty(sim.workspace_bytes(n, caps, allflags, rows), dtype=torch.uint8, device=sim.device)
 
 def timeit(label, flags, use_tracks):
     for _ in range(2):
-        sim.launch(0, n, seed=7, flags=flags, slabs=slabs, tracks=tracks if use_tracks else None, bases_in=bases, bases_out=bases, totals=totals, workspace=ws)
+        sim.launch(0, n, seed=7, flags=flags, slabs=slabs, tracks=tracks if use_tracks else None, bases_in=bases, bases_out=bases, totals=totals, workspace=ws, scratch_rows=rows)
     torch.cuda.synchronize()
     sim.timing(True)
     for _ in range(3):
-        sim.launch(0, n, seed=7, flags=flags, slabs=slabs, tracks=tracks if use_tracks else None, bases_in=bases, bases_out=bases, totals=totals, workspace=ws)
+        sim.launch(0, n, seed=7, flags=flags, slabs=slabs, tracks=tracks if use_tracks else None, bases_in=bases, bases_out=bases, totals=totals, workspace=ws, scratch_rows=rows)
     torch.cuda.synchronize()
     a, b, k = sim.timing_read()
     sim.timing(False)
