@@ -78,16 +78,33 @@ __host__ __device__ __forceinline__ void mulhilo(uint32_t a, uint32_t b, uint32_
 #endif
 }
 
-__host__ __device__ __forceinline__ U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1)
+// The ten round keys (key + r * Weyl constants) of a seed, worked out once on the host: as part of a kernel parameter
+// they sit in the constant bank and enter the round's XOR as an operand, instead of being re-derived by every call.
+struct PhiloxKeys {
+    uint32_t k0[10], k1[10];
+};
+
+__host__ __device__ inline PhiloxKeys philox_keys(uint64_t seed)
+{
+    PhiloxKeys k;
+    uint32_t   a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        k.k0[r] = a;
+        k.k1[r] = b;
+        a += 0x9E3779B9u;
+        b += 0xBB67AE85u;
+    }
+    return k;
+}
+
+__host__ __device__ __forceinline__ U4 philox4x32_10(U4 c, const PhiloxKeys &key)
 {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         uint32_t h0, l0, h1, l1;
         mulhilo(0xD2511F53u, c.x, h0, l0);
         mulhilo(0xCD9E8D57u, c.z, h1, l1);
-        c = U4{h1 ^ c.y ^ k0, l1, h0 ^ c.w ^ k1, l0};
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
+        c = U4{h1 ^ c.y ^ key.k0[r], l1, h0 ^ c.w ^ key.k1[r], l0};
     }
     return c;
 }
@@ -95,10 +112,9 @@ __host__ __device__ __forceinline__ U4 philox4x32_10(U4 c, uint32_t k0, uint32_t
 // draw sites of one particle; plane-dependent sites are SITE_PLANE + 4*plane + {STEP,DIG,PIX}
 enum : uint32_t { SITE_EVENT = 0, SITE_START = 1, SITE_PLANE = 4, SUB_STEP = 0, SUB_DIG = 1, SUB_PIX = 2 };
 
-__device__ __forceinline__ U4 philox_at(uint64_t seed, uint64_t particle, uint32_t site, uint32_t index)
+__device__ __forceinline__ U4 philox_at(const PhiloxKeys &seed, uint64_t particle, uint32_t site, uint32_t index)
 {
-    return philox4x32_10(U4{(uint32_t)particle, (uint32_t)(particle >> 32), site, index}, (uint32_t)seed,
-                         (uint32_t)(seed >> 32));
+    return philox4x32_10(U4{(uint32_t)particle, (uint32_t)(particle >> 32), site, index}, seed);
 }
 
 // 53-bit uniform in [0,1) the way numpy/numba build it from two words
@@ -139,7 +155,7 @@ __device__ __forceinline__ double log_gamma_kp1(double k)
 // deterministic (injected) and the production (Philox) mode run the very same physics code.
 // ---------------------------------------------------------------------------------------------------
 struct PhiloxSource {
-    uint64_t seed;
+    PhiloxKeys seed;
 
     __device__ bool accepted(const ConfigK &cfg, uint64_t k) const
     {

@@ -120,6 +120,7 @@ static size_t carve_workspace(int D, unsigned long long n, const unsigned long l
 
 // shared memory of one warp: the per-particle cluster descriptors
 struct WarpShared {
+    double   in[2][3][32];   // (x, y, energy loss) of the current and the next plane, filled by cp.async
     double   x[32], y[32], rx[32], ry[32], q[32], inx[32], iny[32], seedq[32];
     double   yx[32], yy[32];   // RN(1/rx^2), RN(1/ry^2) for div_rcp
     int      clo[32], rlo[32];                         // trimmed box: first column / row ...
@@ -137,6 +138,15 @@ __host__ __device__ constexpr size_t warp_shared_bytes(int pool)
     b += (size_t)pool * 16;               // profile value and ellipse term per box column / row
     return (b + 15) / 16 * 16;
 }
+
+// 8-byte asynchronous global -> shared copy (LDGSTS) and its completion
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ unsigned lanemask_lt()
 {
@@ -305,21 +315,34 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
     unsigned long long n_pairs = 0, n_inside = 0, n_pixels = 0;
     unsigned           err = 0;
 
+    // Digitisation inputs (x, y, energy loss) of plane d: fetched one plane ahead with asynchronous copies into a
+    // double-buffered shared-memory slot of the lane, so that the loads' latency hides behind the previous plane's
+    // work without holding registers.
+    auto fetch = [&](int d) {
+        double *slot = &W.in[d & 1][0][lane];
+        if (from_table) {
+            if (valid) {
+                cp_async8(slot, &P.trk.x[kl * D + d]);
+                cp_async8(slot + 32, &P.trk.y[kl * D + d]);
+                cp_async8(slot + 64, &P.trk.eloss[(unsigned long long)d * P.n + kl]);
+            } else {
+                slot[0] = slot[32] = slot[64] = 0.0;
+            }
+        } else {
+            cp_async8(slot, &park[d * 96]);
+            cp_async8(slot + 32, &park[d * 96 + 32]);
+            cp_async8(slot + 64, &park[d * 96 + 64]);
+        }
+        cp_async_commit();
+    };
+    fetch(0);
+
 #pragma unroll 1
     for (int d = 0; d < D; ++d) {
         const PlaneK &pl = cfg.pl[d];
-        double        x = 0, y = 0, eloss = 0;
-        if (from_table) {
-            if (valid) {
-                x = P.trk.x[kl * D + d];
-                y = P.trk.y[kl * D + d];
-                eloss = P.trk.eloss[(unsigned long long)d * P.n + kl];
-            }
-        } else {
-            x = park[d * 96];
-            y = park[d * 96 + 32];
-            eloss = park[d * 96 + 64];
-        }
+        cp_async_wait_all();   // every lane reads only what it copied itself
+        const double x = W.in[d & 1][0][lane], y = W.in[d & 1][1][lane], eloss = W.in[d & 1][2][lane];
+        if (d + 1 < D) fetch(d + 1);
 
         // ---- cluster descriptors, one lane per particle (main/device.py:137-140, 241-266) -----------
         int  cnt = 0;          // pixels of the reference's bounding box (census)
@@ -1256,7 +1279,7 @@ int ptb_prefix(PtbHandle h, uint64_t first, uint64_t n, uint64_t seed, const Ptb
         InjectedSource src{*inj, first, n};
         k_prefix<InjectedSource><<<blocks, 256, 0, st>>>(h->cfg, first, n, src, (long long *)out_dev);
     } else {
-        PhiloxSource src{seed};
+        PhiloxSource src{philox_keys(seed)};
         k_prefix<PhiloxSource><<<blocks, 256, 0, st>>>(h->cfg, first, n, src, (long long *)out_dev);
     }
     ++g_launches;
@@ -1321,7 +1344,7 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
         if (run->injected)
             k_tracks<InjectedSource><<<tb, TRACK_BLOCK, 0, st>>>(c, P, InjectedSource{*run->injected, run->first, run->n});
         else
-            k_tracks<PhiloxSource><<<tb, TRACK_BLOCK, 0, st>>>(c, P, PhiloxSource{run->seed});
+            k_tracks<PhiloxSource><<<tb, TRACK_BLOCK, 0, st>>>(c, P, PhiloxSource{philox_keys(run->seed)});
         ++g_launches;
         e = cudaGetLastError();
         if (e != cudaSuccess) return fail_cuda(h, e, "k_tracks launch");
@@ -1339,7 +1362,7 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
                 e = keep64 ? launch_digitise<InjectedSource, POOL_ENTRIES, true>(blocks, st, c, P, src)
                            : launch_digitise<InjectedSource, POOL_ENTRIES, false>(blocks, st, c, P, src);
         } else {
-            PhiloxSource src{run->seed};
+            PhiloxSource src{philox_keys(run->seed)};
             if (small)
                 e = keep64 ? launch_digitise<PhiloxSource, SMALL_POOL, true>(blocks, st, c, P, src)
                            : launch_digitise<PhiloxSource, SMALL_POOL, false>(blocks, st, c, P, src);

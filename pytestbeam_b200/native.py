@@ -87,7 +87,7 @@ _lib = None
 
 def default_scratch_rows(capacity: int) -> int:
     """PTB_DEFAULT_SCRATCH_ROWS of include/ptb.h."""
-    return 2 * int(capacity) + 4096
+    return 4 * int(capacity) + 4096
 
 
 def load() -> C.CDLL:
