@@ -262,12 +262,18 @@ struct PhiloxSource {
         normal_pair_f32(w.x, w.y, zrx, zry);
         normal_pair_f32(w.z, w.w, zseed, spare);
     }
-    // noise normals of the q-th group of four candidate pixels of particle k on plane d: one Philox block
-    __device__ void pixel4(uint64_t k, int d, uint32_t q, const int * /*jf*/, int /*count*/, double z[4]) const
+    // noise normal of the p-th candidate pixel of particle k on plane d: four consecutive pixels share one Philox
+    // block, every lane works out the one normal it needs
+    __device__ double pixel(uint64_t k, int d, uint32_t p, int /*jf*/) const
     {
-        U4 w = philox_at(seed, k, SITE_PLANE + 4 * d + SUB_PIX, q);
-        normal_pair_f32(w.x, w.y, z[0], z[1]);
-        normal_pair_f32(w.z, w.w, z[2], z[3]);
+        const U4       w = philox_at(seed, k, SITE_PLANE + 4 * d + SUB_PIX, p >> 2);
+        const uint32_t a = (p & 2u) ? w.z : w.x, b = (p & 2u) ? w.w : w.y;
+        const float    u = fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // as normal_pair_f32
+        const float    v = fmaf((float)b, 1.4629180792671596e-09f, 7.3145903963357980e-10f);
+        const float    r = __fsqrt_rn(-1.3862943611198906f * __log2f(u));
+        float          s, c;
+        __sincosf(v, &s, &c);
+        return (double)(r * ((p & 1u) ? s : c));
     }
 };
 
@@ -299,12 +305,10 @@ struct InjectedSource {
         const double *p = v.dig_z + v.dig_off[(uint64_t)d * (n + 1) + (k - first)];
         zrx = p[0]; zry = p[1]; zseed = p[2];
     }
-    // jf[i]: index of the pixel in the reference's walk over its full bounding box = draw order
-    __device__ void pixel4(uint64_t k, int d, uint32_t /*q*/, const int *jf, int count, double z[4]) const
+    // jf: index of the pixel in the reference's walk over its full bounding box = draw order
+    __device__ double pixel(uint64_t k, int d, uint32_t /*p*/, int jf) const
     {
-        const double *p = v.dig_z + v.dig_off[(uint64_t)d * (n + 1) + (k - first)] + 3;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) z[i] = i < count ? p[jf[i]] : 0.0;
+        return v.dig_z[v.dig_off[(uint64_t)d * (n + 1) + (k - first)] + 3 + jf];
     }
 };
 

@@ -7,8 +7,8 @@
 //               (x, y, energy loss) of the group to k_digitise through a coalesced, L2-resident park.
 //   k_digitise  one warp per group, warp-cooperative: the 32 particles' pixel boxes are flattened into work
 //               lists that the lanes walk 32 items at a time (first the separable per-column / per-row
-//               profiles, then four pixels per lane), and hits are compacted in reference order (particle,
-//               column, row) with warp scans.  Only the box pixels that can pass the ellipse test and lie on the
+//               profiles, then the pixels, one per lane), and hits are compacted in reference order (particle,
+//               column, row) with ballots.  Only the box pixels that can pass the ellipse test and lie on the
 //               matrix are evaluated.  Before the pixels of a plane are evaluated the group reserves room for
 //               all of them (an upper bound on its hits) in that plane's scratch slab with one atomic, so
 //               that the kept pixels go straight to their place in the segment.  (Two kernels rather than
@@ -126,7 +126,8 @@ struct WarpShared {
     int      clo[32], rlo[32];                         // trimmed box: first column / row ...
     uint8_t  ncols[32], nrows[32];                     // ... and extent (ncols + nrows <= pool entries <= 128)
     int      jbase[32], nrfull[32];                    // position of the trimmed box inside the reference's box
-    int      pprefix[32], qprefix[32], poff[32];   // work-list prefixes: profile entries, pixel quads; pool offset
+    int      pprefix[32], qprefix[32], poff[32];   // work-list prefixes: profile entries, pixels; pool offset
+    float    rnr[32];                              // 1 / rows of the trimmed box
     uint32_t seedcr[32];
     uint8_t  evoff[32];
 };
@@ -413,6 +414,7 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
                 W.yx[lane] = yx; W.yy[lane] = yy;
                 W.clo[lane] = c_lo + ca; W.rlo[lane] = r_lo + ra; W.ncols[lane] = (uint8_t)ncT; W.nrows[lane] = (uint8_t)nrT;
                 W.jbase[lane] = ca * (int)nr + ra; W.nrfull[lane] = (int)nr;
+                W.rnr[lane] = __fdividef(1.0f, (float)max(nrT, 1));
                 W.seedcr[lane] = (uint32_t)sc | ((uint32_t)sr << 16);
             }
         }
@@ -447,15 +449,15 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
             const int      o_end = (fits == FULL) ? 32 : __ffs(~fits) - 1;  // first lane that does not fit
             const bool     mine = lane >= o_begin && lane < o_end;
             const int      my_prof = mine ? nprof : 0;
-            const int      my_quads = (mine && inside) ? max((cntT + 3) >> 2, 1) : 0;
-            int            qin = my_quads;
+            const int      my_pix = (mine && inside) ? max(cntT, 1) : 0;   // an empty box keeps a slot for the fallback
+            int            qin = my_pix;
 #pragma unroll
             for (int s = 1; s < 32; s <<= 1) {
                 int o = __shfl_up_sync(FULL, qin, s);
                 if (lane >= s) qin += o;
             }
             const int prof_total = __shfl_sync(FULL, pin, o_end - 1);   // o_end > o_begin: one box always fits
-            const int quad_total = __shfl_sync(FULL, qin, 31);
+            const int pix_total = __shfl_sync(FULL, qin, 31);
             __syncwarp();
             W.pprefix[lane] = mine ? pin : (lane < o_begin ? 0 : prof_total);
             W.qprefix[lane] = qin;
@@ -499,12 +501,14 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
                 first_round = false;
             }
 
-            // ---- phase B: pixels in (particle, column, row) order, four per lane and step -----------------
+            // ---- phase B: the pixels of the round in (particle, column, row) order, one per lane and step.  The
+            //      order of the work list is the order of the output, so a kept pixel's place in the group's segment is
+            //      a ballot and a population count away.
             int carry_owner = -1;   // particle whose pixels straddle the previous step, and its kept count
             int carry_kept = 0;
-            for (int w0 = 0; w0 < quad_total; w0 += 32) {
+            for (int w0 = 0; w0 < pix_total; w0 += 32) {
                 const int  w = w0 + lane;
-                const bool has = w < quad_total;
+                const bool has = w < pix_total;
                 int        own = 0;
 #pragma unroll
                 for (int s = 16; s > 0; s >>= 1)
@@ -512,98 +516,55 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
                 own = has ? own : 31;
                 const int excl = own ? W.qprefix[own - 1] : 0;
                 const int end = W.qprefix[own];
-                const int qi = w - excl;            // quad index inside the particle's box
-                int       kq = 0;                   // pixels of this quad that survive
-                unsigned  kmask = 0;                // ... and which ones
-                double    hq[4];
-                uint32_t  hcr[4];
+                const int p = w - excl;             // index of the pixel in its particle's trimmed box, column-major
+                bool      keep = false;
+                double    hq = 0.0;
+                uint32_t  hcr = 0;
                 if (has) {
-                    const int    ncl = W.ncols[own], nrw = W.nrows[own];
-                    const int    box = ncl * nrw;            // trimmed box: may be empty (seed fallback only)
-                    const int    po = W.poff[own];
-                    const double qtot = W.q[own];
-                    const int    clo = W.clo[own], rlo = W.rlo[own];
-                    const int    jbase = W.jbase[own], nrf = W.nrfull[own];
-                    // column / row of the quad's first pixel; the following ones advance row-first
-                    int ci = (4 * qi) / max(nrw, 1);
-                    int ri = 4 * qi - ci * nrw;
-                    // index of every pixel in the reference's (column-major) walk over its full box: the injected
-                    // noise variates are keyed by it
-                    int jf[4];
-                    {
-                        int c2 = ci, r2 = ri;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            jf[i] = jbase + c2 * nrf + r2;
-                            if (++r2 == nrw) {
-                                r2 = 0;
-                                ++c2;
-                            }
-                        }
-                    }
-                    double zn[4];
-                    src.pixel4(P.first + group * 32 + own, d, (uint32_t)qi, jf, min(4, box - 4 * qi), zn);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        if (4 * qi + i < box) {
-                            const int    col = clo + ci, row = rlo + ri;
-                            const double noise = 0.0 + pl.noise_sigma * zn[i];
-                            const double signal = qtot * (pool_g[po + ci] * pool_g[po + ncl + ri]);
-                            const double charge = (signal + noise) * 1e-3 * pl.pitch_c * pl.pitch_r;  // device.py:275-288
-                            // the matrix bounds are implied by the clipped box; a zero radius makes the ellipse terms
-                            // NaN or inf, which fail the comparison as rx > 0 and ry > 0 would (device.py:289-295)
-                            const bool keep = charge >= pl.thr_ke && pool_e[po + ci] + pool_e[po + ncl + ri] <= 1.0;
-                            hq[i] = charge;
-                            hcr[i] = (uint32_t)col | ((uint32_t)row << 16);
-                            if (keep) {
-                                kmask |= 1u << i;
-                                ++kq;
-                            }
-                            if (++ri == nrw) {
-                                ri = 0;
-                                ++ci;
-                            }
-                        }
+                    const int ncl = W.ncols[own], nrw = W.nrows[own];
+                    if (p < ncl * nrw) {            // the trimmed box may be empty (seed fallback only)
+                        const int po = W.poff[own];
+                        // p / nrw through the reciprocal: (p + 0.5) / nrw stays >= 1/256 away from an integer, far
+                        // more than the rounding of the product for p < 4096
+                        const int ci = __float2int_rz(((float)p + 0.5f) * W.rnr[own]);
+                        const int ri = p - ci * nrw;
+                        // index of the pixel in the reference's (column-major) walk over its full box: the injected
+                        // noise variates are keyed by it
+                        const int    jf = W.jbase[own] + ci * W.nrfull[own] + ri;
+                        const double zn = src.pixel(P.first + group * 32 + own, d, (uint32_t)p, jf);
+                        const double noise = 0.0 + pl.noise_sigma * zn;
+                        const double signal = W.q[own] * (pool_g[po + ci] * pool_g[po + ncl + ri]);
+                        hq = (signal + noise) * 1e-3 * pl.pitch_c * pl.pitch_r;   // device.py:275-288
+                        // the matrix bounds are implied by the clipped box; a zero radius makes the ellipse terms
+                        // NaN or inf, which fail the comparison as rx > 0 and ry > 0 would (device.py:289-295)
+                        keep = hq >= pl.thr_ke && pool_e[po + ci] + pool_e[po + ncl + ri] <= 1.0;
+                        hcr = (uint32_t)(W.clo[own] + ci) | ((uint32_t)(W.rlo[own] + ri) << 16);
                     }
                 }
-                // kept pixels of my particle so far: the lanes of one particle are contiguous in the work list
-                int kin = kq;
-#pragma unroll
-                for (int s = 1; s < 32; s <<= 1) {
-                    int o = __shfl_up_sync(FULL, kin, s);
-                    if (lane >= s) kin += o;
-                }
-                const int lo_lane = has ? max(excl - w0, 0) : 0;
-                const int hi_lane = has ? min(end - 1 - w0, 31) : 0;
-                const int k_hi = __shfl_sync(FULL, kin, hi_lane);
-                const int k_lo = __shfl_sync(FULL, kin, max(lo_lane - 1, 0));
-                const int kept_here = k_hi - (lo_lane > 0 ? k_lo : 0);
-                const int kept_before = (own == carry_owner) ? carry_kept : 0;
-                // seed fallback (main/device.py:299-302): the lane holding the particle's last quad emits the
-                // seed pixel when nothing in the box survived (its own kq is then 0)
+                // kept pixels of my particle in this step: the lanes of one particle are contiguous in the work list
+                const unsigned kballot = __ballot_sync(FULL, keep);
+                const int      lo_lane = has ? max(excl - w0, 0) : 0;
+                const int      hi_lane = has ? min(end - 1 - w0, 31) : 0;
+                const unsigned span = (2u << hi_lane) - (1u << lo_lane);   // lanes lo..hi (2u << 31 wraps to 0)
+                const int      kept_here = __popc(kballot & span);
+                const int      kept_before = (own == carry_owner) ? carry_kept : 0;
+                // seed fallback (main/device.py:299-302): the lane holding the particle's last pixel emits the seed
+                // pixel when nothing in the box survived (its own pixel was not kept either, then)
                 const bool fb = has && w == end - 1 && kept_before + kept_here == 0 && W.seedq[own] >= pl.thr_ke;
                 if (fb) {
-                    hq[0] = W.seedq[own];
-                    hcr[0] = W.seedcr[own];
-                    kmask = 1u;
+                    hq = W.seedq[own];
+                    hcr = W.seedcr[own];
                 }
-                const unsigned fbmask = __ballot_sync(FULL, fb);
-                // position = hits of earlier steps + kept pixels of lower lanes + fallbacks of lower lanes
-                const unsigned pos = (unsigned)(n_plane + (kin - kq) + __popc(fbmask & lanemask_lt()));
-                const unsigned wmask = room ? kmask : 0u;
-                const unsigned ev_off = W.evoff[own];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if (wmask & (1u << i)) {
-                        const unsigned at = pos + __popc(kmask & ((1u << i) - 1u));
-                        seg_hit[at] = make_uint2(hcr[i], __float_as_uint((float)hq[i]));
-                        seg_ev[at] = (uint8_t)ev_off;
-                        if (keep64) seg_q64[at] = hq[i];
-                    }
+                const unsigned emask = kballot | __ballot_sync(FULL, fb);
+                if ((keep || fb) && room) {
+                    const unsigned at = (unsigned)n_plane + __popc(emask & lanemask_lt());
+                    seg_hit[at] = make_uint2(hcr, __float_as_uint((float)hq));
+                    seg_ev[at] = W.evoff[own];
+                    if (keep64) seg_q64[at] = hq;
                 }
-                n_plane += __shfl_sync(FULL, kin, 31) + __popc(fbmask);
+                n_plane += __popc(emask);
                 // carry for a particle that continues into the next step
-                const int last_lane = min(quad_total - w0, 32) - 1;
+                const int last_lane = min(pix_total - w0, 32) - 1;
                 carry_owner = __shfl_sync(FULL, own, last_lane);
                 carry_kept = __shfl_sync(FULL, kept_before + kept_here, last_lane);
             }
