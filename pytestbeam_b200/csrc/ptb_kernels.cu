@@ -34,7 +34,7 @@ namespace ptb {
 constexpr int      WARPS_PER_BLOCK = 4;                 // k_digitise
 constexpr int      BLOCK = 32 * WARPS_PER_BLOCK;
 #ifndef PTB_DIGI_MIN_BLOCKS
-#define PTB_DIGI_MIN_BLOCKS 7
+#define PTB_DIGI_MIN_BLOCKS 8
 #endif
 #ifndef PTB_TRACK_MIN_BLOCKS
 #define PTB_TRACK_MIN_BLOCKS 7
@@ -120,16 +120,19 @@ static size_t carve_workspace(int D, unsigned long long n, const unsigned long l
 
 // shared memory of one warp: the per-particle cluster descriptors
 struct WarpShared {
-    double   in[2][3][32];   // (x, y, energy loss) of the current and the next plane, filled by cp.async
+    double   in[3][32];      // (x, y, energy loss) of the next plane, filled by cp.async while the current one is worked on
     double   x[32], y[32], rx[32], ry[32], q[32], inx[32], iny[32], seedq[32];
     double   yx[32], yy[32];   // RN(1/rx^2), RN(1/ry^2) for div_rcp
     int      clo[32], rlo[32];                         // trimmed box: first column / row ...
     uint8_t  ncols[32], nrows[32];                     // ... and extent (ncols + nrows <= pool entries <= 128)
     int      jbase[32], nrfull[32];                    // position of the trimmed box inside the reference's box
-    int      pprefix[32], qprefix[32], poff[32];   // work-list prefixes: profile entries, pixels; pool offset
+    int      qexcl[32], qprefix[32], poff[32];     // work lists: first / one-past-last pixel slot, pool offset
+    uint8_t  ownA[32], ownB[32];                   // the particles that own profile entries / pixel slots, in order
     float    rnr[32];                              // 1 / rows of the trimmed box
     uint32_t seedcr[32];
-    uint8_t  evoff[32];
+    uint8_t  evoff[32], accb[32];
+    unsigned long long cen_pixels;                 // census of the group, kept by lane 0
+    unsigned cen_pairs, cen_inside;
 };
 
 // bytes of one warp's region: descriptors, profile pool (2 doubles per column / row)
@@ -310,17 +313,28 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
         accmask = __ballot_sync(FULL, valid && (P.trk.accepted ? P.trk.accepted[kl] != 0 : src.accepted(cfg, k)));
     else
         accmask = P.ws.accmask[group];
-    const bool acc = (accmask >> lane) & 1u;
+    // the trigger bit of the lane lives in shared memory (read back only on triggered planes) rather than in a
+    // register that would have to survive the whole plane loop
+    W.accb[lane] = (uint8_t)((accmask >> lane) & 1u);
     W.evoff[lane] = (uint8_t)__popc(accmask & lanemask_lt());   // accepted particles of this group before me
+    if (from_table && lane == 0) {
+        P.ws.table[(unsigned long long)(D + 0) * P.n_groups + group] = (unsigned long long)__popc(accmask);
+        P.ws.table[(unsigned long long)(D + 1) * P.n_groups + group] = 0;
+    }
 
-    unsigned long long n_pairs = 0, n_inside = 0, n_pixels = 0;
-    unsigned           err = 0;
+    // census of the group (digitised pairs, in-acceptance pairs, box pixels): summed over the warp plane by plane and
+    // kept in shared memory by lane 0, so that it costs no registers across the plane loop
+    if (lane == 0) {
+        W.cen_pairs = W.cen_inside = 0u;
+        W.cen_pixels = 0ull;
+    }
+    unsigned err = 0;
 
-    // Digitisation inputs (x, y, energy loss) of plane d: fetched one plane ahead with asynchronous copies into a
-    // double-buffered shared-memory slot of the lane, so that the loads' latency hides behind the previous plane's
-    // work without holding registers.
+    // Digitisation inputs (x, y, energy loss) of plane d: fetched one plane ahead with asynchronous copies into the
+    // lane's shared-memory slot (free again as soon as the current plane's values sit in registers), so that the
+    // loads' latency hides behind the previous plane's work without holding registers.
     auto fetch = [&](int d) {
-        double *slot = &W.in[d & 1][0][lane];
+        double *slot = &W.in[0][lane];
         if (from_table) {
             if (valid) {
                 cp_async8(slot, &P.trk.x[kl * D + d]);
@@ -342,7 +356,7 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
     for (int d = 0; d < D; ++d) {
         const PlaneK &pl = cfg.pl[d];
         cp_async_wait_all();   // every lane reads only what it copied itself
-        const double x = W.in[d & 1][0][lane], y = W.in[d & 1][1][lane], eloss = W.in[d & 1][2][lane];
+        const double x = W.in[0][lane], y = W.in[1][lane], eloss = W.in[2][lane];
         if (d + 1 < D) fetch(d + 1);
 
         // ---- cluster descriptors, one lane per particle (main/device.py:137-140, 241-266) -----------
@@ -350,8 +364,8 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
         int  nprof = 0;        // columns + rows that can pass the ellipse test and lie on the matrix
         int  cntT = 0;         // pixels of that trimmed box: the only ones that can become hits
         bool inside = false;   // seed pixel on the matrix: the particle owns a work item even with an empty box
-        if (valid && (acc || !pl.triggered)) {
-            ++n_pairs;
+        const bool digitised = valid && (!pl.triggered || W.accb[lane]);
+        if (digitised) {
             const double sig = cloud_sigma(cfg, eloss);
             double       zrx, zry, zseed;
             src.dig(k, d, zrx, zry, zseed);
@@ -361,7 +375,6 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
             const int    sc = pixel_index(x, pl.delta_x, pl.pitch_c, pl.rcp_pc, pl.half_nc);
             const int    sr = pixel_index(y, pl.delta_y, pl.pitch_r, pl.rcp_pr, pl.half_nr);
             if (sc >= 1 && sc <= pl.ncol && sr >= 1 && sr <= pl.nrow) {
-                ++n_inside;
                 inside = true;
                 const double inx = profile_norm(profile_radius(rx));
                 const double iny = profile_norm(profile_radius(ry));
@@ -418,7 +431,15 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
                 W.seedcr[lane] = (uint32_t)sc | ((uint32_t)sr << 16);
             }
         }
-        n_pixels += (unsigned)cnt;
+        {
+            const unsigned pairs_d = __popc(__ballot_sync(FULL, digitised)), inside_d = __popc(__ballot_sync(FULL, inside));
+            const unsigned pixels_d = __reduce_add_sync(FULL, (unsigned)cnt);   // <= 32 boxes of <= 2^20 pixels
+            if (lane == 0) {
+                W.cen_pairs += pairs_d;
+                W.cen_inside += inside_d;
+                W.cen_pixels += pixels_d;
+            }
+        }
 
         // ---- room for every pixel that can become a hit (all trimmed-box pixels, or the seed fallback), reserved
         //      in the plane's scratch slab before the pixels are evaluated: the kept ones go straight to their place
@@ -438,42 +459,57 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
         int o_begin = 0;
         bool first_round = true;
         while (true) {
-            // inclusive prefix of the profile entries of lanes >= o_begin
-            int pin = (lane >= o_begin) ? nprof : 0;
+            // inclusive prefixes of the profile entries (<= 128 per particle: 13 bits hold the warp's sum) and of the
+            // pixel slots (<= 4096 per particle) of lanes >= o_begin, scanned as one packed word
+            unsigned both = (lane >= o_begin) ? (unsigned)nprof | ((inside ? (unsigned)max(cntT, 1) : 0u) << 13) : 0u;
 #pragma unroll
             for (int s = 1; s < 32; s <<= 1) {
-                int o = __shfl_up_sync(FULL, pin, s);
-                if (lane >= s) pin += o;
+                unsigned o = __shfl_up_sync(FULL, both, s);
+                if (lane >= s) both += o;
             }
+            const int      pin = (int)(both & 0x1fffu);
             const unsigned fits = __ballot_sync(FULL, pin <= PC);           // a prefix: monotone in the lane
             const int      o_end = (fits == FULL) ? 32 : __ffs(~fits) - 1;  // first lane that does not fit
             const bool     mine = lane >= o_begin && lane < o_end;
             const int      my_prof = mine ? nprof : 0;
             const int      my_pix = (mine && inside) ? max(cntT, 1) : 0;   // an empty box keeps a slot for the fallback
-            int            qin = my_pix;
+            int            qin = (int)(both >> 13);
+            if (o_end < 32) {   // the round ends early: the pixel slots of the lanes left out do not count
+                qin = my_pix;
 #pragma unroll
-            for (int s = 1; s < 32; s <<= 1) {
-                int o = __shfl_up_sync(FULL, qin, s);
-                if (lane >= s) qin += o;
+                for (int s = 1; s < 32; s <<= 1) {
+                    int o = __shfl_up_sync(FULL, qin, s);
+                    if (lane >= s) qin += o;
+                }
             }
             const int prof_total = __shfl_sync(FULL, pin, o_end - 1);   // o_end > o_begin: one box always fits
             const int pix_total = __shfl_sync(FULL, qin, 31);
+            // Work-list look-up: the owner of item t is the first particle (with items) whose inclusive prefix exceeds
+            // t.  The particles with items are listed once per round; inside a step every such particle whose items end
+            // there raises the bit of its last item, so that a lane finds its owner's rank by counting the bits below
+            // its own position -- one warp-wide OR and one shared-memory read instead of a five-level binary search.
+            const unsigned actA = __ballot_sync(FULL, my_prof > 0), actB = __ballot_sync(FULL, my_pix > 0);
             __syncwarp();
-            W.pprefix[lane] = mine ? pin : (lane < o_begin ? 0 : prof_total);
+            if (my_prof > 0) W.ownA[__popc(actA & lanemask_lt())] = (uint8_t)lane;
+            if (my_pix > 0) W.ownB[__popc(actB & lanemask_lt())] = (uint8_t)lane;
+            W.qexcl[lane] = qin - my_pix;
             W.qprefix[lane] = qin;
             W.poff[lane] = pin - my_prof;
+            const int endA = my_prof > 0 ? pin : 0;   // one past my last profile entry; 0: none
             __syncwarp();
 
             // ---- phase A: the separable parts of every pixel of the round, once per column and per row:
             //      profile = 1/(sigma sqrt(2pi)) exp(-(d^2)/(2 sigma^2))  (main/device.py:378)
             //      ellipse = d^2 / r^2                                    (main/device.py:291-293)
+            int doneA = 0;   // particles whose entries end before this step
             for (int t0 = 0; t0 < prof_total; t0 += 32) {
-                const int t = t0 + lane;
+                const int      t = t0 + lane;
+                const unsigned relA = (unsigned)(endA - t0 - 1);   // my last entry's position in this step, if below 32
+                const unsigned endsA = __reduce_or_sync(FULL, relA < 32u ? 1u << relA : 0u);
+                const int      rankA = doneA + __popc(endsA & lanemask_lt());
+                doneA += __popc(endsA);
                 if (t < prof_total) {
-                    int own = 0;
-#pragma unroll
-                    for (int s = 16; s > 0; s >>= 1)
-                        if (W.pprefix[own + s - 1] <= t) own += s;
+                    const int    own = W.ownA[rankA];
                     const int    e = t - W.poff[own];
                     const int    ncl = W.ncols[own];
                     const bool   is_row = e >= ncl;
@@ -506,15 +542,17 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
             //      a ballot and a population count away.
             int carry_owner = -1;   // particle whose pixels straddle the previous step, and its kept count
             int carry_kept = 0;
+            int doneB = 0;          // particles whose pixels end before this step
+            // one past my last pixel slot, 0: none (re-read rather than kept in a register through phase A)
+            const int endB = W.qprefix[lane] != W.qexcl[lane] ? W.qprefix[lane] : 0;
             for (int w0 = 0; w0 < pix_total; w0 += 32) {
-                const int  w = w0 + lane;
-                const bool has = w < pix_total;
-                int        own = 0;
-#pragma unroll
-                for (int s = 16; s > 0; s >>= 1)
-                    if (W.qprefix[own + s - 1] <= w) own += s;
-                own = has ? own : 31;
-                const int excl = own ? W.qprefix[own - 1] : 0;
+                const int      w = w0 + lane;
+                const bool     has = w < pix_total;
+                const unsigned relB = (unsigned)(endB - w0 - 1);
+                const unsigned endsB = __reduce_or_sync(FULL, relB < 32u ? 1u << relB : 0u);
+                const int      own = has ? W.ownB[doneB + __popc(endsB & lanemask_lt())] : 31;
+                doneB += __popc(endsB);
+                const int excl = W.qexcl[own];
                 const int end = W.qprefix[own];
                 const int p = w - excl;             // index of the pixel in its particle's trimmed box, column-major
                 bool      keep = false;
@@ -581,22 +619,12 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
 
 
     // ---- per-group counters for k_scan ---------------------------------------------------------------
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) {
-        n_pairs += __shfl_xor_sync(FULL, n_pairs, s);
-        n_inside += __shfl_xor_sync(FULL, n_inside, s);
-        n_pixels += __shfl_xor_sync(FULL, n_pixels, s);
-        err |= __shfl_xor_sync(FULL, err, s);
-    }
+    err = __reduce_or_sync(FULL, err);
     if (lane == 0) {
         unsigned long long *t = P.ws.table + group;
-        if (from_table) {
-            t[(unsigned long long)(D + 0) * P.n_groups] = (unsigned long long)__popc(accmask);
-            t[(unsigned long long)(D + 1) * P.n_groups] = 0;
-        }
-        t[(unsigned long long)(D + 2) * P.n_groups] = n_pairs;
-        t[(unsigned long long)(D + 3) * P.n_groups] = n_inside;
-        t[(unsigned long long)(D + 4) * P.n_groups] = n_pixels;
+        t[(unsigned long long)(D + 2) * P.n_groups] = W.cen_pairs;
+        t[(unsigned long long)(D + 3) * P.n_groups] = W.cen_inside;
+        t[(unsigned long long)(D + 4) * P.n_groups] = W.cen_pixels;
         if (err) atomicOr(&P.totals->error, err);
     }
 }
