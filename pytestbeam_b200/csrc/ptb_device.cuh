@@ -128,6 +128,21 @@ __device__ __forceinline__ double u53_open(uint32_t a, uint32_t b)
     return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6) + 0.5) * (1.0 / 9007199254740992.0);
 }
 
+// lg2 / sqrt straight from the special-function unit (no denormal fix-up, no correctly-rounded square root: their
+// arguments here are uniforms in [2^-33, 1] and 0 <= -2 ln u < 46)
+__device__ __forceinline__ float lg2_sfu(float x)
+{
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sqrt_sfu(float x)
+{
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // Box-Muller pair in fp32 arithmetic, returned as doubles (sites that tolerate 24-bit normals: scattering
 // kicks, cluster radii, pixel noise).  Special-function-unit approximations throughout: lg2 / sin / cos are
 // good to ~2^-21 absolute on these ranges, far below what any of the consumers resolves.
@@ -135,7 +150,7 @@ __device__ __forceinline__ void normal_pair_f32(uint32_t a, uint32_t b, double &
 {
     float u = fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // (0,1]
     float v = fmaf((float)b, 1.4629180792671596e-09f, 7.3145903963357980e-10f);   // (0,2pi]
-    float r = __fsqrt_rn(-1.3862943611198906f * __log2f(u));                       // sqrt(-2 ln u)
+    float r = sqrt_sfu(-1.3862943611198906f * lg2_sfu(u));                         // sqrt(-2 ln u)
     float s, c;
     __sincosf(v, &s, &c);
     n0 = (double)(r * c);
@@ -236,9 +251,9 @@ struct PhiloxSource {
         if (p.lan_direct) {
             double z0, z1;
             normal_pair_f32(a, b, z0, z1);
-            double e = p.lan_loc + p.lan_scale * (double)(-1.3862943611198906f * __log2f(fabsf((float)z0)));
+            double e = p.lan_loc + p.lan_scale * (double)(-1.3862943611198906f * lg2_sfu(fabsf((float)z0)));
             if (e >= 0.0 && e <= 0.5) return e;
-            e = p.lan_loc + p.lan_scale * (double)(-1.3862943611198906f * __log2f(fabsf((float)z1)));
+            e = p.lan_loc + p.lan_scale * (double)(-1.3862943611198906f * lg2_sfu(fabsf((float)z1)));
             if (e >= 0.0 && e <= 0.5) return e;
             U4 w = philox_at(seed, k, SITE_PLANE + 4 * d + SUB_STEP, 1);
             a = w.x;
@@ -270,7 +285,7 @@ struct PhiloxSource {
         const uint32_t a = (p & 2u) ? w.z : w.x, b = (p & 2u) ? w.w : w.y;
         const float    u = fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // as normal_pair_f32
         const float    v = fmaf((float)b, 1.4629180792671596e-09f, 7.3145903963357980e-10f);
-        const float    r = __fsqrt_rn(-1.3862943611198906f * __log2f(u));
+        const float    r = sqrt_sfu(-1.3862943611198906f * lg2_sfu(u));
         float          s, c;
         __sincosf(v, &s, &c);
         return (double)(r * ((p & 1u) ? s : c));

@@ -328,7 +328,6 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
         W.cen_pairs = W.cen_inside = 0u;
         W.cen_pixels = 0ull;
     }
-    unsigned err = 0;
 
     // Digitisation inputs (x, y, energy loss) of plane d: fetched one plane ahead with asynchronous copies into the
     // lane's shared-memory slot (free again as soon as the current plane's values sit in registers), so that the
@@ -364,6 +363,7 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
         int  nprof = 0;        // columns + rows that can pass the ellipse test and lie on the matrix
         int  cntT = 0;         // pixels of that trimmed box: the only ones that can become hits
         bool inside = false;   // seed pixel on the matrix: the particle owns a work item even with an empty box
+        bool too_large = false;
         const bool digitised = valid && (!pl.triggered || W.accb[lane]);
         if (digitised) {
             const double sig = cloud_sigma(cfg, eloss);
@@ -382,6 +382,9 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
                 const double noise = 0.0 + pl.noise_sigma * zseed;
                 // seed pixel: both profile factors are exp(-0) = 1; no pixel-area factor (Q9)
                 const double seedq = (q * (inx * iny) + noise) * 1e-3;
+                // (descriptors go to shared memory as soon as they exist: the fewer values live at once, the better)
+                W.q[lane] = q; W.inx[lane] = inx; W.iny[lane] = iny; W.seedq[lane] = seedq;
+                W.seedcr[lane] = (uint32_t)sc | ((uint32_t)sr << 16);
                 const int    c_hi = pixel_index(x + rx, pl.delta_x, pl.pitch_c, pl.rcp_pc, pl.half_nc);
                 const int    c_lo = pixel_index(x - rx, pl.delta_x, pl.pitch_c, pl.rcp_pc, pl.half_nc);
                 const int    r_hi = pixel_index(y + ry, pl.delta_y, pl.pitch_r, pl.rcp_pr, pl.half_nr);
@@ -389,7 +392,7 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
                 const long long nc = (long long)c_hi - c_lo + 1, nr = (long long)r_hi - r_lo + 1;
                 long long       box = (nc > 0 && nr > 0) ? nc * nr : 0;
                 if (box > (1ll << 20)) {
-                    err |= PTB_DEV_BOX_TOO_LARGE;
+                    too_large = true;
                     box = 0;
                 }
                 cnt = (int)box;
@@ -417,18 +420,16 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
                 int ncT = max(cb - ca + 1, 0), nrT = max(rb - ra + 1, 0);
                 if (ncT == 0 || nrT == 0) ncT = nrT = 0;
                 if (ncT + nrT > PC) {
-                    err |= PTB_DEV_BOX_TOO_LARGE;
+                    too_large = true;
                     ncT = nrT = 0;
                 }
                 cntT = ncT * nrT;
                 nprof = ncT + nrT;
                 W.x[lane] = x; W.y[lane] = y; W.rx[lane] = rx; W.ry[lane] = ry;
-                W.q[lane] = q; W.inx[lane] = inx; W.iny[lane] = iny; W.seedq[lane] = seedq;
                 W.yx[lane] = yx; W.yy[lane] = yy;
                 W.clo[lane] = c_lo + ca; W.rlo[lane] = r_lo + ra; W.ncols[lane] = (uint8_t)ncT; W.nrows[lane] = (uint8_t)nrT;
                 W.jbase[lane] = ca * (int)nr + ra; W.nrfull[lane] = (int)nr;
                 W.rnr[lane] = __fdividef(1.0f, (float)max(nrT, 1));
-                W.seedcr[lane] = (uint32_t)sc | ((uint32_t)sr << 16);
             }
         }
         {
@@ -614,18 +615,21 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
             P.ws.table[(unsigned long long)d * P.n_groups + group] = (unsigned long long)n_plane;
             P.ws.table[(unsigned long long)(D + 5 + d) * P.n_groups + group] = base;
         }
-        if (!room) err |= PTB_DEV_SCRATCH_OVERFLOW;   // totals stay exact; the host retries with the reported sizes
+        // device-side conditions go straight to the totals (rare), so that no error word has to live across the planes
+        {
+            const unsigned e = (__any_sync(FULL, too_large) ? PTB_DEV_BOX_TOO_LARGE : 0u) |
+                               (room ? 0u : PTB_DEV_SCRATCH_OVERFLOW);   // totals stay exact; the host retries
+            if (e && lane == 0) atomicOr(&P.totals->error, e);
+        }
     }
 
 
     // ---- per-group counters for k_scan ---------------------------------------------------------------
-    err = __reduce_or_sync(FULL, err);
     if (lane == 0) {
         unsigned long long *t = P.ws.table + group;
         t[(unsigned long long)(D + 2) * P.n_groups] = W.cen_pairs;
         t[(unsigned long long)(D + 3) * P.n_groups] = W.cen_inside;
         t[(unsigned long long)(D + 4) * P.n_groups] = W.cen_pixels;
-        if (err) atomicOr(&P.totals->error, err);
     }
 }
 
