@@ -17,6 +17,11 @@ namespace ptb {
 // configuration derived on the host (ptb_create) and passed as a __grid_constant__ kernel parameter,
 // i.e. it lives in the constant bank and is read with uniform LDC
 // ---------------------------------------------------------------------------------------------------
+// geometry of one pixel axis (x / columns, y / rows): pitch, offset, number / 2, pitch / 2
+struct AxisK {
+    double pitch, delta, half_n, half_p;
+};
+
 struct PlaneK {
     double z;
     double x_pos, x_neg, y_pos, y_neg;   // acceptance window, main/hit.py:56-59
@@ -30,6 +35,7 @@ struct PlaneK {
     double noise_sigma;                  // sqrt(k_b*300*C)/e, main/device.py:410-415
     double lan_loc, lan_scale;           // energy loss = loc + scale * lambda (Moyal variable), main/hit.py:399-400
     double lan_ulo, lan_uspan;           // window of the Moyal CDF that maps onto [0, 0.5] MeV, main/hit.py:99-100
+    AxisK   ax[2];                       // the same geometry once more, by axis index (phase A of k_digitise)
     int32_t ncol, nrow, triggered;
     int32_t lan_direct;                  // 1: the window holds essentially all of the Moyal law: sample -ln(Z^2) directly
 };

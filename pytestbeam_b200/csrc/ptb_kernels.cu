@@ -121,9 +121,11 @@ static size_t carve_workspace(int D, unsigned long long n, const unsigned long l
 // shared memory of one warp: the per-particle cluster descriptors
 struct WarpShared {
     double   in[3][32];      // (x, y, energy loss) of the next plane, filled by cp.async while the current one is worked on
-    double   x[32], y[32], rx[32], ry[32], q[32], inx[32], iny[32], seedq[32];
-    double   yx[32], yy[32];   // RN(1/rx^2), RN(1/ry^2) for div_rcp
-    int      clo[32], rlo[32];                         // trimmed box: first column / row ...
+    // per particle and axis ([0] = x / columns, [1] = y / rows, so that phase A picks its operands by index):
+    double   pos[2][32], rad[2][32], nrm[2][32];       // hit position, cluster radius, 1/(sigma sqrt(2 pi))
+    double   ye[2][32];                                // RN(1/r^2) for div_rcp
+    double   q[32], seedq[32];
+    int      lo[2][32];                                // trimmed box: first column / row ...
     uint8_t  ncols[32], nrows[32];                     // ... and extent (ncols + nrows <= pool entries <= 128)
     int      jbase[32], nrfull[32];                    // position of the trimmed box inside the reference's box
     int      qexcl[32], qprefix[32], poff[32];     // work lists: first / one-past-last pixel slot, pool offset
@@ -383,7 +385,7 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
                 // seed pixel: both profile factors are exp(-0) = 1; no pixel-area factor (Q9)
                 const double seedq = (q * (inx * iny) + noise) * 1e-3;
                 // (descriptors go to shared memory as soon as they exist: the fewer values live at once, the better)
-                W.q[lane] = q; W.inx[lane] = inx; W.iny[lane] = iny; W.seedq[lane] = seedq;
+                W.q[lane] = q; W.nrm[0][lane] = inx; W.nrm[1][lane] = iny; W.seedq[lane] = seedq;
                 W.seedcr[lane] = (uint32_t)sc | ((uint32_t)sr << 16);
                 const int    c_hi = pixel_index(x + rx, pl.delta_x, pl.pitch_c, pl.rcp_pc, pl.half_nc);
                 const int    c_lo = pixel_index(x - rx, pl.delta_x, pl.pitch_c, pl.rcp_pc, pl.half_nc);
@@ -425,9 +427,9 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
                 }
                 cntT = ncT * nrT;
                 nprof = ncT + nrT;
-                W.x[lane] = x; W.y[lane] = y; W.rx[lane] = rx; W.ry[lane] = ry;
-                W.yx[lane] = yx; W.yy[lane] = yy;
-                W.clo[lane] = c_lo + ca; W.rlo[lane] = r_lo + ra; W.ncols[lane] = (uint8_t)ncT; W.nrows[lane] = (uint8_t)nrT;
+                W.pos[0][lane] = x; W.pos[1][lane] = y; W.rad[0][lane] = rx; W.rad[1][lane] = ry;
+                W.ye[0][lane] = yx; W.ye[1][lane] = yy;
+                W.lo[0][lane] = c_lo + ca; W.lo[1][lane] = r_lo + ra; W.ncols[lane] = (uint8_t)ncT; W.nrows[lane] = (uint8_t)nrT;
                 W.jbase[lane] = ca * (int)nr + ra; W.nrfull[lane] = (int)nr;
                 W.rnr[lane] = __fdividef(1.0f, (float)max(nrT, 1));
             }
@@ -513,14 +515,11 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
                     const int    own = W.ownA[rankA];
                     const int    e = t - W.poff[own];
                     const int    ncl = W.ncols[own];
-                    const bool   is_row = e >= ncl;
-                    const int    idx = is_row ? W.rlo[own] + (e - ncl) : W.clo[own] + e;
-                    const double ctr = is_row ? pixel_centre(idx, pl.delta_y, pl.pitch_r, pl.half_nr, pl.half_pr)
-                                              : pixel_centre(idx, pl.delta_x, pl.pitch_c, pl.half_nc, pl.half_pc);
-                    const double pos = is_row ? W.y[own] : W.x[own];
-                    const double r = is_row ? W.ry[own] : W.rx[own];
-                    const double nrm = is_row ? W.iny[own] : W.inx[own];
-                    const double ye = is_row ? W.yy[own] : W.yx[own];
+                    const int    a = e >= ncl ? 1 : 0;            // axis of the entry: a column (x) or a row (y)
+                    const int    idx = W.lo[a][own] + (e - (a ? ncl : 0));
+                    const AxisK &ax = pl.ax[a];
+                    const double ctr = pixel_centre(idx, ax.delta, ax.pitch, ax.half_n, ax.half_p);
+                    const double pos = W.pos[a][own], r = W.rad[a][own], nrm = W.nrm[a][own], ye = W.ye[a][own];
                     const double dd = ctr - pos;
                     // 1/(2 rc^2): half of 1/r^2 (exact scaling) unless the radius is clamped (main/device.py:400-403)
                     const double y2 = r < 1.0 ? PTB_RCP_2RC2_CLAMPED : 0.5 * ye;
@@ -577,7 +576,7 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
                         // the matrix bounds are implied by the clipped box; a zero radius makes the ellipse terms
                         // NaN or inf, which fail the comparison as rx > 0 and ry > 0 would (device.py:289-295)
                         keep = hq >= pl.thr_ke && pool_e[po + ci] + pool_e[po + ncl + ri] <= 1.0;
-                        hcr = (uint32_t)(W.clo[own] + ci) | ((uint32_t)(W.rlo[own] + ri) << 16);
+                        hcr = (uint32_t)(W.lo[0][own] + ci) | ((uint32_t)(W.lo[1][own] + ri) << 16);
                     }
                 }
                 // kept pixels of my particle in this step: the lanes of one particle are contiguous in the work list
@@ -1085,6 +1084,8 @@ int ptb_create(const PtbBeam *beam, const PtbDevice *dev, int32_t n_dev, const P
         double corr = 1 + 0.038 * log(p.eps);
         p.corr2 = corr * corr;
         p.hl_c = 13.6 * sqrt(p.eps * p.corr2);
+        p.ax[0] = AxisK{v.pitch_c, v.delta_x, v.ncol / 2.0, v.pitch_c / 2};
+        p.ax[1] = AxisK{v.pitch_r, v.delta_y, v.nrow / 2.0, v.pitch_r / 2};
         p.pitch_c = v.pitch_c; p.pitch_r = v.pitch_r;
         p.delta_x = v.delta_x; p.delta_y = v.delta_y;
         p.half_nc = v.ncol / 2.0; p.half_nr = v.nrow / 2.0;
