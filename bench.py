@@ -282,7 +282,7 @@ def run_gpu(args):
                 "flops_per_electron": F, "flops_per_electron_whole_path": F_all, "launch_ms": launch_ms,
                 "k_tracks_launch_ms": tracks_launch_ms, "launches_timed": sim_launches,
                 "share_of_step": launch_ms / (ms / K), "traffic": traffic, "ncu": ncu,
-                "binding": "instruction issue (78 % of issue slots busy, FP64 pipe 22 %): see profiles/README.md",
+                "binding": "instruction issue (see ncu.issue_active_pct; FP64 pipe about a quarter busy): profiles/README.md",
                 "hbm": {"achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
                         "bytes_per_electron": alg_bytes / chunk, "peak_source": hbm_src}}
         cpu_sample = args.cpu_sample or 1_000_000
