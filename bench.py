@@ -144,7 +144,7 @@ def run_reference(args):
                              "sample": f"{workers} processes x {sample} electrons per step, distinct seeds; the "
                                        "reference itself is single-threaded Python+Numba and cannot travel"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=args.out, flush=True)
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -309,10 +309,19 @@ def run_gpu(args):
                                               "reference itself, Python+Numba, ran 6.4-7.2e4 electrons/s on one core "
                                               "in the build container and cannot travel to this box)",
                                     "hits_per_s": cpu_hits}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=args.out, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _claim_stdout():
+    """Keep stdout for the one JSON line: whatever libraries print to file descriptor 1 meanwhile (NCCL's version
+    banner, for one) goes to stderr.  Returns the stream to print the line to."""
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(keep, "w")
 
 
 def main():
@@ -327,6 +336,7 @@ def main():
                     help="telescope set-up (default = BASELINE configs 1/2/5; c3, c4 = the other two)")
     ap.add_argument("--cpu-sample", type=int, default=0)
     args = ap.parse_args()
+    args.out = _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
