@@ -160,7 +160,7 @@ def run_gpu(args):
     from pytestbeam_b200 import native as N
     from pytestbeam_b200.engine import Simulator
     from pytestbeam_b200.distributed import exchange_bases
-    from pytestbeam_b200.pipeline import ChunkPipeline
+    from pytestbeam_b200.pipeline import ChunkPipeline, bind_host_to_gpu
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -168,6 +168,7 @@ def run_gpu(args):
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local)
+    numa_bound = bind_host_to_gpu(local) if world > 1 else False   # host buffers next to this rank's GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -292,7 +293,7 @@ def run_gpu(args):
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload + f", {total_particles:.3g} electrons", "electrons_per_step": chunk,
                            "planes": D, "hits_per_electron": hits_per_particle, "seed": seed,
-                           "parallelism": f"index-range shards x{world}",
+                           "parallelism": f"index-range shards x{world}", "host_numa_bound": numa_bound,
                            "l2": "no inputs; 1.2 GB of hit rows written per step (> 126 MB L2)"},
                 "hits_per_s": value * hits_per_particle,
                 "clocks": clocks,

@@ -14,6 +14,22 @@ from . import native as N
 from .engine import _TOTALS_WORDS, PtbError, Simulator
 
 
+def bind_host_to_gpu(index: int) -> bool:
+    """Pin the calling process to the CPUs next to GPU `index` (NVML's ideal affinity), so that the pinned sink buffers
+    allocated afterwards land on that GPU's NUMA node: with several ranks per box the device-to-host copies otherwise
+    cross the socket interconnect.  Returns False (and changes nothing) when NVML is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(int(index)))
+        finally:
+            pynvml.nvmlShutdown()
+        return True
+    except Exception:
+        return False
+
+
 class ChunkPipeline:
     def __init__(self, sim: Simulator, chunk: int, *, n_buffers: int = 2, capacities=None, host: bool = False,
                  seed: int = 0, scratch_rows=None):
