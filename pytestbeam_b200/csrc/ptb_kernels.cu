@@ -20,6 +20,7 @@
 //
 // The kernels never wait on each other inside a launch (no look-back spinning), so forward progress
 // does not depend on block scheduling order.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -54,7 +55,9 @@ static unsigned long long g_launches = 0;
 // workspace layout (device memory owned by the caller)
 // ---------------------------------------------------------------------------------------------------
 struct Workspace {
-    unsigned long long *alloc;      // [PTB_MAX_PLANES * 16] one counter per 128-byte line
+    unsigned long long *alloc;      // [(PTB_MAX_PLANES + 1) * 16] one counter per 128-byte line: scratch rows handed out
+                                    // per plane; the last one counts the deferred (group, plane) items
+    unsigned long long *deferred;   // [n_groups * D] (group << 8 | plane) of the pairs k_digitise left to k_digitise_big
     unsigned long long *table;      // [(2D+5)][n_groups]: hits[D], accepted, tsum, pairs, inside, pixels, base[D]
     unsigned long long *prefix;     // [(D+2)][n_groups]
     PtbBases           *bases_used; // copy of bases_in taken by k_scan before bases_out is written
@@ -89,8 +92,10 @@ static size_t carve_workspace(int D, unsigned long long n, const unsigned long l
         return base ? base + at : (char *)nullptr;
     };
     char *p;
-    p = take(sizeof(unsigned long long) * PTB_MAX_PLANES * 16);
+    p = take(sizeof(unsigned long long) * (PTB_MAX_PLANES + 1) * 16);
     if (ws) ws->alloc = (unsigned long long *)p;
+    p = take((flags & PTB_DIGITISE) ? sizeof(unsigned long long) * (size_t)D * ng : 0);
+    if (ws) ws->deferred = (unsigned long long *)p;
     p = take(sizeof(unsigned long long) * (size_t)(2 * D + 5) * ng);
     if (ws) ws->table = (unsigned long long *)p;
     p = take(sizeof(unsigned long long) * (size_t)(D + 2) * ng);
@@ -126,7 +131,8 @@ struct WarpShared {
     double   ye[2][32];                                // RN(1/r^2) for div_rcp
     double   q[32], seedq[32];
     int      lo[2][32];                                // trimmed box: first column / row ...
-    uint8_t  ncols[32], nrows[32];                     // ... and extent (ncols + nrows <= pool entries <= 128)
+    uint16_t ncols[32], nrows[32];                     // ... and extent (ncols + nrows <= pool entries, or the pair is
+                                                       //     left to k_digitise_big)
     int      jbase[32], nrfull[32];                    // position of the trimmed box inside the reference's box
     int      qexcl[32], qprefix[32], poff[32];     // work lists: first / one-past-last pixel slot, pool offset
     uint8_t  ownA[32], ownB[32];                   // the particles that own profile entries / pixel slots, in order
@@ -277,6 +283,97 @@ __global__ void __launch_bounds__(TRACK_BLOCK, PTB_TRACK_MIN_BLOCKS) k_tracks(co
     }
 }
 
+// Cluster descriptor of one (particle, plane) pair, main/device.py:137-140, 241-266: radii, seed pixel and charge, the
+// reference's bounding box and its trimmed version.  The per-particle values the later phases read go to the warp's
+// shared memory (as soon as they exist: the fewer values live at once, the better); the counts come back.
+struct Cluster {
+    int  cnt;        // pixels of the reference's bounding box (census)
+    int  ncT, nrT;   // columns / rows of the trimmed box
+    bool inside;     // seed pixel on the matrix
+    bool too_large;  // bounding box beyond 2^20 pixels: refused
+};
+
+template <class Src>
+__device__ __forceinline__ Cluster describe(const ConfigK &cfg, const PlaneK &pl, uint32_t flags, const Src &src,
+                                            unsigned long long k, int d, double x, double y, double eloss, WarpShared &W,
+                                            int lane)
+{
+    Cluster      out{0, 0, 0, false, false};
+    const double sig = cloud_sigma(cfg, eloss);
+    double       zrx, zry, zseed;
+    src.dig(k, d, zrx, zry, zseed);
+    const bool   injected_charge = (flags & PTB_ZERO_RADIUS) != 0;   // threshold scan: radius 0
+    const double rx = injected_charge ? 0.0 : fabs(0.0 + sig * zrx);
+    const double ry = injected_charge ? 0.0 : fabs(0.0 + sig * zry);
+    const int    sc = pixel_index(x, pl.delta_x, pl.pitch_c, pl.rcp_pc, pl.half_nc);
+    const int    sr = pixel_index(y, pl.delta_y, pl.pitch_r, pl.rcp_pr, pl.half_nr);
+    if (sc >= 1 && sc <= pl.ncol && sr >= 1 && sr <= pl.nrow) {
+        out.inside = true;
+        const double inx = profile_norm(profile_radius(rx));
+        const double iny = profile_norm(profile_radius(ry));
+        const double q = eloss == 0.0 ? 0.0 : div_rcp(eloss * 1e6, 3.6, cfg.rcp_3p6);
+        const double noise = 0.0 + pl.noise_sigma * zseed;
+        // seed pixel: both profile factors are exp(-0) = 1; no pixel-area factor (Q9)
+        const double seedq = (q * (inx * iny) + noise) * 1e-3;
+        W.q[lane] = q; W.nrm[0][lane] = inx; W.nrm[1][lane] = iny; W.seedq[lane] = seedq;
+        W.seedcr[lane] = (uint32_t)sc | ((uint32_t)sr << 16);
+        const int    c_hi = pixel_index(x + rx, pl.delta_x, pl.pitch_c, pl.rcp_pc, pl.half_nc);
+        const int    c_lo = pixel_index(x - rx, pl.delta_x, pl.pitch_c, pl.rcp_pc, pl.half_nc);
+        const int    r_hi = pixel_index(y + ry, pl.delta_y, pl.pitch_r, pl.rcp_pr, pl.half_nr);
+        const int    r_lo = pixel_index(y - ry, pl.delta_y, pl.pitch_r, pl.rcp_pr, pl.half_nr);
+        const long long nc = (long long)c_hi - c_lo + 1, nr = (long long)r_hi - r_lo + 1;
+        long long       box = (nc > 0 && nr > 0) ? nc * nr : 0;
+        if (box > (1ll << 20)) {
+            out.too_large = true;
+            box = 0;
+        }
+        out.cnt = (int)box;
+        // A box pixel can only be kept if its column passes dx^2/rx^2 <= 1, its row dy^2/ry^2 <= 1 (both terms
+        // of the ellipse test are non-negative) and it lies on the matrix (main/device.py:290-295).  The box
+        // is clipped to the matrix, and its edge columns / rows -- the usual casualties, their centres lie up
+        // to half a pitch outside x +- rx -- are dropped when they fail the very expression the pixel test
+        // uses.  Whatever else fails is still rejected by the full test of every pixel.
+        const double yx = 1.0 / (rx * rx), yy = 1.0 / (ry * ry);
+        int ca = 0, cb = -1, ra = 0, rb = -1;      // box-relative, inclusive
+        if (box > 0) {
+            ca = max(0, 1 - c_lo); cb = min((int)nc - 1, pl.ncol - c_lo);
+            ra = max(0, 1 - r_lo); rb = min((int)nr - 1, pl.nrow - r_lo);
+            auto term = [&](int idx, double delta, double pitch, double hn, double hp, double pos, double r,
+                            double y_) {
+                const double dd = pixel_centre(idx, delta, pitch, hn, hp) - pos;
+                return div_rcp(dd * dd, r * r, y_);
+            };
+            const bool f0 = !(term(c_lo + ca, pl.delta_x, pl.pitch_c, pl.half_nc, pl.half_pc, x, rx, yx) <= 1.0);
+            const bool f1 = !(term(c_lo + cb, pl.delta_x, pl.pitch_c, pl.half_nc, pl.half_pc, x, rx, yx) <= 1.0);
+            const bool f2 = !(term(r_lo + ra, pl.delta_y, pl.pitch_r, pl.half_nr, pl.half_pr, y, ry, yy) <= 1.0);
+            const bool f3 = !(term(r_lo + rb, pl.delta_y, pl.pitch_r, pl.half_nr, pl.half_pr, y, ry, yy) <= 1.0);
+            ca += f0; cb -= f1; ra += f2; rb -= f3;
+        }
+        int ncT = max(cb - ca + 1, 0), nrT = max(rb - ra + 1, 0);
+        if (ncT == 0 || nrT == 0) ncT = nrT = 0;
+        out.ncT = ncT;
+        out.nrT = nrT;
+        W.pos[0][lane] = x; W.pos[1][lane] = y; W.rad[0][lane] = rx; W.rad[1][lane] = ry;
+        W.ye[0][lane] = yx; W.ye[1][lane] = yy;
+        W.lo[0][lane] = c_lo + ca; W.lo[1][lane] = r_lo + ra; W.ncols[lane] = (uint16_t)ncT; W.nrows[lane] = (uint16_t)nrT;
+        W.jbase[lane] = ca * (int)nr + ra; W.nrfull[lane] = (int)nr;
+        W.rnr[lane] = __fdividef(1.0f, (float)max(nrT, 1));
+    }
+    return out;
+}
+
+// The separable parts of a pixel's charge and ellipse test for one column (axis 0) or row (axis 1):
+//      g = 1/(sigma sqrt(2pi)) exp(-(d^2)/(2 sigma^2))  (main/device.py:378),   e = d^2 / r^2  (main/device.py:291-293)
+__device__ __forceinline__ void profile_entry(const AxisK &ax, int idx, double pos, double r, double nrm, double ye,
+                                              double &g, double &e)
+{
+    const double dd = pixel_centre(idx, ax.delta, ax.pitch, ax.half_n, ax.half_p) - pos;
+    // 1/(2 rc^2): half of 1/r^2 (exact scaling) unless the radius is clamped (main/device.py:400-403)
+    const double y2 = r < 1.0 ? PTB_RCP_2RC2_CLAMPED : 0.5 * ye;
+    g = nrm * profile_shape(dd, profile_radius(r), y2);
+    e = div_rcp(dd * dd, r * r, ye);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // k_digitise: one warp per group of 32 particles, plane by plane (main/device.py:132-168).  Inputs come from
 // k_tracks' park or, with PTB_TRACKS_FROM_TABLE, from the caller's hit_tables arrays exactly as
@@ -361,79 +458,15 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
         if (d + 1 < D) fetch(d + 1);
 
         // ---- cluster descriptors, one lane per particle (main/device.py:137-140, 241-266) -----------
-        int  cnt = 0;          // pixels of the reference's bounding box (census)
-        int  nprof = 0;        // columns + rows that can pass the ellipse test and lie on the matrix
-        int  cntT = 0;         // pixels of that trimmed box: the only ones that can become hits
-        bool inside = false;   // seed pixel on the matrix: the particle owns a work item even with an empty box
-        bool too_large = false;
         const bool digitised = valid && (!pl.triggered || W.accb[lane]);
-        if (digitised) {
-            const double sig = cloud_sigma(cfg, eloss);
-            double       zrx, zry, zseed;
-            src.dig(k, d, zrx, zry, zseed);
-            const bool   injected_charge = (P.flags & PTB_ZERO_RADIUS) != 0;   // threshold scan: radius 0
-            const double rx = injected_charge ? 0.0 : fabs(0.0 + sig * zrx);
-            const double ry = injected_charge ? 0.0 : fabs(0.0 + sig * zry);
-            const int    sc = pixel_index(x, pl.delta_x, pl.pitch_c, pl.rcp_pc, pl.half_nc);
-            const int    sr = pixel_index(y, pl.delta_y, pl.pitch_r, pl.rcp_pr, pl.half_nr);
-            if (sc >= 1 && sc <= pl.ncol && sr >= 1 && sr <= pl.nrow) {
-                inside = true;
-                const double inx = profile_norm(profile_radius(rx));
-                const double iny = profile_norm(profile_radius(ry));
-                const double q = eloss == 0.0 ? 0.0 : div_rcp(eloss * 1e6, 3.6, cfg.rcp_3p6);
-                const double noise = 0.0 + pl.noise_sigma * zseed;
-                // seed pixel: both profile factors are exp(-0) = 1; no pixel-area factor (Q9)
-                const double seedq = (q * (inx * iny) + noise) * 1e-3;
-                // (descriptors go to shared memory as soon as they exist: the fewer values live at once, the better)
-                W.q[lane] = q; W.nrm[0][lane] = inx; W.nrm[1][lane] = iny; W.seedq[lane] = seedq;
-                W.seedcr[lane] = (uint32_t)sc | ((uint32_t)sr << 16);
-                const int    c_hi = pixel_index(x + rx, pl.delta_x, pl.pitch_c, pl.rcp_pc, pl.half_nc);
-                const int    c_lo = pixel_index(x - rx, pl.delta_x, pl.pitch_c, pl.rcp_pc, pl.half_nc);
-                const int    r_hi = pixel_index(y + ry, pl.delta_y, pl.pitch_r, pl.rcp_pr, pl.half_nr);
-                const int    r_lo = pixel_index(y - ry, pl.delta_y, pl.pitch_r, pl.rcp_pr, pl.half_nr);
-                const long long nc = (long long)c_hi - c_lo + 1, nr = (long long)r_hi - r_lo + 1;
-                long long       box = (nc > 0 && nr > 0) ? nc * nr : 0;
-                if (box > (1ll << 20)) {
-                    too_large = true;
-                    box = 0;
-                }
-                cnt = (int)box;
-                // A box pixel can only be kept if its column passes dx^2/rx^2 <= 1, its row dy^2/ry^2 <= 1 (both terms
-                // of the ellipse test are non-negative) and it lies on the matrix (main/device.py:290-295).  The box
-                // is clipped to the matrix, and its edge columns / rows -- the usual casualties, their centres lie up
-                // to half a pitch outside x +- rx -- are dropped when they fail the very expression the pixel test
-                // uses.  Whatever else fails is still rejected by the full test in phase B.
-                const double yx = 1.0 / (rx * rx), yy = 1.0 / (ry * ry);
-                int ca = 0, cb = -1, ra = 0, rb = -1;      // box-relative, inclusive
-                if (box > 0) {
-                    ca = max(0, 1 - c_lo); cb = min((int)nc - 1, pl.ncol - c_lo);
-                    ra = max(0, 1 - r_lo); rb = min((int)nr - 1, pl.nrow - r_lo);
-                    auto term = [&](int idx, double delta, double pitch, double hn, double hp, double pos, double r,
-                                    double y_) {
-                        const double dd = pixel_centre(idx, delta, pitch, hn, hp) - pos;
-                        return div_rcp(dd * dd, r * r, y_);
-                    };
-                    const bool f0 = !(term(c_lo + ca, pl.delta_x, pl.pitch_c, pl.half_nc, pl.half_pc, x, rx, yx) <= 1.0);
-                    const bool f1 = !(term(c_lo + cb, pl.delta_x, pl.pitch_c, pl.half_nc, pl.half_pc, x, rx, yx) <= 1.0);
-                    const bool f2 = !(term(r_lo + ra, pl.delta_y, pl.pitch_r, pl.half_nr, pl.half_pr, y, ry, yy) <= 1.0);
-                    const bool f3 = !(term(r_lo + rb, pl.delta_y, pl.pitch_r, pl.half_nr, pl.half_pr, y, ry, yy) <= 1.0);
-                    ca += f0; cb -= f1; ra += f2; rb -= f3;
-                }
-                int ncT = max(cb - ca + 1, 0), nrT = max(rb - ra + 1, 0);
-                if (ncT == 0 || nrT == 0) ncT = nrT = 0;
-                if (ncT + nrT > PC) {
-                    too_large = true;
-                    ncT = nrT = 0;
-                }
-                cntT = ncT * nrT;
-                nprof = ncT + nrT;
-                W.pos[0][lane] = x; W.pos[1][lane] = y; W.rad[0][lane] = rx; W.rad[1][lane] = ry;
-                W.ye[0][lane] = yx; W.ye[1][lane] = yy;
-                W.lo[0][lane] = c_lo + ca; W.lo[1][lane] = r_lo + ra; W.ncols[lane] = (uint8_t)ncT; W.nrows[lane] = (uint8_t)nrT;
-                W.jbase[lane] = ca * (int)nr + ra; W.nrfull[lane] = (int)nr;
-                W.rnr[lane] = __fdividef(1.0f, (float)max(nrT, 1));
-            }
-        }
+        Cluster    cl{0, 0, 0, false, false};
+        if (digitised) cl = describe(cfg, pl, P.flags, src, k, d, x, y, eloss, W, lane);
+        const int  cnt = cl.cnt;                  // pixels of the reference's bounding box (census)
+        bool       inside = cl.inside;            // seed pixel on the matrix: the particle owns a work item even with an empty box
+        int        nprof = cl.ncT + cl.nrT;       // columns + rows that can pass the ellipse test and lie on the matrix
+        int        cntT = cl.ncT * cl.nrT;        // pixels of that trimmed box: the only ones that can become hits
+        const bool too_large = cl.too_large;
+        const bool big = nprof > PC;              // more columns + rows than the profile pool holds
         {
             const unsigned pairs_d = __popc(__ballot_sync(FULL, digitised)), inside_d = __popc(__ballot_sync(FULL, inside));
             const unsigned pixels_d = __reduce_add_sync(FULL, (unsigned)cnt);   // <= 32 boxes of <= 2^20 pixels
@@ -442,6 +475,15 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
                 W.cen_inside += inside_d;
                 W.cen_pixels += pixels_d;
             }
+        }
+
+        // A pair whose trimmed box has more columns + rows than the pool holds (pitch far below the cloud width) takes the
+        // whole (group, plane) out of this kernel: it is listed for k_digitise_big and counts as empty here.
+        if (__any_sync(FULL, big)) {
+            if (lane == 0)
+                P.ws.deferred[atomicAdd(&P.ws.alloc[PTB_MAX_PLANES * 16], 1ull)] = (group << 8) | (unsigned long long)d;
+            inside = false;
+            nprof = cntT = 0;
         }
 
         // ---- room for every pixel that can become a hit (all trimmed-box pixels, or the seed fallback), reserved
@@ -517,14 +559,8 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
                     const int    ncl = W.ncols[own];
                     const int    a = e >= ncl ? 1 : 0;            // axis of the entry: a column (x) or a row (y)
                     const int    idx = W.lo[a][own] + (e - (a ? ncl : 0));
-                    const AxisK &ax = pl.ax[a];
-                    const double ctr = pixel_centre(idx, ax.delta, ax.pitch, ax.half_n, ax.half_p);
-                    const double pos = W.pos[a][own], r = W.rad[a][own], nrm = W.nrm[a][own], ye = W.ye[a][own];
-                    const double dd = ctr - pos;
-                    // 1/(2 rc^2): half of 1/r^2 (exact scaling) unless the radius is clamped (main/device.py:400-403)
-                    const double y2 = r < 1.0 ? PTB_RCP_2RC2_CLAMPED : 0.5 * ye;
-                    pool_g[t] = nrm * profile_shape(dd, profile_radius(r), y2);
-                    pool_e[t] = div_rcp(dd * dd, r * r, ye);
+                    profile_entry(pl.ax[a], idx, W.pos[a][own], W.rad[a][own], W.nrm[a][own], W.ye[a][own], pool_g[t],
+                                  pool_e[t]);
                 }
             }
             __syncwarp();
@@ -629,6 +665,118 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
         t[(unsigned long long)(D + 2) * P.n_groups] = W.cen_pairs;
         t[(unsigned long long)(D + 3) * P.n_groups] = W.cen_inside;
         t[(unsigned long long)(D + 4) * P.n_groups] = W.cen_pixels;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_digitise_big: the (group, plane) pairs k_digitise left aside because a cluster of theirs has more box columns + rows
+// than the profile pool holds (pixel pitch far below the cloud width).  One warp per pair; the particles are served one
+// after the other, the warp walking the pixels of one particle 32 per step and working out both profiles per pixel
+// with the very expressions of phase A -- no pool, no limit but the 2^20 pixels of a bounding box.  Launched only when
+// the geometry or the caller's own variates make such clusters possible.
+// ---------------------------------------------------------------------------------------------------
+constexpr int BIG_WARPS = 2;
+
+template <class Src, bool KEEP64>
+__global__ void __launch_bounds__(32 * BIG_WARPS) k_digitise_big(const __grid_constant__ ConfigK cfg,
+                                                                 const __grid_constant__ KParams P, const Src src)
+{
+    __shared__ WarpShared Ws[BIG_WARPS];
+    const int                lane = threadIdx.x & 31;
+    WarpShared              &W = Ws[threadIdx.x >> 5];
+    const int                D = cfg.n_planes;
+    const bool               from_table = (P.flags & PTB_TRACKS_FROM_TABLE) != 0;
+    const unsigned long long n_items = P.ws.alloc[PTB_MAX_PLANES * 16];
+    for (unsigned long long item = (unsigned long long)blockIdx.x * BIG_WARPS + (threadIdx.x >> 5); item < n_items;
+         item += (unsigned long long)gridDim.x * BIG_WARPS) {
+        const unsigned long long entry = P.ws.deferred[item];
+        const unsigned long long group = entry >> 8;
+        const int                d = (int)(entry & 0xffu);
+        const PlaneK            &pl = cfg.pl[d];
+        const unsigned long long kl = group * 32 + lane;
+        const bool               valid = kl < P.n;
+        const unsigned long long k = P.first + kl;
+        unsigned                 accmask;
+        if (from_table)
+            accmask = __ballot_sync(FULL, valid && (P.trk.accepted ? P.trk.accepted[kl] != 0 : src.accepted(cfg, k)));
+        else
+            accmask = P.ws.accmask[group];
+        __syncwarp();
+        W.evoff[lane] = (uint8_t)__popc(accmask & lanemask_lt());
+        double x = 0.0, y = 0.0, eloss = 0.0;
+        if (from_table) {
+            if (valid) {
+                x = P.trk.x[kl * D + d];
+                y = P.trk.y[kl * D + d];
+                eloss = P.trk.eloss[(unsigned long long)d * P.n + kl];
+            }
+        } else {
+            const double *park = P.ws.park + group * (unsigned long long)(D * 96) + lane;
+            x = park[d * 96];
+            y = park[d * 96 + 32];
+            eloss = park[d * 96 + 64];
+        }
+        const bool digitised = valid && (!pl.triggered || ((accmask >> lane) & 1u));
+        Cluster    cl{0, 0, 0, false, false};
+        if (digitised) cl = describe(cfg, pl, P.flags, src, k, d, x, y, eloss, W, lane);
+        __syncwarp();
+        const unsigned     insidemask = __ballot_sync(FULL, cl.inside);
+        const int          ub = __reduce_add_sync(FULL, cl.inside ? max(cl.ncT * cl.nrT, 1) : 0);
+        unsigned long long base = 0;
+        if (lane == 0 && ub > 0) base = atomicAdd(&P.ws.alloc[d * 16], (unsigned long long)ub);
+        base = __shfl_sync(FULL, base, 0);
+        const bool room = base + (unsigned long long)ub <= P.ws.cap[d];
+        uint2     *seg_hit = P.ws.s_hit[d] + base;
+        uint8_t   *seg_ev = P.ws.s_ev[d] + base;
+        double    *seg_q64 = KEEP64 ? P.ws.s_q64[d] + base : nullptr;
+        int        n_plane = 0;
+        for (unsigned left = insidemask; left; left &= left - 1) {
+            const int    b = __ffs(left) - 1;   // the particles in order
+            const int    ncl = W.ncols[b], nrw = W.nrows[b], box = ncl * nrw;
+            const double px = W.pos[0][b], py = W.pos[1][b], rx = W.rad[0][b], ry = W.rad[1][b], q = W.q[b];
+            int          kept = 0;
+            for (int p0 = 0; p0 < box; p0 += 32) {
+                const int p = p0 + lane;
+                bool      keep = false;
+                double    hq = 0.0;
+                uint32_t  hcr = 0;
+                if (p < box) {
+                    const int ci = p / nrw, ri = p - ci * nrw;
+                    double    gc, ec, gr, er;
+                    profile_entry(pl.ax[0], W.lo[0][b] + ci, px, rx, W.nrm[0][b], W.ye[0][b], gc, ec);
+                    profile_entry(pl.ax[1], W.lo[1][b] + ri, py, ry, W.nrm[1][b], W.ye[1][b], gr, er);
+                    const double zn = src.pixel(P.first + group * 32 + b, d, (uint32_t)p, W.jbase[b] + ci * W.nrfull[b] + ri);
+                    const double noise = 0.0 + pl.noise_sigma * zn;
+                    const double signal = q * (gc * gr);
+                    hq = (signal + noise) * 1e-3 * pl.pitch_c * pl.pitch_r;   // device.py:275-288
+                    keep = hq >= pl.thr_ke && ec + er <= 1.0;
+                    hcr = (uint32_t)(W.lo[0][b] + ci) | ((uint32_t)(W.lo[1][b] + ri) << 16);
+                }
+                const unsigned kballot = __ballot_sync(FULL, keep);
+                if (keep && room) {
+                    const unsigned at = (unsigned)(n_plane + kept) + __popc(kballot & lanemask_lt());
+                    seg_hit[at] = make_uint2(hcr, __float_as_uint((float)hq));
+                    seg_ev[at] = W.evoff[b];
+                    if (KEEP64) seg_q64[at] = hq;
+                }
+                kept += __popc(kballot);
+            }
+            if (kept == 0 && W.seedq[b] >= pl.thr_ke) {   // seed fallback, main/device.py:299-302
+                if (lane == 0 && room) {
+                    seg_hit[n_plane] = make_uint2(W.seedcr[b], __float_as_uint((float)W.seedq[b]));
+                    seg_ev[n_plane] = W.evoff[b];
+                    if (KEEP64) seg_q64[n_plane] = W.seedq[b];
+                }
+                kept = 1;
+            }
+            n_plane += kept;
+        }
+        if (lane == 0) {
+            P.ws.table[(unsigned long long)d * P.n_groups + group] = (unsigned long long)n_plane;
+            P.ws.table[(unsigned long long)(D + 5 + d) * P.n_groups + group] = base;
+            if (!room) atomicOr(&P.totals->error, PTB_DEV_SCRATCH_OVERFLOW);
+        }
+        __syncwarp();
     }
 }
 
@@ -980,6 +1128,7 @@ struct PtbContext {
     void   *alias_dev;   // device copy of the Poisson alias table (cfg.alias points at it)
     int     device;
     int     sm_count;
+    int     may_be_big;   // a production-mode cluster can outgrow the profile pool: k_digitise_big is launched
     int     timing;
     std::vector<cudaEvent_t> ev;   // (start, after k_tracks, after k_digitise) per ptb_simulate, when timing is enabled
     size_t  ev_used;
@@ -1127,6 +1276,16 @@ int ptb_create(const PtbBeam *beam, const PtbDevice *dev, int32_t n_dev, const P
         }
     }
     c.theta0_first = highland_theta0(beam->energy, c.pl[0].eps, c.pl[0].corr2);
+    // Can a production-mode cluster outgrow the profile pool?  The widest cloud belongs to the largest deposit (0.5 MeV,
+    // main/hit.py:99-100), the 24-bit normals stop at sqrt(2 ln 2^33) = 6.8, and a radius r spans 2r/pitch + 2 pixels.
+    {
+        const double q = c.qe * (0.5 * 1e6) / 3.6;
+        const double coul = 0.2 * cbrt(c.c3mu * q * c.t90 / c.cden);
+        const double r_max = 6.8 * sqrt(c.diff2 + coul * coul) * 1e6 * 1.01;
+        h->may_be_big = 0;
+        for (int d = 0; d < n_dev; ++d)
+            if (2 * r_max / dev[d].pitch_c + 2 * r_max / dev[d].pitch_r + 6 > c.pool_entries) h->may_be_big = 1;
+    }
 
     cudaError_t e = cudaGetDevice(&h->device);
     if (e != cudaSuccess) return fail_cuda(h, e, "cudaGetDevice");
@@ -1325,7 +1484,7 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
     if (P.n_groups > 0x7fffffffull * WARPS_PER_BLOCK) return fail(h, PTB_E_INVALID, "range too large for one call");
 
     cudaError_t e;
-    e = cudaMemsetAsync(P.ws.alloc, 0, sizeof(unsigned long long) * PTB_MAX_PLANES * 16, st);
+    e = cudaMemsetAsync(P.ws.alloc, 0, sizeof(unsigned long long) * (PTB_MAX_PLANES + 1) * 16, st);
     if (e != cudaSuccess) return fail_cuda(h, e, "memset alloc");
     e = cudaMemsetAsync(run->totals, 0, sizeof(PtbTotals), st);
     if (e != cudaSuccess) return fail_cuda(h, e, "memset totals");
@@ -1366,6 +1525,25 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
         }
         ++g_launches;
         if (e != cudaSuccess) return fail_cuda(h, e, "k_digitise launch");
+        // clusters wider than the profile pool: possible with the caller's own variates / deposits, or when the geometry
+        // says so (ptb_create); the default telescope never launches this
+        if (run->injected || (flags & PTB_TRACKS_FROM_TABLE) || h->may_be_big) {
+            const unsigned long long items = P.n_groups * (unsigned long long)D;
+            const unsigned bb = (unsigned)std::min<unsigned long long>((items + BIG_WARPS - 1) / BIG_WARPS,
+                                                                       (unsigned long long)h->sm_count * 16);
+            if (run->injected) {
+                InjectedSource src{*run->injected, run->first, run->n};
+                if (keep64) k_digitise_big<InjectedSource, true><<<bb, 32 * BIG_WARPS, 0, st>>>(c, P, src);
+                else        k_digitise_big<InjectedSource, false><<<bb, 32 * BIG_WARPS, 0, st>>>(c, P, src);
+            } else {
+                PhiloxSource src{philox_keys(run->seed)};
+                if (keep64) k_digitise_big<PhiloxSource, true><<<bb, 32 * BIG_WARPS, 0, st>>>(c, P, src);
+                else        k_digitise_big<PhiloxSource, false><<<bb, 32 * BIG_WARPS, 0, st>>>(c, P, src);
+            }
+            ++g_launches;
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return fail_cuda(h, e, "k_digitise_big launch");
+        }
     }
     if (tp) cudaEventRecord(tp[2], st);
 

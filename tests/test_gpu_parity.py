@@ -199,6 +199,37 @@ def test_fine_pitch_planes_exercise_pool_rounds_and_overflow_retries(torch_cuda)
         assert res4.hits_numpy(d).tobytes() == res.hits_numpy(d).tobytes()
 
 
+def test_clusters_wider_than_the_profile_pool(torch_cuda):
+    """0.25 um pixels: practically every cluster spans more columns + rows than the 128-entry profile pool of a whole
+    group holds; 1 um pixels: some do.  Such (group, plane) pairs are served by k_digitise_big (both profiles per
+    pixel, no pool).  Deterministic mode must equal the oracle; in production mode the tables must not depend on which
+    of the two kernels served a pair (pools of 128 and 96 entries draw the line differently)."""
+    from pytestbeam_b200 import config as cfg
+    from oracle import cpu_oracle as co
+    from pytestbeam_b200.engine import Simulator
+    n = 600
+    setup = cfg.c1(n)
+    setup["beam"].update(sigma_x=1500.0, sigma_y=1500.0)
+    setup["devices"]["mimosa26_p2"].update(column=60000, row=40000, column_pitch=0.25, row_pitch=0.25, threshold=0)
+    setup["devices"]["mimosa26_p4"].update(column=20000, row=10000, column_pitch=1.0, row_pitch=1.0, threshold=0)
+    beam, devices, materials, names = cfg.flatten(setup)
+    run = co.run(beam, devices, materials, n, 81, 82)
+    assert len(run.hits[1]) > 2000 * n and len(run.hits[3]) > 100 * n     # thousands of hits per particle at 0.25 um
+    sim = Simulator(beam, devices, materials)
+    caps = [max(2 * len(h), 1000) for h in run.hits]
+    res = sim.run(0, n, injected=H.injected_for(sim, run, 0, n), keep_charge64=True, capacities=caps)
+    assert res.totals["error"] == 0
+    _compare_hits(res, run, len(devices))
+    assert res.totals["pixels"] == run.census["pixels"]
+    # production mode: 128- and 96-entry pools split the pairs differently between the two kernels
+    a = sim.run(1000, n, seed=5, capacities=caps)
+    small = Simulator(beam, devices, materials, pool_entries=96)
+    b = small.run(1000, n, seed=5, capacities=caps)
+    assert a.totals["hits"][1] > 2000 * n
+    for d in range(len(devices)):
+        assert a.hits_numpy(d).tobytes() == b.hits_numpy(d).tobytes(), names[d]
+
+
 def test_one_million_electrons_deterministic_in_chunks(torch_cuda):
     """BASELINE config 2's deterministic leg at the size the CPU oracle affords here: 1e6 electrons of the default
     telescope, fed to CUDA in four chunks of recorded variates with chained bases.  Every event / column / row must
