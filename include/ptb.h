@@ -25,8 +25,9 @@
  *   ptb_correlate   _eventloop_fast of the correlation plot (main/plotting.py:730-764)
  *
  * Error convention: 0 on success, negative PTB_E_* otherwise; nothing is thrown across the ABI.
- * Conditions detected on the device (slab overflow, oversized cluster box) are reported in PtbTotals.error, which
- * the caller reads after synchronising the stream.
+ * Conditions detected on the device (slab / scratch overflow, a cluster bounding box beyond 2^20 pixels) are reported
+ * in PtbTotals.error, which the caller reads after synchronising the stream; on an overflow the totals still hold the
+ * exact sizes, so the call can be repeated with them.
  * One handle per GPU; a handle is not thread-safe, distinct handles are independent.
  */
 #ifndef PTB_H_
@@ -78,7 +79,8 @@ typedef struct PtbDevice {
 
 typedef struct PtbOptions {
     int32_t pool_entries; /* box columns + rows one round of a 32-particle group may hold in shared memory; 0 = default
-                             (128).  Compile-time variants: 128 and 96 (drives the multi-round path in the tests) */
+                             (128).  Compile-time variants: 128 and 96 (drives the multi-round path in the tests).
+                             No limit on the clusters: a single cluster beyond it is served without the pool */
     int32_t _pad;
     double  trigger_accept; /* main/device.py:56 hard-codes 0.7; 0 = use that */
 } PtbOptions;
