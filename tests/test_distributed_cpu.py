@@ -20,6 +20,27 @@ def test_shard_ranges_tile_the_particles():
     assert list(exclusive_prefix(vals, 0)) == [0, 0] and list(exclusive_prefix(vals, 2)) == [7, 30]
 
 
+def test_numa_binding_is_a_no_op_without_nvml():
+    """No GPU driver here: the helper reports False and leaves the affinity alone."""
+    from pytestbeam_b200.pipeline import bind_host_to_gpu
+    before = os.sched_getaffinity(0)
+    assert bind_host_to_gpu(0) is False
+    assert os.sched_getaffinity(0) == before
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (CPU port on the host cores): stdout carries exactly the JSON line."""
+    import json, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--cpu-sample", "2000"], capture_output=True, text=True, timeout=300)
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert out.returncode == 0 and len(lines) == 1, out.stderr[-500:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "electrons/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
 def _worker(rank, size, port, folder, q):
     import torch.distributed as dist
     from pytestbeam_b200 import distributed as D
