@@ -139,8 +139,7 @@ struct WarpShared {
     float    rnr[32];                              // 1 / rows of the trimmed box
     uint32_t seedcr[32];
     uint8_t  evoff[32], accb[32];
-    unsigned long long cen_pixels;                 // census of the group, kept by lane 0
-    unsigned cen_pairs, cen_inside;
+    unsigned long long census;                     // census of the group (packed), kept by lane 0
 };
 
 // bytes of one warp's region: descriptors, profile pool (2 doubles per column / row)
@@ -423,10 +422,7 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
 
     // census of the group (digitised pairs, in-acceptance pairs, box pixels): summed over the warp plane by plane and
     // kept in shared memory by lane 0, so that it costs no registers across the plane loop
-    if (lane == 0) {
-        W.cen_pairs = W.cen_inside = 0u;
-        W.cen_pixels = 0ull;
-    }
+    if (lane == 0) W.census = 0ull;
 
     // Digitisation inputs (x, y, energy loss) of plane d: fetched one plane ahead with asynchronous copies into the
     // lane's shared-memory slot (free again as soon as the current plane's values sit in registers), so that the
@@ -449,6 +445,8 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
         cp_async_commit();
     };
     fetch(0);
+    int                my_rows = 0;    // lane d: hits of this group on plane d ...
+    unsigned long long my_base = 0;    // ... and the start of its scratch segment
 
 #pragma unroll 1
     for (int d = 0; d < D; ++d) {
@@ -467,14 +465,10 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
         int        cntT = cl.ncT * cl.nrT;        // pixels of that trimmed box: the only ones that can become hits
         const bool too_large = cl.too_large;
         const bool big = nprof > PC;              // more columns + rows than the profile pool holds
-        {
-            const unsigned pairs_d = __popc(__ballot_sync(FULL, digitised)), inside_d = __popc(__ballot_sync(FULL, inside));
-            const unsigned pixels_d = __reduce_add_sync(FULL, (unsigned)cnt);   // <= 32 boxes of <= 2^20 pixels
-            if (lane == 0) {
-                W.cen_pairs += pairs_d;
-                W.cen_inside += inside_d;
-                W.cen_pixels += pixels_d;
-            }
+        {   // census, one packed word: box pixels (<= 2^30 per group), in-acceptance pairs << 32, digitised pairs << 44
+            const unsigned long long pairs_d = __popc(__ballot_sync(FULL, digitised)), inside_d = __popc(__ballot_sync(FULL, inside));
+            const unsigned           pixels_d = __reduce_add_sync(FULL, (unsigned)cnt);   // <= 32 boxes of <= 2^20 pixels
+            if (lane == 0) W.census += (unsigned long long)pixels_d | (inside_d << 32) | (pairs_d << 44);
         }
 
         // A pair whose trimmed box has more columns + rows than the pool holds (pitch far below the cloud width) takes the
@@ -646,9 +640,10 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
             o_begin = o_end;
         }
         __syncwarp();
-        if (lane == 0) {
-            P.ws.table[(unsigned long long)d * P.n_groups + group] = (unsigned long long)n_plane;
-            P.ws.table[(unsigned long long)(D + 5 + d) * P.n_groups + group] = base;
+        // lane d keeps the plane's row count and segment start; the table is written once, after the last plane
+        if (lane == d) {
+            my_rows = n_plane;
+            my_base = base;
         }
         // device-side conditions go straight to the totals (rare), so that no error word has to live across the planes
         {
@@ -660,11 +655,16 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
 
 
     // ---- per-group counters for k_scan ---------------------------------------------------------------
+    if (lane < D) {
+        P.ws.table[(unsigned long long)lane * P.n_groups + group] = (unsigned long long)my_rows;
+        P.ws.table[(unsigned long long)(D + 5 + lane) * P.n_groups + group] = my_base;
+    }
     if (lane == 0) {
         unsigned long long *t = P.ws.table + group;
-        t[(unsigned long long)(D + 2) * P.n_groups] = W.cen_pairs;
-        t[(unsigned long long)(D + 3) * P.n_groups] = W.cen_inside;
-        t[(unsigned long long)(D + 4) * P.n_groups] = W.cen_pixels;
+        const unsigned long long census = W.census;
+        t[(unsigned long long)(D + 2) * P.n_groups] = census >> 44;
+        t[(unsigned long long)(D + 3) * P.n_groups] = (census >> 32) & 0xfffull;
+        t[(unsigned long long)(D + 4) * P.n_groups] = census & 0xffffffffull;
     }
 }
 
