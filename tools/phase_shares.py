@@ -14,12 +14,13 @@ src = open(os.path.join(here, '..', 'pytestbeam_b200', 'csrc', 'ptb_kernels.cu')
 def find(txt):
     for i, l in enumerate(src):
         if txt in l: return i + 1
+# (code inlined from describe() / profile_entry() is attributed to its call site in the kernel)
 marks = [('prolog', find('k_digitise(const __grid_constant__')), ('fetch', find('cp_async_wait_all();   //')),
-         ('descriptors', find('// ---- cluster descriptors')), ('trim', find('// A box pixel can only be kept')),
-         ('descr. store', find('int ncT = max(cb - ca + 1, 0)')), ('census+reserve', find('const unsigned pairs_d =')),
+         ('descriptors', find('// ---- cluster descriptors')), ('census+reserve', find('{   // census, one packed word')),
          ('rounds setup', find('// inclusive prefixes of the profile entries')), ('phase A', find('// ---- phase A')),
          ('phase B', find('// ---- phase B')), ('emit', find('// kept pixels of my particle in this step')),
          ('plane end', find('if (o_end >= 32) break;')), ('epilog', find('// ---- per-group counters for k_scan'))]
+marks.sort(key=lambda m: m[1])
 lines = open(src_csv).read().split('\n')
 starts = [i for i, l in enumerate(lines) if l.startswith('"Kernel Name"')] + [len(lines)]
 blk = blk % (len(starts) - 1)
