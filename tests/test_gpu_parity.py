@@ -199,6 +199,75 @@ def test_fine_pitch_planes_exercise_pool_rounds_and_overflow_retries(torch_cuda)
         assert res4.hits_numpy(d).tobytes() == res.hits_numpy(d).tobytes()
 
 
+def _random_setup(rng, n):
+    """A telescope drawn at random inside the schema of setup.yml: 2..9 planes, pitches from 3 um to centimetres
+    (single-pixel absorbers included), matrices from 1 x 1 to thousands of pixels, offsets of either sign up to the
+    beam width, thresholds from 0 to far above any charge, both trigger modes, both materials, tilted / displaced beam,
+    energies from 20 MeV to 6 GeV, rates on both branches of the Poisson sampler."""
+    from pytestbeam_b200 import config as cfg
+    n_planes = int(rng.integers(2, 10))
+    z, devices = 0, {}
+    for i in range(n_planes):
+        kind = rng.integers(0, 4)
+        if kind == 0:      # absorber: one big pixel
+            col = row = 1
+            pc = pr = float(rng.choice([20000.0, 40000.0, 5000.0]))
+            thick, mat, thr = float(rng.choice([200.0, 1000.0])), "lead", 1e9
+        else:
+            col, row = int(rng.integers(1, 3000)), int(rng.integers(1, 3000))
+            pc, pr = float(np.round(rng.uniform(3.0, 120.0), 2)), float(np.round(rng.uniform(3.0, 120.0), 2))
+            thick, mat = float(rng.choice([25.0, 50.0, 100.0, 300.0])), "silicon"
+            thr = float(rng.choice([0.0, 0.0, 1.0, 10.0, 100.0, 1000.0]))
+        devices[f"plane{i}"] = {
+            "column": col, "row": row, "column_pitch": pc, "row_pitch": pr, "thickness": thick, "z_position": z,
+            "delta_x": float(np.round(rng.normal(0, 1500), 1)), "delta_y": float(np.round(rng.normal(0, 1500), 1)),
+            "threshold": thr, "trigger": str(rng.choice(["triggered", "untriggered"])), "material": mat}
+        z += int(rng.integers(1000, 80000))
+    beam = {"energy": float(rng.choice([20.0, 100.0, 1000.0, 6000.0])), "sigma_x": float(rng.uniform(50, 6000)),
+            "sigma_y": float(rng.uniform(50, 6000)), "loc_x": float(rng.normal(0, 500)), "loc_y": float(rng.normal(0, 500)),
+            "x_disp": float(rng.uniform(0, 2e-3)), "y_disp": float(rng.uniform(0, 2e-3)),
+            "x_angle": float(rng.normal(0, 2e-3)), "y_angle": float(rng.normal(0, 2e-3)), "nmb_particles": n,
+            "particle_rate": float(rng.choice([5000.0, 2e8, 5e7]))}
+    return cfg.flatten({"devices": devices, "beam": beam, "data_output": None, "plotting": False, "saving_tracks": False})
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_geometries_deterministic(torch_cuda, seed):
+    """Deterministic-mode parity on telescopes drawn at random (see _random_setup): every event / column / row equal to
+    the oracle's, track state within 1e-6 relative, census equal."""
+    from oracle import cpu_oracle as co
+    from pytestbeam_b200.engine import Simulator
+    rng = np.random.default_rng(1000 + seed)
+    n = 4000
+    beam, devices, materials, names = _random_setup(rng, n)
+    rs = np.random.RandomState(77 + seed)
+    table = co.landau_table(rs, beam, devices, materials, 1 << 15)[:, :n]   # the pool of small runs can be empty (Q15)
+    run = co.run(beam, devices, materials, n, 300 + seed, 400 + seed, table_override=table)
+    sim = Simulator(beam, devices, materials)
+    caps = [max(2 * len(h), 1000) for h in run.hits]
+    res = sim.run(0, n, injected=H.injected_for(sim, run, 0, n), write_tracks=True, keep_charge64=True, capacities=caps)
+    assert res.totals["error"] == 0
+    _compare_hits(res, run, len(devices), exact_charge_fraction=0.995)
+    for i, k in enumerate(TRACK_KEYS):
+        want, got = run.tracks[i], res.tracks[k].cpu().numpy()
+        ok = np.isfinite(want)
+        assert np.array_equal(np.isfinite(got), ok), k                 # NaN below the electron mass stays NaN (Q17)
+        assert H.rel_err(got[ok], want[ok]) < 1e-6, k
+    assert np.array_equal(res.tracks["time_stamp"].cpu().numpy(), run.tracks[6])
+    for k in ("pairs", "inside", "pixels"):
+        assert res.totals[k] == run.census[k], k
+    # production mode on the same telescope: the tables do not depend on how the particle range is cut
+    whole = sim.run(500, n, seed=seed, capacities=caps)
+    cuts = [500, 500 + int(rng.integers(1, 200)), 500 + int(rng.integers(200, n - 1)), 500 + n]
+    bases, parts = None, []
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        r = sim.run(lo, hi - lo, seed=seed, bases_in=bases, capacities=caps)
+        bases = r.bases_out
+        parts.append([r.hits_numpy(d) for d in range(sim.D)])
+    for d in range(sim.D):
+        assert np.concatenate([p[d] for p in parts]).tobytes() == whole.hits_numpy(d).tobytes(), (cuts, names[d])
+
+
 def test_clusters_wider_than_the_profile_pool(torch_cuda):
     """0.25 um pixels: practically every cluster spans more columns + rows than the 128-entry profile pool of a whole
     group holds; 1 um pixels: some do.  Such (group, plane) pairs are served by k_digitise_big (both profiles per
