@@ -47,6 +47,7 @@ constexpr int      POOL_ENTRIES = 128;
 constexpr int      SMALL_POOL = 96;
 constexpr int      TRACK_BLOCK = 128;                   // k_tracks
 constexpr unsigned FULL = 0xffffffffu;
+constexpr uint32_t KFLAG_BIG_LAUNCHED = 1u << 31;     // internal flag handed to k_scan: k_digitise_big ran
 constexpr int      SCAN_SEGMENTS = 16;                  // every counter column is scanned by this many blocks
 
 static unsigned long long g_launches = 0;
@@ -884,6 +885,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(int D, unsigned long long
             totals->reserved[c] = ws.alloc[c * 16];   // scratch rows the groups asked for (k_digitise has finished)
             if (bases_out) bases_out->hits[c] = recycle ? 0ull : b + total;
         } else if (c == D) {
+            // pairs left to k_digitise_big although it was not launched (cannot happen while ptb_create's bound on the
+            // cluster width holds): their hits are missing, say so
+            if ((flags & PTB_DIGITISE) && !(flags & KFLAG_BIG_LAUNCHED) && ws.alloc[PTB_MAX_PLANES * 16] != 0)
+                atomicOr(&totals->error, PTB_DEV_BOX_TOO_LARGE);
             const int64_t b = bases_in ? bases_in->event : 0;
             ws.bases_used->event = b;
             totals->accepted = total;
@@ -1490,6 +1495,7 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
     if (e != cudaSuccess) return fail_cuda(h, e, "memset totals");
 
     const bool keep64 = (flags & PTB_KEEP_CHARGE64) != 0;
+    bool       big_launched = false;
     cudaEvent_t *tp = timing_pair(h);
     if (tp) cudaEventRecord(tp[0], st);
     if (!(flags & PTB_TRACKS_FROM_TABLE)) {
@@ -1527,7 +1533,8 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
         if (e != cudaSuccess) return fail_cuda(h, e, "k_digitise launch");
         // clusters wider than the profile pool: possible with the caller's own variates / deposits, or when the geometry
         // says so (ptb_create); the default telescope never launches this
-        if (run->injected || (flags & PTB_TRACKS_FROM_TABLE) || h->may_be_big) {
+        big_launched = run->injected || (flags & PTB_TRACKS_FROM_TABLE) || h->may_be_big;
+        if (big_launched) {
             const unsigned long long items = P.n_groups * (unsigned long long)D;
             const unsigned bb = (unsigned)std::min<unsigned long long>((items + BIG_WARPS - 1) / BIG_WARPS,
                                                                        (unsigned long long)h->sm_count * 16);
@@ -1548,7 +1555,7 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
     if (tp) cudaEventRecord(tp[2], st);
 
     k_scan_sums<<<(D + 5) * SCAN_SEGMENTS, SCAN_THREADS, 0, st>>>(P.n_groups, P.ws);
-    k_scan<<<(D + 5) * SCAN_SEGMENTS, SCAN_THREADS, 0, st>>>(D, P.n_groups, flags, P.ws, run->bases_in, run->bases_out,
+    k_scan<<<(D + 5) * SCAN_SEGMENTS, SCAN_THREADS, 0, st>>>(D, P.n_groups, flags | (big_launched ? KFLAG_BIG_LAUNCHED : 0u), P.ws, run->bases_in, run->bases_out,
                                                              run->totals);
     g_launches += 2;
     e = cudaGetLastError();
