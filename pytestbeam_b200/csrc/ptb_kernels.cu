@@ -52,6 +52,20 @@ constexpr int      SCAN_SEGMENTS = 16;                  // every counter column 
 
 static unsigned long long g_launches = 0;
 
+// Index checks of the warp-cooperative phases (compute-sanitizer is not available on the GPU pool): compiled in with
+// -DPTB_DEBUG_CHECKS (tools/build_variants.py dbg=-DPTB_DEBUG_CHECKS), a violated check raises PTB_DEV_INTERNAL in the totals.
+#define PTB_DEV_INTERNAL 0x80000000u
+#ifdef PTB_DEBUG_CHECKS
+#define PTB_DBG_CHECK(cond)                                           \
+    do {                                                              \
+        if (!(cond)) atomicOr(&P.totals->error, PTB_DEV_INTERNAL);    \
+    } while (0)
+#else
+#define PTB_DBG_CHECK(cond) \
+    do {                    \
+    } while (0)
+#endif
+
 // ---------------------------------------------------------------------------------------------------
 // workspace layout (device memory owned by the caller)
 // ---------------------------------------------------------------------------------------------------
@@ -549,8 +563,10 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
                 const int      rankA = doneA + __popc(endsA & lanemask_lt());
                 doneA += __popc(endsA);
                 if (t < prof_total) {
+                    PTB_DBG_CHECK(rankA >= 0 && rankA < 32 && t < PC);
                     const int    own = W.ownA[rankA];
                     const int    e = t - W.poff[own];
+                    PTB_DBG_CHECK(own < 32 && e >= 0 && e < (int)W.ncols[own] + (int)W.nrows[own]);
                     const int    ncl = W.ncols[own];
                     const int    a = e >= ncl ? 1 : 0;            // axis of the entry: a column (x) or a row (y)
                     const int    idx = W.lo[a][own] + (e - (a ? ncl : 0));
@@ -597,6 +613,8 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
                         // more than the rounding of the product for p < 4096
                         const int ci = __float2int_rz(((float)p + 0.5f) * W.rnr[own]);
                         const int ri = p - ci * nrw;
+                        PTB_DBG_CHECK(own < 32 && p >= 0 && ci >= 0 && ci < ncl && ri >= 0 && ri < nrw && po >= 0 &&
+                                      po + ncl + nrw <= PC);
                         // index of the pixel in the reference's (column-major) walk over its full box: the injected
                         // noise variates are keyed by it
                         const int    jf = W.jbase[own] + ci * W.nrfull[own] + ri;
@@ -627,6 +645,7 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
                 const unsigned emask = kballot | __ballot_sync(FULL, fb);
                 if ((keep || fb) && room) {
                     const unsigned at = (unsigned)n_plane + __popc(emask & lanemask_lt());
+                    PTB_DBG_CHECK((int)at < ub && base + at < P.ws.cap[d]);
                     seg_hit[at] = make_uint2(hcr, __float_as_uint((float)hq));
                     seg_ev[at] = W.evoff[own];
                     if (keep64) seg_q64[at] = hq;
@@ -756,6 +775,7 @@ __global__ void __launch_bounds__(32 * BIG_WARPS) k_digitise_big(const __grid_co
                 const unsigned kballot = __ballot_sync(FULL, keep);
                 if (keep && room) {
                     const unsigned at = (unsigned)(n_plane + kept) + __popc(kballot & lanemask_lt());
+                    PTB_DBG_CHECK((int)at < ub && base + at < P.ws.cap[d]);
                     seg_hit[at] = make_uint2(hcr, __float_as_uint((float)hq));
                     seg_ev[at] = W.evoff[b];
                     if (KEEP64) seg_q64[at] = hq;

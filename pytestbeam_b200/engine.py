@@ -262,6 +262,8 @@ class Simulator:
             torch.cuda.synchronize(self.device)
             tot = self.decode_totals(totals, self.D)
             err = tot["error"]
+            if err & ~(N.PTB_DEV_BOX_TOO_LARGE | N.PTB_DEV_SLAB_OVERFLOW | N.PTB_DEV_SCRATCH_OVERFLOW):
+                raise PtbError(f"device reported an internal consistency failure (error bits {err:#x})")
             if err & N.PTB_DEV_BOX_TOO_LARGE:
                 raise PtbError("a cluster bounding box exceeded 2^20 pixels (check pitch / geometry)")
             if err & (N.PTB_DEV_SLAB_OVERFLOW | N.PTB_DEV_SCRATCH_OVERFLOW):
