@@ -32,7 +32,10 @@
 
 namespace ptb {
 
-constexpr int      WARPS_PER_BLOCK = 4;                 // k_digitise
+#ifndef PTB_DIGI_WARPS
+#define PTB_DIGI_WARPS 4
+#endif
+constexpr int      WARPS_PER_BLOCK = PTB_DIGI_WARPS;    // k_digitise
 constexpr int      BLOCK = 32 * WARPS_PER_BLOCK;
 #ifndef PTB_DIGI_MIN_BLOCKS
 #define PTB_DIGI_MIN_BLOCKS 8
