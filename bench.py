@@ -45,13 +45,14 @@ def digitise_flops_per_particle(tot: dict, n: int) -> float:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled every 20 ms; the samples stamped inside the timed region count."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.t_begin = self.t_end = None
 
     def start(self):
         try:
@@ -66,26 +67,38 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def begin(self):
+        import datetime
+        self.t_begin = datetime.datetime.now()
+
+    def end(self):
+        import datetime
+        self.t_end = datetime.datetime.now()
+
     def stop(self) -> dict:
+        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
-        sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        slack = datetime.timedelta(milliseconds=25)       # one sampling period either side of the region
+        inside, every, mx, reasons = [], [], None, set()
         for r in self.rows:
             try:
-                sm.append(float(r[0]))
-                mx = float(r[1])
-                for nm, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
+                ts = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f")
+                clk, mx = float(r[1]), float(r[2])
             except Exception:
                 continue
-        sm.sort()
-        busy = [v for v in sm if mx and v > 0.5 * mx] or sm
-        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+            every.append(clk)
+            if self.t_begin and self.t_end and self.t_begin - slack <= ts <= self.t_end + slack:
+                inside.append(clk)
+                for nm, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        use = sorted(inside or every)
+        return {"sm_mhz": use[len(use) // 2] if use else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(inside), "samples_total": len(every)}
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -202,6 +215,10 @@ def run_gpu(args):
         p.run(first, K)
         return None
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()          # up and sampling by the time the timed region begins
+
     # warm-up: W untimed steps on both paths (for N>1 including the prefix exchange, so that the NCCL communicator
     # exists before the timed region)
     if world > 1:
@@ -215,17 +232,16 @@ def run_gpu(args):
     fp64_peak = lib.ptb_measure_fp64_peak(None) if rank == 0 else 0.0
     sync_all()
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = lib.ptb_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sim.timing(True)                 # CUDA events around every k_simulate launch, on the launch stream
     sync_all()
+    sampler.begin()
     e0.record()
     job(pipe, False)
     e1.record()
     sync_all()
+    sampler.end()
     ms = e0.elapsed_time(e1)
     launches = lib.ptb_launch_count() - launches0
     trk_ms, dig_ms, sim_launches = sim.timing_read()
