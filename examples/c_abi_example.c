@@ -1,0 +1,117 @@
+/*
+ * The C ABI of libptb_b200 used from plain C: no Python, no torch -- device memory from the CUDA runtime, the
+ * default telescope of the reference's setup.yml, production (Philox) mode.  Prints the hit rows per plane and the
+ * first rows of the last plane.
+ *
+ *   nvcc -x c -I include -o c_abi_example examples/c_abi_example.c -L pytestbeam_b200/_lib -lptb_b200 -lcudart
+ *   LD_LIBRARY_PATH=pytestbeam_b200/_lib ./c_abi_example [n_electrons] [seed]
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "ptb.h"
+
+#define CK(call)                                                                      \
+    do {                                                                              \
+        cudaError_t e_ = (call);                                                      \
+        if (e_ != cudaSuccess) {                                                      \
+            fprintf(stderr, "%s: %s\n", #call, cudaGetErrorString(e_));               \
+            return 2;                                                                 \
+        }                                                                             \
+    } while (0)
+
+int main(int argc, char **argv)
+{
+    const uint64_t n = argc > 1 ? strtoull(argv[1], NULL, 10) : 1000000ull;
+    const uint64_t seed = argc > 2 ? strtoull(argv[2], NULL, 10) : 1ull;
+
+    /* pytestbeam/setup.yml:2-109 and material.yml (silicon), flattened the way ptb_create expects them */
+    const double z[7] = {0, 30250, 61800, 202550, 225000, 250700, 288150};
+    const double dx[7] = {100, 0, 0, 100, 0, 0, 0};
+    PtbDevice    dev[7];
+    memset(dev, 0, sizeof(dev));
+    for (int d = 0; d < 7; ++d) {
+        const int itk = d == 6;
+        dev[d].ncol = itk ? 400 : 1152;
+        dev[d].nrow = itk ? 384 : 576;
+        dev[d].pitch_c = dev[d].pitch_r = itk ? 50.0 : 18.4;
+        dev[d].thickness = itk ? 300.0 : 50.0;
+        dev[d].z = z[d];
+        dev[d].delta_x = dx[d];
+        dev[d].threshold_e = itk ? 1000.0 : 100.0;
+        dev[d].triggered = itk;
+        dev[d].rad_length = 93650;
+        dev[d].Z = 14;
+        dev[d].A = 24;
+        dev[d].rho = 2.33;
+    }
+    PtbBeam beam = {5000.0, 5000.0, 5000.0, 0.0, 0.0, 1e-4, 1e-4, 0.0, 0.0, 5000.0};
+
+    PtbHandle h = NULL;
+    int       rc = ptb_create(&beam, dev, 7, NULL, &h);
+    if (rc != PTB_OK) {
+        fprintf(stderr, "ptb_create: %d %s\n", rc, ptb_last_error(h));
+        return 1;
+    }
+
+    PtbRun run;
+    memset(&run, 0, sizeof(run));
+    run.first = 0;
+    run.n = n;
+    run.seed = seed;
+    run.flags = PTB_DIGITISE | PTB_RECYCLE_SLABS;
+    uint64_t cap[PTB_MAX_PLANES] = {0};
+    for (int d = 0; d < 7; ++d) {
+        cap[d] = (uint64_t)(1.5 * (double)n) + 4096; /* 1.2 hits per electron and plane on this telescope */
+        run.slabs[d].capacity = cap[d];
+        CK(cudaMalloc((void **)&run.slabs[d].event, cap[d] * sizeof(int64_t)));
+        CK(cudaMalloc((void **)&run.slabs[d].col, cap[d] * sizeof(uint16_t)));
+        CK(cudaMalloc((void **)&run.slabs[d].row, cap[d] * sizeof(uint16_t)));
+        CK(cudaMalloc((void **)&run.slabs[d].charge, cap[d] * sizeof(float)));
+    }
+    CK(cudaMalloc((void **)&run.totals, sizeof(PtbTotals)));
+    run.workspace_bytes = ptb_workspace_bytes(h, n, cap, NULL, run.flags);
+    CK(cudaMalloc(&run.workspace, run.workspace_bytes));
+
+    rc = ptb_simulate(h, &run, NULL); /* default stream */
+    if (rc != PTB_OK) {
+        fprintf(stderr, "ptb_simulate: %d %s\n", rc, ptb_last_error(h));
+        return 1;
+    }
+    PtbTotals tot;
+    CK(cudaMemcpy(&tot, run.totals, sizeof(tot), cudaMemcpyDeviceToHost)); /* synchronises */
+    if (tot.error) {
+        fprintf(stderr, "device error bits %#x\n", tot.error);
+        return 1;
+    }
+    printf("electrons %llu accepted %llu pixels %llu\n", (unsigned long long)n, (unsigned long long)tot.accepted,
+           (unsigned long long)tot.pixels);
+    for (int d = 0; d < 7; ++d) printf("plane %d rows %llu\n", d, (unsigned long long)tot.hits[d]);
+
+    /* the first rows of the last plane, as the reference's (event_number, frame, column, row, charge) records */
+    const uint64_t show = tot.hits[6] < 5 ? tot.hits[6] : 5;
+    void          *packed = NULL;
+    CK(cudaMalloc(&packed, 18 * (show ? show : 1)));
+    if (show) {
+        rc = ptb_pack_hits(&run.slabs[6], show, packed, NULL);
+        if (rc != PTB_OK) return 1;
+        unsigned char rows[5 * 18];
+        CK(cudaMemcpy(rows, packed, 18 * show, cudaMemcpyDeviceToHost));
+        for (uint64_t i = 0; i < show; ++i) {
+            int64_t  ev;
+            uint16_t f, c, r;
+            float    q;
+            memcpy(&ev, rows + 18 * i, 8);
+            memcpy(&f, rows + 18 * i + 8, 2);
+            memcpy(&c, rows + 18 * i + 10, 2);
+            memcpy(&r, rows + 18 * i + 12, 2);
+            memcpy(&q, rows + 18 * i + 14, 4);
+            printf("itkpix row %llu: event %lld frame %u column %u row %u charge %.6f\n", (unsigned long long)i,
+                   (long long)ev, f, c, r, q);
+        }
+    }
+    ptb_destroy(h);
+    return 0;
+}
