@@ -60,3 +60,15 @@ def test_struct_layout_agrees_with_a_c_compiler(tmp_path):
 def test_launch_counter_starts_at_zero_without_gpu_work():
     lib = native.load()
     assert lib.ptb_launch_count() >= 0
+
+
+def test_plain_c_example_compiles_against_the_header():
+    """examples/c_abi_example.c is C (not C++): the header must be usable from a C compiler."""
+    import shutil, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda_inc = "/usr/local/cuda/include"
+    if shutil.which("gcc") is None or not os.path.isdir(cuda_inc):
+        import pytest
+        pytest.skip("gcc or the CUDA headers are not installed")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(root, "include"),
+                           "-I", cuda_inc, os.path.join(root, "examples", "c_abi_example.c")])
