@@ -1,10 +1,12 @@
 """TEST INFRASTRUCTURE ONLY -- import shim for the *unmodified* reference (rpartzsch/pytestbeam).
 
-Loads ``main.hit`` / ``main.device`` from ``/root/reference/pytestbeam`` (the read-only mount that
-exists in the build container only) after stubbing the two third-party imports that are absent on
-this image (``numba_progress`` and ``tables``).  Nothing on the product path
+Loads ``main.hit`` / ``main.device`` from ``baseline/_ref/pytestbeam`` (the git-ignored installation made by
+``tools/install_reference.py``, which travels to the GPU box) or, failing that, from ``/root/reference/pytestbeam``
+(the read-only mount that exists in the build container only), after stubbing the two third-party imports that
+are absent on this image (``numba_progress`` and ``tables``).  Nothing on the product path
 imports this module; it is used by ``oracle/make_golden.py`` (fixture generation, run in the build
-container) and by the ``-m "not gpu"`` tests that pin the oracle when the mount is present.
+container), by the ``-m "not gpu"`` tests that pin the oracle when a reference tree is present, and by
+``bench.py``'s two CPU legs (``--impl reference`` and ``cpu_baseline``), which time the reference's own Numba path.
 
 Reference call sites this drives: ``main/hit.py:8`` (``tracks``), ``main/device.py:7``
 (``calculate_device_hit``).
@@ -18,7 +20,8 @@ import types
 
 import numpy as np
 
-REF_CANDIDATES = ("/root/reference",)
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_CANDIDATES = (os.path.join(_ROOT, "baseline", "_ref"), "/root/reference")
 
 _loaded = None
 
@@ -47,7 +50,7 @@ def load():
         return _loaded
     root = reference_root()
     if root is None:
-        raise RuntimeError("reference tree not present (it only exists in the build container)")
+        raise RuntimeError("reference tree not present (baseline/_ref is made by tools/install_reference.py)")
     from numba import int64, njit
     from numba.experimental import jitclass
 
@@ -118,3 +121,62 @@ def run_reference(beam: dict, devices: list, materials: list, names: list, seed_
     device.calculate_device_hit(beam, devices, ht, names, "", log)
     hits = {k: v.copy() for k, v in capture.items()}
     return tracks, energy_lost, hits
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# timing of the reference's own hot path (bench.py's CPU legs)
+# ---------------------------------------------------------------------------------------------------------------
+
+def timed_run(beam: dict, devices: list, materials: list, names: list, seed: int):
+    """One pass of the unmodified ``hit.tracks`` (main/hit.py:8) + ``device.calculate_device_hit`` (main/device.py:7)
+    with the HDF5 writer replaced by an in-memory capture.  Returns (seconds, hit rows)."""
+    import time
+    hit, device, capture, nseed = load()
+    log = logging.getLogger("ptb_reference")
+    capture.clear()
+    np.random.seed(seed & 0x7FFFFFFF)
+    nseed((seed + 1) & 0x7FFFFFFF)
+    t = time.perf_counter()
+    ht = hit.tracks(beam, devices, materials, log)
+    device.calculate_device_hit(beam, devices, ht, names, "", log)
+    dt = time.perf_counter() - t
+    rows = sum(len(v) for v in capture.values())
+    capture.clear()
+    return dt, rows
+
+
+def warm_jit(setup_fn, flatten):
+    """Compile the reference's two Numba loops with a throw-away N=2000 pass."""
+    beam, devices, materials, names = flatten(setup_fn(2000))
+    return timed_run(beam, devices, materials, names, 12345)[0]
+
+
+def _pool_worker(args):
+    setup_fn, flatten, n, seed = args
+    beam, devices, materials, names = flatten(setup_fn(n))
+    return timed_run(beam, devices, materials, names, seed)
+
+
+class ReferencePool:
+    """``workers`` forked processes that share the parent's warm JIT (the reference has no threading of its own:
+    independent processes with distinct seeds are the fairest all-core figure)."""
+
+    def __init__(self, workers: int):
+        import multiprocessing as mp
+        self.workers = int(workers)
+        self.pool = mp.get_context("fork").Pool(self.workers) if self.workers > 1 else None
+
+    def rate(self, setup_fn, flatten, n_each: int, seed: int):
+        """(electrons/s, hit rows/s) of one round: every worker simulates n_each electrons."""
+        import time
+        jobs = [(setup_fn, flatten, n_each, seed + 7919 * i) for i in range(self.workers)]
+        t = time.perf_counter()
+        res = self.pool.map(_pool_worker, jobs, chunksize=1) if self.pool else [_pool_worker(jobs[0])]
+        wall = time.perf_counter() - t
+        return n_each * self.workers / wall, sum(r for _, r in res) / wall
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
+            self.pool = None
