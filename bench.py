@@ -9,8 +9,13 @@ digitisation, ordered hit collection into structure-of-arrays slabs) over one ch
 config 2: 1e8 electrons on one B200.  N>1 (torchrun): every rank owns a contiguous index range of K*C electrons,
 event-number / time bases come from one all-gather of per-rank prefixes, no data-path collective (weak scaling).
 
---impl reference times the CPU port of the reference algorithm (oracle/, kind "port": the reference is Python+Numba
-and cannot travel to the GPU box) on all host cores for the same workload, metric and unit.
+After the timed passes every run checks its own output (`shard_check`): the ranks' tables, digested with ptb_digest and
+put end to end, must equal what rank 0 produces for the whole range alone; a mismatch ends the run non-zero.
+--config c5 is BASELINE config 5 as one timed job (fixed total, index-range shards, HDF5 files for the first 1e7).
+
+--impl reference times the reference's own CPU implementation on all host cores for the same workload, metric and
+unit: the unmodified Numba path from baseline/_ref (tools/install_reference.py; kind "reference"), or the oracle port
+(kind "port") when no reference tree is on the box.
 """
 from __future__ import annotations
 
@@ -173,7 +178,7 @@ def run_reference(args):
     legs = None
     try:
         sample = args.cpu_sample or 100_000       # BASELINE config 1's size, per process and step
-        legs = reference_legs(0, sample, workers, rounds=args.steps, warm_rounds=args.warmup) if workers > 1 else \
+        legs = None if args.reference_tree == "none" else reference_legs(0, sample, workers, rounds=args.steps, warm_rounds=args.warmup) if workers > 1 else \
             reference_legs(sample, 0, 1)
     except Exception as exc:                      # a broken numba install must not take the arm down: say so, use the port
         print(f"reference tree unusable ({exc!r}); timing the oracle port instead", file=sys.stderr)
@@ -217,83 +222,221 @@ def run_reference(args):
 # GPU arm
 # --------------------------------------------------------------------------------------------------------------
 
-def run_gpu(args):
-    import numpy as np
-    import torch
-    import torch.distributed as dist
+M64 = (1 << 64) - 1
 
-    from pytestbeam_b200 import config as cfg
-    from pytestbeam_b200 import native as N
-    from pytestbeam_b200.engine import Simulator
-    from pytestbeam_b200.distributed import exchange_bases
-    from pytestbeam_b200.pipeline import ChunkPipeline, bind_host_to_gpu
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
-    torch.cuda.set_device(local)
-    numa_bound = bind_host_to_gpu(local) if world > 1 else False   # host buffers next to this rank's GPU
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+class Job:
+    """One rank's share of a benchmark job: contiguous index range [first, first + n), chunked."""
 
-    K, W, chunk, seed = args.steps, args.warmup, args.chunk, args.seed
-    setup_fn = {"default": cfg.default_setup, "c3": cfg.c3, "c4": cfg.c4}[args.config]
-    workload = WORKLOAD if args.config == "default" else f"BASELINE config {args.config} (pytestbeam_b200/config.py), production RNG"
-    beam, devices, materials, _ = cfg.flatten(setup_fn(chunk * K * world))
-    sim = Simulator(beam, devices, materials)
-    D = sim.D
-    lib = sim.lib
-    n_rank = chunk * K
-    first = rank * n_rank            # contiguous index range of this rank
-    pipe = ChunkPipeline(sim, chunk, seed=seed)
-    host_pipe = ChunkPipeline(sim, chunk, seed=seed, host=True, capacities=pipe.caps)
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def job(p, to_host):
-        """The timed region: shard prefixes (N>1), then K chunks."""
-        if world > 1:
-            acc, tsum = sim.prefix(first, n_rank, seed=seed)          # this rank's own range only
-            p.set_bases(*exchange_bases(acc, tsum, device=sim.device))  # one all-gather of 2 int64 per rank
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        from pytestbeam_b200 import config as cfg
+        from pytestbeam_b200.engine import Simulator
+        from pytestbeam_b200.pipeline import bind_host_to_gpu, shard_range
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus:
+            raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={self.world}: launch with torchrun --nproc-per-node {args.gpus}")
+        torch.cuda.set_device(self.local)
+        self.numa_bound = bind_host_to_gpu(self.local) if self.world > 1 else False   # host buffers next to this rank's GPU
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.chunk, self.seed = args.chunk, args.seed
+        if args.config == "c5":
+            # BASELINE config 5: a fixed total (strong scaling), cut into index-range shards of whole chunks
+            total = int(args.electrons)
+            self.first, self.n_rank = shard_range(total // self.chunk, self.rank, self.world)
+            self.first, self.n_rank = self.first * self.chunk, self.n_rank * self.chunk
+            self.total = (total // self.chunk) * self.chunk
+            setup_fn = cfg.c5
         else:
-            p.set_bases(0, 0)
+            self.n_rank = self.chunk * args.steps
+            self.first = self.rank * self.n_rank
+            self.total = self.n_rank * self.world
+            setup_fn = {"default": cfg.default_setup, "c3": cfg.c3, "c4": cfg.c4}[args.config]
+        self.K = self.n_rank // self.chunk
+        self.setup = cfg.flatten(setup_fn(self.total))
+        beam, devices, materials, self.names = self.setup
+        self.sim = Simulator(beam, devices, materials)
+        self.D = self.sim.D
+
+    def sync_all(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def bases(self):
+        """(event base, time base) of this rank: its own prefix kernel + one all-gather of 2 int64 per rank."""
+        from pytestbeam_b200.distributed import exchange_bases
+        if self.world == 1:
+            return 0, 0
+        acc, tsum = self.sim.prefix(self.first, self.n_rank, seed=self.seed)
+        return exchange_bases(acc, tsum, device=self.sim.device)
+
+    def max_over_ranks(self, *vals):
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.sim.device)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in t.cpu()]
+
+
+def digest_range(sim, first, n, chunk, seed, ev_base, t_base, pipe=None):
+    """Per-plane checksums (ptb_digest) of the hit tables of particles [first, first+n), simulated in chunks with bases
+    chained from (ev_base, t_base).  Returns a [D][7] list of Python ints modulo 2^64 with S2 taken relative to this
+    range's first row."""
+    import torch
+    from pytestbeam_b200.engine import Simulator
+    from pytestbeam_b200.pipeline import ChunkPipeline
+    D = sim.D
+    pipe = pipe or ChunkPipeline(sim, chunk, seed=seed, n_buffers=1)
+    pipe.set_bases(ev_base, t_base)
+    out = torch.zeros(D, 7, dtype=torch.int64, device=sim.device)
+    rows = [0] * D
+    s = pipe.sets[0]
+    for lo in range(first, first + n, pipe.chunk):
+        m = min(pipe.chunk, first + n - lo)
+        pipe._launch(s, lo, m)
+        tot = Simulator.decode_totals(s["totals"], D)        # one host read per chunk: this pass is not timed
+        if tot["error"]:
+            raise SystemExit(f"device error bits {tot['error']:#x} in the check pass")
+        for d in range(D):
+            sim.digest(s["slabs"][d], tot["hits"][d], rows[d], out[d])
+            rows[d] += tot["hits"][d]
+    torch.cuda.synchronize()
+    return [[int(v) & M64 for v in row] for row in out.cpu().tolist()]
+
+
+def combine_digests(per_rank):
+    """Rank-local digests (S2 relative to the rank's first row) -> the digest of the concatenated table."""
+    D = len(per_rank[0])
+    tot = [[0] * 7 for _ in range(D)]
+    for d in range(D):
+        base = 0
+        for dig in per_rank:
+            w = dig[d]
+            for j in range(6):
+                tot[d][j] = (tot[d][j] + w[j]) & M64
+            tot[d][6] = (tot[d][6] + w[6] + base * w[5]) & M64
+            base += w[0]
+    return tot
+
+
+def shard_check(job, args):
+    """Are the tables of the N shards, put end to end, the tables one GPU produces for the whole range?  Every rank
+    digests its own range (same seed, same bases as the timed pass), rank 0 gathers and combines the digests and then
+    simulates the WHOLE range [0, N*n) alone, bases chained from zero, with a different chunk size.  At N=1 the second
+    pass checks the invariance under re-chunking only."""
+    import torch
+    sim, world, rank = job.sim, job.world, job.rank
+    ev, t = job.bases()
+    mine = digest_range(sim, job.first, job.n_rank, job.chunk, job.seed, ev, t)
+    gathered = [mine]
+    if world > 1:
+        # the words are unsigned modulo 2^64; they travel as the int64 with the same bits
+        me = torch.tensor([[v - (1 << 64) if v >= (1 << 63) else v for v in row] for row in mine], dtype=torch.int64,
+                          device=sim.device)
+        parts = [torch.zeros_like(me) for _ in range(world)]
+        job.dist.all_gather(parts, me)
+        gathered = [[[int(v) & M64 for v in row] for row in p.cpu().tolist()] for p in parts]
+    result = None
+    if rank == 0:
+        sharded = combine_digests(gathered)
+        limit = int(args.check_limit)
+        n_check = min(job.total, limit)
+        if n_check == job.total:
+            alone = digest_range(sim, 0, job.total, max(32, (job.chunk * 3) // 4 + 17), job.seed, 0, 0)
+            equal, how = alone == sharded, "rank 0 re-ran the whole range alone, bases chained from zero, other chunk size"
+        else:
+            # too large to repeat on one GPU within the time budget: compare the head of the range, which still
+            # crosses every rank boundary it contains
+            alone = digest_range(sim, 0, n_check, max(32, (job.chunk * 3) // 4 + 17), job.seed, 0, 0)
+            equal, how = None, f"whole-range repeat skipped (> {limit:.3g} electrons)"
+        result = {"equal": equal, "rows": sum(w[0] for w in sharded), "electrons": job.total, "ranks": world, "how": how,
+                  "digest_words": "rows, sum event, sum column, sum row, sum charge bits, S1, S2 (order-sensitive); per plane",
+                  "sharded": {job.names[d]: sharded[d] for d in range(job.D)}}
+        if equal is False:
+            result["alone"] = {job.names[d]: alone[d] for d in range(job.D)}
+    if world > 1:
+        job.dist.barrier()
+    return result
+
+
+def entry_point_rate(n: int, seed: int):
+    """The reference-shaped entry: hit.tracks + device.calculate_device_hit of the drop-in modules, files included
+    (seven *_dut.h5 tables streamed to a scratch directory)."""
+    import logging
+    import shutil
+    import tempfile
+    from pytestbeam_b200 import config as cfg
+    from pytestbeam_b200.main import device, hit
+    beam, devices, materials, names = cfg.flatten(cfg.default_setup(n))
+    beam["seed"] = seed
+    log = logging.getLogger("bench-entry")
+    log.setLevel(logging.WARNING)
+    tmp = tempfile.mkdtemp(prefix="ptb_entry_", dir=os.environ.get("PTB_ENTRY_DIR") or None)
+    try:
+        t = time.perf_counter()
+        tables = hit.tracks(beam, devices, materials, log)
+        device.calculate_device_hit(beam, devices, tables, names, tmp + "/", log)
+        dt = time.perf_counter() - t
+        size = sum(os.path.getsize(os.path.join(tmp, f)) for f in os.listdir(tmp))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return {"value": n / dt, "unit": UNIT, "electrons": n, "seconds": dt, "file_bytes": size,
+            "what": "hit.tracks + device.calculate_device_hit (pytestbeam_b200.main), seven streamed *_dut.h5 files written"}
+
+
+def run_gpu(args):
+    import torch
+
+    from pytestbeam_b200.pipeline import ChunkPipeline
+
+    job = Job(args)
+    sim, D, lib = job.sim, job.D, job.sim.lib
+    world, rank, chunk, seed = job.world, job.rank, job.chunk, job.seed
+    K, W = job.K, args.warmup
+    workload = {"default": WORKLOAD, "c5": WORKLOAD + " (BASELINE config 5: fixed total, index-range shards)"}.get(
+        args.config, f"BASELINE config {args.config} (pytestbeam_b200/config.py), production RNG")
+    pipe = ChunkPipeline(sim, chunk, seed=seed)
+    host_pipe = ChunkPipeline(sim, chunk, seed=seed, host=True, capacities=pipe.caps, scratch_rows=pipe.rows)
+
+    def run_job(p, to_host):
+        """The timed region: shard prefixes (N>1), then this rank's K chunks."""
+        p.set_bases(*job.bases())
         if to_host:
-            return p.run_to_host(first, K)
-        p.run(first, K)
+            return p.run_to_host(job.first, K)
+        p.run(job.first, K)
         return None
 
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(job.local)
     if rank == 0:
         sampler.start()          # up and sampling by the time the timed region begins
 
     # warm-up: W untimed steps on both paths (for N>1 including the prefix exchange, so that the NCCL communicator
     # exists before the timed region)
     if world > 1:
-        exchange_bases(*sim.prefix(first, min(n_rank, 1 << 20), seed=seed), device=sim.device)
+        job.bases()
     pipe.set_bases(0, 0)
-    pipe.run(first, W)
+    pipe.run(job.first, W)
     host_pipe.set_bases(0, 0)
-    host_pipe.run_to_host(first, max(W, 2))
-    sync_all()
-
+    host_pipe.run_to_host(job.first, max(W, 2))
+    job.sync_all()
     fp64_peak = lib.ptb_measure_fp64_peak(None) if rank == 0 else 0.0
-    sync_all()
+    job.sync_all()
 
     launches0 = lib.ptb_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sim.timing(True)                 # CUDA events around every k_simulate launch, on the launch stream
-    sync_all()
+    sim.timing(True)                 # CUDA events around every k_tracks / k_digitise launch, on the launch stream
+    job.sync_all()
     sampler.begin()
     e0.record()
-    job(pipe, False)
+    run_job(pipe, False)
     e1.record()
-    sync_all()
+    job.sync_all()
     sampler.end()
     ms = e0.elapsed_time(e1)
     launches = lib.ptb_launch_count() - launches0
@@ -302,26 +445,25 @@ def run_gpu(args):
     launch_ms = dig_ms / max(sim_launches, 1)        # dominant kernel: k_digitise
     tracks_launch_ms = trk_ms / max(sim_launches, 1)
     clocks = sampler.stop() if rank == 0 else None
+    err = pipe.errors()                              # every buffer set, not only the last one used
+    if err:
+        raise SystemExit(f"device error bits {err:#x}")
     tot = pipe.totals(0)
-    if tot["error"]:
-        raise SystemExit(f"device error bits {tot['error']:#x}")
 
-    # end to end through the public API: host buffers, D2H of every chunk's hits inside the timed region
-    sync_all()
+    # end to end through the public API: host buffers, the device->host copy of every chunk's tables inside the timed
+    # region (compressed-row form, include/ptb.h PtbCompactOut)
+    job.sync_all()
     t0 = time.perf_counter()
     e0.record()
-    rows, d2h = job(host_pipe, True)
+    rows, d2h = run_job(host_pipe, True)
     e1.record()
-    sync_all()
+    job.sync_all()
     e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)   # wall clock: what the caller waits for
-
-    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=sim.device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = (float(v) for v in t.cpu())
-    total_particles = n_rank * world
-    value = total_particles / (ms * 1e-3)
+    ms, e2e_ms = job.max_over_ranks(ms, e2e_ms)
+    value = job.total / (ms * 1e-3)
     hits_per_particle = sum(tot["hits"]) / chunk
+
+    check = shard_check(job, args) if not args.no_check else None
 
     if rank == 0:
         peaks = {}
@@ -340,7 +482,8 @@ def run_gpu(args):
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
                 tj = json.load(f)
             traffic = tj["dram_bytes_per_launch"] * (chunk / tj["chunk"])
-            ncu = {k: tj[k] for k in ("issue_active_pct", "lanes_active_per_instruction", "pipe_pct") if k in tj}
+            ncu = {k: tj[k] for k in ("issue_active_pct", "lanes_active_per_instruction", "pipe_pct",
+                                      "warp_instructions_per_launch") if k in tj}
             ncu["note"] = "from the committed ncu capture (profiles/), not measured in this run"
         except Exception:
             pass
@@ -351,38 +494,168 @@ def run_gpu(args):
                 "peak_source": "in-job DFMA probe (ptb_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
                 "flops_per_electron": F, "flops_per_electron_whole_path": F_all, "launch_ms": launch_ms,
                 "k_tracks_launch_ms": tracks_launch_ms, "launches_timed": sim_launches,
-                "share_of_step": launch_ms / (ms / K), "traffic": traffic, "ncu": ncu,
+                "share_of_step": launch_ms / (ms / K), "traffic": traffic, "traffic_over_algorithmic":
+                    traffic / alg_bytes if traffic else None, "ncu": ncu,
                 "binding": "instruction issue (see ncu.issue_active_pct; FP64 pipe about a quarter busy): profiles/README.md",
                 "hbm": {"achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
                         "bytes_per_electron": alg_bytes / chunk, "peak_source": hbm_src}}
-        cpu_sample = args.cpu_sample or 1_000_000
-        cpu_val, cpu_hits = cpu_port_rate(cpu_sample, 1) if (world == 1 and args.config == "default") else (None, None)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload + f", {total_particles:.3g} electrons", "electrons_per_step": chunk,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if args.config == "c5" else "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload + f", {job.total:.3g} electrons", "electrons_per_step": chunk,
                            "planes": D, "hits_per_electron": hits_per_particle, "seed": seed,
-                           "parallelism": f"index-range shards x{world}", "host_numa_bound": numa_bound,
+                           "parallelism": f"index-range shards x{world}", "host_numa_bound": job.numa_bound,
+                           "variates": "physics arithmetic in fp64; normal variates are 24-bit (fp32 special-function-unit "
+                                       "Box-Muller, tails end at 6.8 sigma) except the beam position (fp64 Box-Muller on "
+                                       "32-bit uniforms); Landau loss from the same 24-bit normals (ptb_device.cuh)",
                            "l2": "no inputs; 1.2 GB of hit rows written per step (> 126 MB L2)"},
                 "hits_per_s": value * hits_per_particle,
                 "clocks": clocks,
-                "e2e": {"value": total_particles / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 0,
+                "e2e": {"value": job.total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": d2h / K, "rows_per_step": rows / K,
-                        "note": "ChunkPipeline.run_to_host: SoA hit slabs copied to pinned host memory on a second "
-                                "stream; production mode has no per-step input arrays"},
+                        "bytes_per_electron": d2h / K / chunk,
+                        "note": "ChunkPipeline.run_to_host: every chunk's hit tables copied to pinned host memory on a "
+                                "second stream in compressed-row form (PtbCompactOut: 8-byte rows + one count byte per "
+                                "particle and plane + trigger mask; ptb_expand_hits turns it into the reference's 18-byte "
+                                "rows); production mode has no per-step input arrays"},
                 "gpu_launches": int(launches),
                 "roofline": roof}
-        if cpu_val is not None:
-            line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": 1, "kind": "port",
-                                    "sample": f"{cpu_sample} electrons, default telescope, single thread "
-                                              "(oracle/ C + numpy port of the reference's sequential loops; the "
-                                              "reference itself, Python+Numba, ran 6.4-7.2e4 electrons/s on one core "
-                                              "in the build container and cannot travel to this box)",
-                                    "hits_per_s": cpu_hits}
+        if check is not None:
+            line["shard_check"] = check
+        if world == 1 and args.config == "default":
+            if not args.no_entry:
+                line["e2e_entry"] = entry_point_rate(args.entry_electrons, seed)
+            line["cpu_baseline"] = cpu_baseline_legs(args)
         print(json.dumps(line), file=args.out, flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        job.dist.barrier()
+        job.dist.destroy_process_group()
+    if check is not None and check["equal"] is False:
+        raise SystemExit("shard_check failed: the sharded tables differ from the single-GPU tables")
+
+
+def cpu_baseline_legs(args) -> dict:
+    """The reference's own Numba path on this box's host cores (1 process = what the reference does; all cores as forked
+    processes), with the oracle port beside it; the port alone when no reference tree is installed."""
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 64))
+    port_n = args.cpu_sample or 1_000_000
+    port_v, port_h = cpu_port_rate(port_n, 1)
+    port = {"value": port_v, "hits_per_s": port_h, "cores": 1, "kind": "port",
+            "sample": f"{port_n} electrons, single thread, oracle/ C + numpy port of the reference's loops"}
+    legs = None
+    try:
+        if args.reference_tree != "none":
+            legs = reference_legs(args.cpu_sample or 1_000_000, args.cpu_sample or 100_000, workers, rounds=2)
+    except Exception as exc:
+        print(f"reference tree unusable ({exc!r}); cpu_baseline falls back to the oracle port", file=sys.stderr)
+    if legs is None:
+        return dict(port, unit=UNIT, note="no reference tree under baseline/_ref or /root/reference on this box")
+    one = legs["single"]
+    out = {"value": one["value"], "unit": UNIT, "cores": 1, "kind": "reference", "hits_per_s": one["hits_per_s"],
+           "sample": f"{one['electrons']} electrons, default telescope, one process, warm JIT: the unmodified hit.tracks + "
+                     f"device.calculate_device_hit of {legs['root']} (HDF5 writer stubbed)",
+           "jit_s": legs["jit_s"], "port": port}
+    if "pool" in legs:
+        pl = legs["pool"]
+        out["all_cores"] = {"value": pl["value"], "hits_per_s": pl["hits_per_s"], "cores": pl["cores"], "kind": "reference",
+                            "sample": f"{pl['cores']} forked processes x {pl['electrons_per_round'] // pl['cores']} "
+                                      f"electrons, {pl['rounds']} rounds, distinct seeds"}
+    return out
+
+
+def run_c5(args):
+    """BASELINE config 5 as a bench arm: the default telescope, a fixed total (default 1e10 electrons) in index-range
+    shards; per-rank hit slabs; the rows of the first --keep electrons go through the host pipeline into per-rank HDF5
+    part files that rank 0 concatenates, everything else is produced into the recycled device slabs and dropped
+    (1.3 TB of rows).  One timed pass over the whole job; then the shard check."""
+    import torch
+
+    from pytestbeam_b200.distributed import merge_part_files, part_path
+    from pytestbeam_b200.main.device import FileSink, stream_fused
+    from pytestbeam_b200.pipeline import ChunkPipeline
+
+    job = Job(args)
+    sim, D, lib = job.sim, job.D, job.sim.lib
+    world, rank, chunk, seed = job.world, job.rank, job.chunk, job.seed
+    keep = min(int(args.keep), job.total) // chunk * chunk                 # whole chunks
+    folder = args.out_dir if args.out_dir.endswith("/") else args.out_dir + "/"
+    os.makedirs(folder, exist_ok=True)
+    pipe = ChunkPipeline(sim, chunk, seed=seed)
+    sampler = ClockSampler(job.local)
+    if rank == 0:
+        sampler.start()
+    job.bases()
+    pipe.set_bases(0, 0)
+    pipe.run(job.first, args.warmup)
+    job.sync_all()
+    launches0 = lib.ptb_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    job.sync_all()
+    sampler.begin()
+    t0 = time.perf_counter()
+    e0.record()
+    ev, t = job.bases()
+    n_keep = max(0, min(job.first + job.n_rank, keep) - job.first)          # this rank's share of the kept head
+    sink = FileSink([part_path(folder, name, rank) for name in job.names])
+    kept_rows = 0
+    try:
+        if n_keep:
+            head = stream_fused(sim, job.first, n_keep, seed, sink, ev, t, chunk=chunk)
+            ev, t, kept_rows = ev + head["accepted"], t + head["time_sum"], head["rows"]
+    finally:
+        sink.close()
+    pipe.set_bases(ev, t)
+    pipe.run(job.first + n_keep, (job.n_rank - n_keep) // chunk)
+    e1.record()
+    job.sync_all()
+    if rank == 0:
+        merge_part_files(folder, job.names, world)
+    job.sync_all()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    sampler.end()
+    dev_ms = e0.elapsed_time(e1)
+    launches = lib.ptb_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    err = pipe.errors()
+    if err:
+        raise SystemExit(f"device error bits {err:#x}")
+    wall_ms, dev_ms = job.max_over_ranks(wall_ms, dev_ms)
+    check = shard_check(job, args) if not args.no_check else None
+    if rank == 0:
+        from pytestbeam_b200 import h5min
+        rows_in_files = []
+        for name in job.names:
+            with h5min.TableReader(f"{folder}{name}_dut.h5") as r:
+                rows_in_files.append(r.nrows("Hits"))
+        value = job.total / (wall_ms * 1e-3)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": job.K, "warmup": args.warmup,
+                "ms_per_step": wall_ms / job.K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": WORKLOAD + f" (BASELINE config 5), {job.total:.3g} electrons in index-range shards",
+                           "electrons_per_step": chunk, "planes": D, "seed": seed, "parallelism": f"index-range shards x{world}",
+                           "kept_electrons": keep, "sink": f"rows of the first {keep:.3g} electrons -> per-rank HDF5 part "
+                           "files -> concatenated by rank 0; all other rows produced into recycled device slabs and dropped"},
+                "wall_s": wall_ms * 1e-3, "device_s": dev_ms * 1e-3, "target": "1e10 electrons < 60 s on 8 B200 (BASELINE.json)",
+                "rows_in_hdf5": rows_in_files, "rows_kept_this_rank": kept_rows, "clocks": clocks,
+                "gpu_launches": int(launches),
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": None,
+                        "note": "value IS the end-to-end figure of this arm: wall clock over prefix exchange, all chunks, "
+                                "part files and the merge"}}
+        if check is not None:
+            line["shard_check"] = check
+        print(json.dumps(line), file=args.out, flush=True)
+        if not args.keep_files:
+            for name in job.names:
+                try:
+                    os.remove(f"{folder}{name}_dut.h5")
+                except OSError:
+                    pass
+    if world > 1:
+        job.dist.barrier()
+        job.dist.destroy_process_group()
+    if check is not None and check["equal"] is False:
+        raise SystemExit("shard_check failed: the sharded tables differ from the single-GPU tables")
 
 
 def _claim_stdout():
@@ -402,13 +675,26 @@ def main():
     ap.add_argument("--chunk", type=int, default=10_000_000)
     ap.add_argument("--seed", type=int, default=20261019)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="default", choices=["default", "c3", "c4"],
-                    help="telescope set-up (default = BASELINE configs 1/2/5; c3, c4 = the other two)")
+    ap.add_argument("--config", default="default", choices=["default", "c3", "c4", "c5"],
+                    help="default = BASELINE configs 1/2; c3, c4 = the other telescopes; c5 = the sharded 1e10 target run")
+    ap.add_argument("--electrons", type=float, default=1e10, help="c5: total electrons over all ranks")
+    ap.add_argument("--keep", type=float, default=1e7, help="c5: electrons whose rows are written to HDF5")
+    ap.add_argument("--out-dir", default=os.path.join(ROOT, "gpurun_out", "c5"), help="c5: where the HDF5 files go")
+    ap.add_argument("--keep-files", action="store_true", help="c5: leave the merged *_dut.h5 files in --out-dir")
+    ap.add_argument("--no-check", action="store_true", help="skip the shard check pass")
+    ap.add_argument("--check-limit", type=float, default=2.5e10,
+                    help="largest job rank 0 repeats alone for the shard check (electrons)")
+    ap.add_argument("--no-entry", action="store_true", help="skip the entry-point (files included) measurement")
+    ap.add_argument("--entry-electrons", type=int, default=2_000_000, help="size of the entry-point run (setup.yml's)")
     ap.add_argument("--cpu-sample", type=int, default=0)
+    ap.add_argument("--reference-tree", default="auto", choices=["auto", "none"],
+                    help="none: time the oracle port even when a reference tree is installed (tests)")
     args = ap.parse_args()
     args.out = _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "c5":
+        run_c5(args)
     else:
         run_gpu(args)
 

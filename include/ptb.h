@@ -21,6 +21,11 @@
  *   PtbTrackTable   the 8-tuple returned by hit.tracks (main/hit.py:138)
  *   PtbHitSlab      the per-device hit table (main/device.py:20-28,66,156-163), as structure of arrays
  *   ptb_pack_hits   the structured-array rows handed to create_hit_file (main/device.py:317-327)
+ *   PtbCompactOut   the same hit tables in compressed-row form for the trip to the host: per (plane, particle) the
+ *                   number of rows calc_position appended for it (main/device.py:156-163) instead of a repeated event
+ *                   number, the trigger mask (main/device.py:56) and 8-byte (column, row, charge) rows
+ *   ptb_expand_hits that form back into the 18-byte rows of main/device.py:20-28 (host code, multi-threaded)
+ *   ptb_digest      no counterpart: order-sensitive checksums of a hit table, for comparing sharded runs
  *   PTB_ZERO_RADIUS the calc_cluster_hits call of the threshold scan (main/threshold_scan.py:55-69)
  *   ptb_correlate   _eventloop_fast of the correlation plot (main/plotting.py:730-764)
  *
@@ -52,6 +57,8 @@ extern "C" {
 #define PTB_DEV_SCRATCH_OVERFLOW 1u /* the workspace's scratch rows of a plane ran out; PtbTotals.reserved is exact */
 #define PTB_DEV_SLAB_OVERFLOW 2u  /* a hit slab's capacity was exceeded; totals still hold the exact counts */
 #define PTB_DEV_BOX_TOO_LARGE 4u  /* a cluster bounding box exceeded 2^20 pixels */
+#define PTB_DEV_COUNT_OVERFLOW 8u /* PTB_COMPACT: one particle left more than 255 rows on a plane (the u8 count
+                                     saturated); rerun the range without PTB_COMPACT */
 
 /* flags of PtbRun.flags */
 #define PTB_DIGITISE 1u          /* run the cluster digitisation and fill the hit slabs */
@@ -61,6 +68,7 @@ extern "C" {
 #define PTB_ZERO_RADIUS 32u      /* charge injection (threshold scan, threshold_scan.py:55-69): the cluster radii are 0
                                     instead of being drawn, so only the seed-pixel fallback of calc_cluster_hits fires */
 #define PTB_RECYCLE_SLABS 16u    /* rows start at 0 of each slab: ignore bases_in->hits and write bases_out->hits = 0 */
+#define PTB_COMPACT 64u          /* with PTB_DIGITISE: write PtbRun.compact instead of PtbRun.slabs (always recycled) */
 
 /* beam block of setup.yml; lengths um, angles rad, energy MeV, rate Hz */
 typedef struct PtbBeam {
@@ -119,6 +127,20 @@ typedef struct PtbHitSlab {
     uint64_t  capacity; /* rows */
 } PtbHitSlab;
 
+/*
+ * Compressed-row form of the hit tables of particles [first, first+n) (PTB_COMPACT), device memory owned by the caller.
+ * Plane d's rows sit at hits[sum(totals.hits[0..d-1]) ...], in the reference's order (particle, column, row).  Row i of
+ * plane d belongs to the particle k whose running count range covers i:  sum(counts[d][0..k-1]) <= i < ... + counts[d][k];
+ * its event number is  bases_in->event + 1 + (accepted particles among first .. first+k-1)  (main/device.py:159,164-165),
+ * frame is 0.  66 instead of 118 bytes per electron on the default telescope: this is what travels over PCIe.
+ */
+typedef struct PtbCompactOut {
+    uint64_t *hits;     /* [capacity] column | row << 16 | (f32 charge bits) << 32 */
+    uint8_t  *counts;   /* [D][n] rows of particle k on plane d */
+    uint32_t *accepted; /* [(n+31)/32] trigger mask, bit j of word g = particle first + 32 g + j */
+    uint64_t  capacity; /* rows over all planes */
+} PtbCompactOut;
+
 /* running prefixes carried from one particle range to the next (device memory) */
 typedef struct PtbBases {
     int64_t  event;            /* accepted particles before `first` */
@@ -154,6 +176,7 @@ typedef struct PtbRun {
     size_t             workspace_bytes;
     uint64_t           scratch_rows[PTB_MAX_PLANES]; /* rows of the workspace's scratch slab per plane; 0 = the default
                                                         rule.  On PTB_DEV_SCRATCH_OVERFLOW retry with totals.reserved */
+    PtbCompactOut      compact;    /* used with PTB_COMPACT; scratch_rows[d] = 0 then means the default rule on compact.capacity */
 } PtbRun;
 
 typedef struct PtbContext *PtbHandle;
@@ -190,6 +213,23 @@ int ptb_correlate(const int64_t *ev1, const uint16_t *col1, const uint16_t *row1
 /* SoA slab rows [0, n) -> packed 18-byte records (event_number <i8, frame <u2 = 0, column <u2, row <u2, charge <f4) */
 int ptb_pack_hits(const PtbHitSlab *slab, uint64_t n, void *out_dev, void *stream);
 
+/*
+ * PtbCompactOut (copied to the host) -> the 18-byte rows of one plane.  hits: the plane's rows; counts: the plane's
+ * [n] counts; accepted: [(n+31)/32] words; event_base: bases_in->event of the call.  Writes sum(counts) records to out
+ * (host memory, e.g. the mapped dataset region of an HDF5 file) with `threads` host threads (<= 0: one per core, at most
+ * 16) and returns the number of rows, or a negative PTB_E_* when n_rows_expected differs from sum(counts).
+ */
+int64_t ptb_expand_hits(const uint64_t *hits, const uint8_t *counts, const uint32_t *accepted, uint64_t n,
+                        int64_t event_base, uint64_t n_rows_expected, void *out, int32_t threads);
+
+/*
+ * Checksums of rows [0, n) of a hit table, added (modulo 2^64) to out_dev[0..6]:
+ *   rows, sum event_number, sum column, sum row, sum of the charges' bit patterns, S1 = sum m_i, S2 = sum (row_base+i+1) m_i
+ * with m_i = a 64-bit mix of row i's (event, column, row, charge bits).  S2 depends on the order of the rows.  For a table
+ * cut into pieces (chunks, ranks) the pieces' words add up when every piece is given its global row_base; a piece
+ * digested with row_base 0 is moved to base b afterwards by S2 += b * S1.
+ */
+int ptb_digest(const PtbHitSlab *slab, uint64_t n, uint64_t row_base, uint64_t *out_dev, void *stream);
 /*
  * Optional per-kernel timing: while enabled, every ptb_simulate brackets its k_tracks and k_digitise launches
  * with CUDA events on the caller's stream.  ptb_timing_read waits for the recorded events, returns the summed

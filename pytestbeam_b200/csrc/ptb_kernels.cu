@@ -26,6 +26,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "ptb_device.cuh"
@@ -50,7 +51,7 @@ constexpr int      POOL_ENTRIES = 128;
 constexpr int      SMALL_POOL = 96;
 constexpr int      TRACK_BLOCK = 128;                   // k_tracks
 constexpr unsigned FULL = 0xffffffffu;
-constexpr uint32_t KFLAG_BIG_LAUNCHED = 1u << 31;     // internal flag handed to k_scan: k_digitise_big ran
+constexpr unsigned long long NO_SEGMENT = ~0ull;      // table entry of a group whose scratch reservation did not fit
 constexpr int      SCAN_SEGMENTS = 16;                  // every counter column is scanned by this many blocks
 
 static unsigned long long g_launches = 0;
@@ -95,6 +96,7 @@ struct KParams {
     PtbTrackTable      trk;
     Workspace          ws;
     PtbTotals         *totals;
+    PtbCompactOut      cmp;   // PTB_COMPACT
 };
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -157,6 +159,7 @@ struct WarpShared {
     float    rnr[32];                              // 1 / rows of the trimmed box
     uint32_t seedcr[32];
     uint8_t  evoff[32], accb[32];
+    uint8_t  cnt[32];                              // PTB_COMPACT: rows of every particle on the current plane (saturating)
     unsigned long long census;                     // census of the group (packed), kept by lane 0
 };
 
@@ -324,7 +327,9 @@ __device__ __forceinline__ Cluster describe(const ConfigK &cfg, const PlaneK &pl
     const double ry = injected_charge ? 0.0 : fabs(0.0 + sig * zry);
     const int    sc = pixel_index(x, pl.delta_x, pl.pitch_c, pl.rcp_pc, pl.half_nc);
     const int    sr = pixel_index(y, pl.delta_y, pl.pitch_r, pl.rcp_pr, pl.half_nr);
-    if (sc >= 1 && sc <= pl.ncol && sr >= 1 && sr <= pl.nrow) {
+    // a NaN position (energy below the electron mass upstream, Q17) converts to 0 here but to INT64_MIN under Numba,
+    // which fails the matrix test: such a track leaves no hit
+    if (sc >= 1 && sc <= pl.ncol && sr >= 1 && sr <= pl.nrow && x == x && y == y) {
         out.inside = true;
         const double inx = profile_norm(profile_radius(rx));
         const double iny = profile_norm(profile_radius(ry));
@@ -411,6 +416,7 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
     const int    D = cfg.n_planes;
     constexpr bool   keep64 = KEEP64;
     const bool       from_table = (P.flags & PTB_TRACKS_FROM_TABLE) != 0;
+    const bool       compact = (P.flags & PTB_COMPACT) != 0;
     constexpr size_t wbytes = warp_shared_bytes(PC);
 
     unsigned char *wbase = smem_raw + wbytes * wib;
@@ -436,6 +442,7 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
     if (from_table && lane == 0) {
         P.ws.table[(unsigned long long)(D + 0) * P.n_groups + group] = (unsigned long long)__popc(accmask);
         P.ws.table[(unsigned long long)(D + 1) * P.n_groups + group] = 0;
+        P.ws.accmask[group] = accmask;
     }
 
     // census of the group (digitised pairs, in-acceptance pairs, box pixels): summed over the warp plane by plane and
@@ -476,6 +483,7 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
         // ---- cluster descriptors, one lane per particle (main/device.py:137-140, 241-266) -----------
         const bool digitised = valid && (!pl.triggered || W.accb[lane]);
         Cluster    cl{0, 0, 0, false, false};
+        if (compact) W.cnt[lane] = 0;
         if (digitised) cl = describe(cfg, pl, P.flags, src, k, d, x, y, eloss, W, lane);
         const int  cnt = cl.cnt;                  // pixels of the reference's bounding box (census)
         bool       inside = cl.inside;            // seed pixel on the matrix: the particle owns a work item even with an empty box
@@ -650,8 +658,13 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
                     const unsigned at = (unsigned)n_plane + __popc(emask & lanemask_lt());
                     PTB_DBG_CHECK((int)at < ub && base + at < P.ws.cap[d]);
                     seg_hit[at] = make_uint2(hcr, __float_as_uint((float)hq));
-                    seg_ev[at] = W.evoff[own];
+                    if (!compact) seg_ev[at] = W.evoff[own];
                     if (keep64) seg_q64[at] = hq;
+                }
+                if (compact && has && w == end - 1) {   // the lane holding a particle's last slot knows its row count
+                    const int rows_k = kept_before + kept_here + (fb ? 1 : 0);
+                    W.cnt[own] = (uint8_t)min(rows_k, 255);
+                    if (rows_k > 255) atomicOr(&P.totals->error, PTB_DEV_COUNT_OVERFLOW);
                 }
                 n_plane += __popc(emask);
                 // carry for a particle that continues into the next step
@@ -663,10 +676,13 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
             o_begin = o_end;
         }
         __syncwarp();
-        // lane d keeps the plane's row count and segment start; the table is written once, after the last plane
+        if (compact && valid) P.cmp.counts[(unsigned long long)d * P.n + kl] = W.cnt[lane];
+        // lane d keeps the plane's row count and segment start; the table is written once, after the last plane.  A group
+        // whose reservation did not fit wrote nothing: its count stays exact (the host retries with it), its segment
+        // start tells k_gather that there is nothing to copy
         if (lane == d) {
             my_rows = n_plane;
-            my_base = base;
+            my_base = room ? base : NO_SEGMENT;
         }
         // device-side conditions go straight to the totals (rare), so that no error word has to live across the planes
         {
@@ -719,11 +735,8 @@ __global__ void __launch_bounds__(32 * BIG_WARPS) k_digitise_big(const __grid_co
         const unsigned long long kl = group * 32 + lane;
         const bool               valid = kl < P.n;
         const unsigned long long k = P.first + kl;
-        unsigned                 accmask;
-        if (from_table)
-            accmask = __ballot_sync(FULL, valid && (P.trk.accepted ? P.trk.accepted[kl] != 0 : src.accepted(cfg, k)));
-        else
-            accmask = P.ws.accmask[group];
+        const bool               compact = (P.flags & PTB_COMPACT) != 0;
+        const unsigned           accmask = P.ws.accmask[group];   // k_tracks' ballot, or k_digitise's copy of the table's
         __syncwarp();
         W.evoff[lane] = (uint8_t)__popc(accmask & lanemask_lt());
         double x = 0.0, y = 0.0, eloss = 0.0;
@@ -780,7 +793,7 @@ __global__ void __launch_bounds__(32 * BIG_WARPS) k_digitise_big(const __grid_co
                     const unsigned at = (unsigned)(n_plane + kept) + __popc(kballot & lanemask_lt());
                     PTB_DBG_CHECK((int)at < ub && base + at < P.ws.cap[d]);
                     seg_hit[at] = make_uint2(hcr, __float_as_uint((float)hq));
-                    seg_ev[at] = W.evoff[b];
+                    if (!compact) seg_ev[at] = W.evoff[b];
                     if (KEEP64) seg_q64[at] = hq;
                 }
                 kept += __popc(kballot);
@@ -788,16 +801,20 @@ __global__ void __launch_bounds__(32 * BIG_WARPS) k_digitise_big(const __grid_co
             if (kept == 0 && W.seedq[b] >= pl.thr_ke) {   // seed fallback, main/device.py:299-302
                 if (lane == 0 && room) {
                     seg_hit[n_plane] = make_uint2(W.seedcr[b], __float_as_uint((float)W.seedq[b]));
-                    seg_ev[n_plane] = W.evoff[b];
+                    if (!compact) seg_ev[n_plane] = W.evoff[b];
                     if (KEEP64) seg_q64[n_plane] = W.seedq[b];
                 }
                 kept = 1;
+            }
+            if (compact && lane == 0) {
+                P.cmp.counts[(unsigned long long)d * P.n + group * 32 + b] = (uint8_t)min(kept, 255);
+                if (kept > 255) atomicOr(&P.totals->error, PTB_DEV_COUNT_OVERFLOW);
             }
             n_plane += kept;
         }
         if (lane == 0) {
             P.ws.table[(unsigned long long)d * P.n_groups + group] = (unsigned long long)n_plane;
-            P.ws.table[(unsigned long long)(D + 5 + d) * P.n_groups + group] = base;
+            P.ws.table[(unsigned long long)(D + 5 + d) * P.n_groups + group] = room ? base : NO_SEGMENT;
             if (!room) atomicOr(&P.totals->error, PTB_DEV_SCRATCH_OVERFLOW);
         }
         __syncwarp();
@@ -908,10 +925,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(int D, unsigned long long
             totals->reserved[c] = ws.alloc[c * 16];   // scratch rows the groups asked for (k_digitise has finished)
             if (bases_out) bases_out->hits[c] = recycle ? 0ull : b + total;
         } else if (c == D) {
-            // pairs left to k_digitise_big although it was not launched (cannot happen while ptb_create's bound on the
-            // cluster width holds): their hits are missing, say so
-            if ((flags & PTB_DIGITISE) && !(flags & KFLAG_BIG_LAUNCHED) && ws.alloc[PTB_MAX_PLANES * 16] != 0)
-                atomicOr(&totals->error, PTB_DEV_BOX_TOO_LARGE);
             const int64_t b = bases_in ? bases_in->event : 0;
             ws.bases_used->event = b;
             totals->accepted = total;
@@ -941,6 +954,7 @@ struct GatherParams {
     unsigned long long n, n_groups;
     Workspace          ws;
     PtbHitSlab         slabs[PTB_MAX_PLANES];
+    PtbCompactOut      cmp;
     int64_t           *time_stamp;
     PtbTotals         *totals;
 };
@@ -955,12 +969,18 @@ __global__ void __launch_bounds__(256) k_gather(const __grid_constant__ GatherPa
     __shared__ uint16_t       *d_col[PTB_MAX_PLANES], *d_row[PTB_MAX_PLANES];
     __shared__ float          *d_charge[PTB_MAX_PLANES];
     __shared__ double         *d_q64[PTB_MAX_PLANES];
-    const int D = G.D;
+    __shared__ unsigned long long plane_base[PTB_MAX_PLANES];   // PTB_COMPACT: first row of every plane in cmp.hits
+    const int  D = G.D;
+    const bool compact = (G.flags & PTB_COMPACT) != 0;
     if (threadIdx.x < D) {
         const int d = threadIdx.x;
         s_hit[d] = G.ws.s_hit[d]; s_ev[d] = G.ws.s_ev[d]; s_q64[d] = G.ws.s_q64[d];
         d_event[d] = G.slabs[d].event; d_col[d] = G.slabs[d].col; d_row[d] = G.slabs[d].row;
         d_charge[d] = G.slabs[d].charge; d_q64[d] = G.slabs[d].charge64;
+        unsigned long long b = 0;
+        if (compact)
+            for (int e = 0; e < d; ++e) b += G.totals->hits[e];   // k_scan has finished
+        plane_base[d] = b;
     }
     __syncthreads();
     const int                lane = threadIdx.x & 31;
@@ -973,13 +993,16 @@ __global__ void __launch_bounds__(256) k_gather(const __grid_constant__ GatherPa
         if (lane < D) {
             n_l = G.ws.table[(unsigned long long)lane * G.n_groups + group];
             src_l = G.ws.table[(unsigned long long)(D + 5 + lane) * G.n_groups + group];
-            dst_l = B.hits[lane] + G.ws.prefix[(unsigned long long)lane * G.n_groups + group];
-            if (n_l != 0 && (dst_l + n_l > G.slabs[lane].capacity || src_l + n_l > G.ws.cap[lane])) {
-                atomicOr(&G.totals->error, dst_l + n_l > G.slabs[lane].capacity ? PTB_DEV_SLAB_OVERFLOW
-                                                                                : PTB_DEV_SCRATCH_OVERFLOW);
+            dst_l = (compact ? plane_base[lane] : B.hits[lane]) + G.ws.prefix[(unsigned long long)lane * G.n_groups + group];
+            const unsigned long long room_l = compact ? G.cmp.capacity : G.slabs[lane].capacity;
+            // a group whose scratch reservation did not fit wrote no rows (NO_SEGMENT): nothing of it may be copied
+            const bool no_src = src_l == NO_SEGMENT || src_l + n_l > G.ws.cap[lane];
+            if (n_l != 0 && (dst_l + n_l > room_l || no_src)) {
+                atomicOr(&G.totals->error, dst_l + n_l > room_l ? PTB_DEV_SLAB_OVERFLOW : PTB_DEV_SCRATCH_OVERFLOW);
                 n_l = 0;
             }
         }
+        if (compact && lane == 0) G.cmp.accepted[group] = G.ws.accmask[group];
         const int64_t ev_base = B.event + (int64_t)G.ws.prefix[(unsigned long long)D * G.n_groups + group] + 1;
         const bool    keep64 = (G.flags & PTB_KEEP_CHARGE64) != 0;
         // the group's segments of all planes form one work list, walked 32 rows at a time: every step is a full
@@ -999,7 +1022,11 @@ __global__ void __launch_bounds__(256) k_gather(const __grid_constant__ GatherPa
             const int                before = __shfl_sync(FULL, cum, max(d - 1, 0));   // all lanes take part
             const int                first = d ? before : 0;
             const unsigned long long src = __shfl_sync(FULL, src_l, d), dst = __shfl_sync(FULL, dst_l, d);
-            if (w < total) {
+            if (w < total && compact) {
+                const unsigned long long i = (unsigned long long)(w - first);
+                const uint2              hit = s_hit[d][src + i];
+                G.cmp.hits[dst + i] = (unsigned long long)hit.x | ((unsigned long long)hit.y << 32);
+            } else if (w < total) {
                 const unsigned long long i = (unsigned long long)(w - first);
                 const uint2              hit = s_hit[d][src + i];
                 d_event[d][dst + i] = ev_base + (int64_t)s_ev[d][src + i];
@@ -1084,6 +1111,52 @@ __global__ void __launch_bounds__(256) k_pack(PtbHitSlab s, unsigned long long n
 }
 
 // ---------------------------------------------------------------------------------------------------
+// k_digest: checksums of a hit table (ptb_digest): five plain sums and two sums over a 64-bit mix of every row, the
+// second weighted with the row's position so that it notices rows in the wrong order
+// ---------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ unsigned long long row_mix(long long ev, unsigned col, unsigned row, unsigned qbits)
+{
+    unsigned long long h = (unsigned long long)ev * 0x9E3779B97F4A7C15ull;
+    h ^= (unsigned long long)col | ((unsigned long long)row << 16) | ((unsigned long long)qbits << 32);
+    h ^= h >> 29;
+    h *= 0xBF58476D1CE4E5B9ull;
+    h ^= h >> 32;
+    return h;
+}
+
+__global__ void __launch_bounds__(256) k_digest(PtbHitSlab s, unsigned long long n, unsigned long long row_base,
+                                                unsigned long long *out)
+{
+    unsigned long long a[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const long long ev = s.event[i];
+        const unsigned  c = s.col[i], r = s.row[i], q = __float_as_uint(s.charge[i]);
+        const unsigned long long m = row_mix(ev, c, r, q);
+        a[0] += 1ull;
+        a[1] += (unsigned long long)ev;
+        a[2] += c;
+        a[3] += r;
+        a[4] += q;
+        a[5] += m;
+        a[6] += (row_base + i + 1ull) * m;
+    }
+    __shared__ unsigned long long part[8][7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) a[j] += __shfl_xor_sync(FULL, a[j], sft);
+        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5][j] = a[j];
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        unsigned long long t = 0;
+        for (int w = 0; w < 8; ++w) t += part[w][threadIdx.x];
+        atomicAdd(&out[threadIdx.x], t);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // k_correlate: one thread per event number; the hits of that event in both tables (plus the first hit of the next
 // event, as the reference's loop does) are found by binary search and their pairs counted with atomics
 // ---------------------------------------------------------------------------------------------------
@@ -1138,12 +1211,34 @@ static cudaError_t launch_digitise(unsigned blocks, cudaStream_t st, const ptb::
 {
     using namespace ptb;
     constexpr size_t smem = warp_shared_bytes(PC) * WARPS_PER_BLOCK;
-    auto             kern = k_digitise<Src, PC, KEEP64>;
-    cudaError_t      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    kern<<<blocks, BLOCK, smem, st>>>(c, P, src);
+    k_digitise<Src, PC, KEEP64><<<blocks, BLOCK, smem, st>>>(c, P, src);
     return cudaGetLastError();
+}
+
+// Shared-memory carve-out of every k_digitise variant: asked for once per handle (ptb_create), not per launch.  The
+// dynamic shared memory stays below the 48 KB that need no opt-in.
+template <class Src, int PC, bool KEEP64>
+static cudaError_t prefer_shared()
+{
+    static_assert(ptb::warp_shared_bytes(PC) * ptb::WARPS_PER_BLOCK <= 48 * 1024, "k_digitise needs the shared-memory opt-in");
+    return cudaFuncSetAttribute(ptb::k_digitise<Src, PC, KEEP64>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                cudaSharedmemCarveoutMaxShared);
+}
+
+static cudaError_t prefer_shared_all()
+{
+    using namespace ptb;
+    cudaError_t e = cudaSuccess;
+    auto also = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    also(prefer_shared<PhiloxSource, POOL_ENTRIES, false>());
+    also(prefer_shared<PhiloxSource, POOL_ENTRIES, true>());
+    also(prefer_shared<PhiloxSource, SMALL_POOL, false>());
+    also(prefer_shared<PhiloxSource, SMALL_POOL, true>());
+    also(prefer_shared<InjectedSource, POOL_ENTRIES, false>());
+    also(prefer_shared<InjectedSource, POOL_ENTRIES, true>());
+    also(prefer_shared<InjectedSource, SMALL_POOL, false>());
+    also(prefer_shared<InjectedSource, SMALL_POOL, true>());
+    return e;
 }
 
 // =====================================================================================================
@@ -1156,7 +1251,7 @@ struct PtbContext {
     void   *alias_dev;   // device copy of the Poisson alias table (cfg.alias points at it)
     int     device;
     int     sm_count;
-    int     may_be_big;   // a production-mode cluster can outgrow the profile pool: k_digitise_big is launched
+    int     may_be_big;   // a production-mode cluster can outgrow the profile pool (sizes k_digitise_big's grid)
     int     timing;
     std::vector<cudaEvent_t> ev;   // (start, after k_tracks, after k_digitise) per ptb_simulate, when timing is enabled
     size_t  ev_used;
@@ -1363,6 +1458,8 @@ int ptb_create(const PtbBeam *beam, const PtbDevice *dev, int32_t n_dev, const P
     }
     e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
     if (e != cudaSuccess) return fail_cuda(h, e, "cudaDeviceGetAttribute");
+    e = prefer_shared_all();
+    if (e != cudaSuccess) return fail_cuda(h, e, "cudaFuncSetAttribute(k_digitise, shared-memory carve-out)");
     return PTB_OK;
 }
 
@@ -1491,12 +1588,17 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
     if (run->injected && (flags & PTB_TRACKS_FROM_TABLE) && !run->tracks.accepted && !run->injected->accepted)
         return fail(h, PTB_E_INVALID, "no trigger mask: neither the track table nor the injected tables carry one");
     unsigned long long cap[PTB_MAX_PLANES] = {0};   // rows of every plane's scratch slab
+    const bool         compact = (flags & PTB_COMPACT) != 0;
+    if (compact && (!(flags & PTB_DIGITISE) || (flags & PTB_KEEP_CHARGE64)))
+        return fail(h, PTB_E_INVALID, "PTB_COMPACT needs PTB_DIGITISE and excludes PTB_KEEP_CHARGE64");
+    if (compact && (!run->compact.hits || !run->compact.counts || !run->compact.accepted))
+        return fail(h, PTB_E_INVALID, "compact output pointers missing");
     if (flags & PTB_DIGITISE) {
         for (int d = 0; d < D; ++d) {
             const PtbHitSlab &s = run->slabs[d];
-            if (!s.event || !s.col || !s.row || !s.charge || ((flags & PTB_KEEP_CHARGE64) && !s.charge64))
+            if (!compact && (!s.event || !s.col || !s.row || !s.charge || ((flags & PTB_KEEP_CHARGE64) && !s.charge64)))
                 return fail(h, PTB_E_INVALID, "hit slab pointers missing");
-            cap[d] = scratch_rows_of(s.capacity, run->scratch_rows[d]);
+            cap[d] = scratch_rows_of(compact ? run->compact.capacity : s.capacity, run->scratch_rows[d]);
         }
     }
     KParams P;
@@ -1507,6 +1609,7 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
     P.flags = flags;
     P.trk = run->tracks;
     P.totals = run->totals;
+    P.cmp = run->compact;
     size_t need = carve_workspace(D, run->n, cap, flags, (char *)run->workspace, &P.ws);
     if (!run->workspace || run->workspace_bytes < need) return fail(h, PTB_E_INVALID, "workspace too small");
     if (P.n_groups > 0x7fffffffull * WARPS_PER_BLOCK) return fail(h, PTB_E_INVALID, "range too large for one call");
@@ -1518,7 +1621,6 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
     if (e != cudaSuccess) return fail_cuda(h, e, "memset totals");
 
     const bool keep64 = (flags & PTB_KEEP_CHARGE64) != 0;
-    bool       big_launched = false;
     cudaEvent_t *tp = timing_pair(h);
     if (tp) cudaEventRecord(tp[0], st);
     if (!(flags & PTB_TRACKS_FROM_TABLE)) {
@@ -1554,13 +1656,15 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
         }
         ++g_launches;
         if (e != cudaSuccess) return fail_cuda(h, e, "k_digitise launch");
-        // clusters wider than the profile pool: possible with the caller's own variates / deposits, or when the geometry
-        // says so (ptb_create); the default telescope never launches this
-        big_launched = run->injected || (flags & PTB_TRACKS_FROM_TABLE) || h->may_be_big;
-        if (big_launched) {
+        if (tp) cudaEventRecord(tp[2], st);
+        // clusters wider than the profile pool (possible with the caller's own variates / deposits, or when the geometry
+        // says so, ptb_create): always launched -- with an empty list the blocks read one counter and leave -- so that
+        // a pair k_digitise defers can never stay unserved; a small grid when no such cluster is expected
+        {
+            const bool               expected = run->injected || (flags & PTB_TRACKS_FROM_TABLE) || h->may_be_big;
             const unsigned long long items = P.n_groups * (unsigned long long)D;
             const unsigned bb = (unsigned)std::min<unsigned long long>((items + BIG_WARPS - 1) / BIG_WARPS,
-                                                                       (unsigned long long)h->sm_count * 16);
+                                                                       (unsigned long long)h->sm_count * (expected ? 16 : 2));
             if (run->injected) {
                 InjectedSource src{*run->injected, run->first, run->n};
                 if (keep64) k_digitise_big<InjectedSource, true><<<bb, 32 * BIG_WARPS, 0, st>>>(c, P, src);
@@ -1575,11 +1679,10 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
             if (e != cudaSuccess) return fail_cuda(h, e, "k_digitise_big launch");
         }
     }
-    if (tp) cudaEventRecord(tp[2], st);
+    if (tp && !(flags & PTB_DIGITISE)) cudaEventRecord(tp[2], st);
 
     k_scan_sums<<<(D + 5) * SCAN_SEGMENTS, SCAN_THREADS, 0, st>>>(P.n_groups, P.ws);
-    k_scan<<<(D + 5) * SCAN_SEGMENTS, SCAN_THREADS, 0, st>>>(D, P.n_groups, flags | (big_launched ? KFLAG_BIG_LAUNCHED : 0u), P.ws, run->bases_in, run->bases_out,
-                                                             run->totals);
+    k_scan<<<(D + 5) * SCAN_SEGMENTS, SCAN_THREADS, 0, st>>>(D, P.n_groups, flags, P.ws, run->bases_in, run->bases_out, run->totals);
     g_launches += 2;
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(h, e, "k_scan launch");
@@ -1593,6 +1696,7 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
         G.n_groups = P.n_groups;
         G.ws = P.ws;
         for (int d = 0; d < D; ++d) G.slabs[d] = run->slabs[d];
+        G.cmp = run->compact;
         G.time_stamp = run->tracks.time_stamp;
         G.totals = run->totals;
         k_gather<<<(unsigned)((P.n_groups + 7) / 8), 256, 0, st>>>(G);
@@ -1622,11 +1726,92 @@ int ptb_correlate(const int64_t *ev1, const uint16_t *col1, const uint16_t *row1
     if (x_dim0 < 1 || x_dim1 < 1 || y_dim0 < 1 || y_dim1 < 1) return PTB_E_INVALID;
     if (n1 == 0 || n2 == 0 || ev_max <= ev_min) return PTB_OK;
     const unsigned long long events = (unsigned long long)(ev_max - ev_min);
-    const unsigned           blocks = (unsigned)std::min<unsigned long long>((events + 255) / 256, 148ull * 16);
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned           blocks = (unsigned)std::min<unsigned long long>((events + 255) / 256, (unsigned long long)sms * 16);
     k_correlate<<<blocks, 256, 0, (cudaStream_t)stream>>>(ev1, col1, row1, n1, ev2, col2, row2, n2, ev_min, ev_max,
                                                          x_hist, x_dim0, x_dim1, y_hist, y_dim0, y_dim1);
     ++g_launches;
     return cudaGetLastError() == cudaSuccess ? PTB_OK : PTB_E_CUDA;
+}
+
+int ptb_digest(const PtbHitSlab *slab, uint64_t n, uint64_t row_base, uint64_t *out_dev, void *stream)
+{
+    if (!slab || !out_dev) return PTB_E_INVALID;
+    if (n == 0) return PTB_OK;
+    if (n > slab->capacity || !slab->event || !slab->col || !slab->row || !slab->charge) return PTB_E_INVALID;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned blocks = (unsigned)std::min<unsigned long long>((n + 255) / 256, (unsigned long long)sms * 8);
+    k_digest<<<blocks, 256, 0, (cudaStream_t)stream>>>(*slab, n, row_base, (unsigned long long *)out_dev);
+    ++g_launches;
+    return cudaGetLastError() == cudaSuccess ? PTB_OK : PTB_E_CUDA;
+}
+
+// Host side of PtbCompactOut: counts + trigger mask -> event numbers, 8-byte rows -> the reference's 18-byte records.
+// The particle range is cut into blocks of whole 32-particle words; a first pass sums every block's rows and accepted
+// particles, the second pass lets each thread expand its blocks from those prefixes.
+int64_t ptb_expand_hits(const uint64_t *hits, const uint8_t *counts, const uint32_t *accepted, uint64_t n,
+                        int64_t event_base, uint64_t n_rows_expected, void *out, int32_t threads)
+{
+    if ((!hits && n_rows_expected) || !counts || !accepted || (!out && n_rows_expected)) return PTB_E_INVALID;
+    int T = threads > 0 ? threads : (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+    const uint64_t words = (n + 31) / 32;
+    T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)T, (words + 4095) / 4096));   // >= 128k particles per thread
+    const uint64_t          per = (words + T - 1) / T;   // words per thread
+    std::vector<uint64_t>   rows(T + 1, 0), acc(T + 1, 0);
+    auto range = [&](int t, uint64_t &k0, uint64_t &k1) {
+        k0 = std::min<uint64_t>(n, per * 32 * (uint64_t)t);
+        k1 = std::min<uint64_t>(n, k0 + per * 32);
+    };
+    auto count_pass = [&](int t) {
+        uint64_t k0, k1, r = 0, a = 0;
+        range(t, k0, k1);
+        for (uint64_t k = k0; k < k1; ++k) r += counts[k];
+        for (uint64_t w = k0 / 32; w < (k1 + 31) / 32; ++w) {
+            uint32_t m = accepted[w];
+            if ((w + 1) * 32 > n) m &= (uint32_t)((1ull << (n - w * 32)) - 1ull);   // bits beyond the range do not count
+            a += (uint64_t)__builtin_popcount(m);
+        }
+        rows[t + 1] = r;
+        acc[t + 1] = a;
+    };
+    auto run_threads = [&](auto fn) {
+        std::vector<std::thread> pool;
+        for (int t = 1; t < T; ++t) pool.emplace_back(fn, t);
+        fn(0);
+        for (auto &th : pool) th.join();
+    };
+    run_threads(count_pass);
+    for (int t = 0; t < T; ++t) {
+        rows[t + 1] += rows[t];
+        acc[t + 1] += acc[t];
+    }
+    if (rows[T] != n_rows_expected) return PTB_E_INVALID;
+    unsigned char *dst = (unsigned char *)out;
+    auto expand_pass = [&](int t) {
+        uint64_t k0, k1;
+        range(t, k0, k1);
+        uint64_t i = rows[t];
+        int64_t  ev = event_base + 1 + (int64_t)acc[t];
+        for (uint64_t k = k0; k < k1; ++k) {
+            const unsigned c = counts[k];
+            for (unsigned j = 0; j < c; ++j, ++i) {
+                const uint64_t h = hits[i];
+                unsigned char *r = dst + i * 18;
+                const uint16_t frame = 0, col = (uint16_t)h, row = (uint16_t)(h >> 16);
+                const uint32_t q = (uint32_t)(h >> 32);
+                memcpy(r, &ev, 8);
+                memcpy(r + 8, &frame, 2);
+                memcpy(r + 10, &col, 2);
+                memcpy(r + 12, &row, 2);
+                memcpy(r + 14, &q, 4);
+            }
+            ev += (accepted[k >> 5] >> (k & 31)) & 1u;
+        }
+    };
+    run_threads(expand_pass);
+    return (int64_t)rows[T];
 }
 
 double ptb_measure_fp64_peak(void *stream)

@@ -43,21 +43,24 @@ def part_path(folder: str, name: str, rank: int) -> str:
 
 
 def merge_part_files(folder: str, names: list, size: int, remove: bool = True) -> None:
-    """Concatenate the per-rank part files of every device in rank order into ``<folder><name>_dut.h5``."""
+    """Concatenate the per-rank part files of every device in rank order into ``<folder><name>_dut.h5``: the parts are
+    appended piece by piece to a streamed table (``h5min.concatenate_tables``), none is ever read as a whole."""
     for name in names:
-        parts = [h5min.read_table(part_path(folder, name, r), "Hits") for r in range(size)]
-        table = np.concatenate(parts) if parts else np.zeros(0, dtype=HITS_DTYPE)
-        h5min.write_table(f"{folder}{name}_dut.h5", "Hits", table)
+        parts = [part_path(folder, name, r) for r in range(size)]
+        h5min.concatenate_tables(f"{folder}{name}_dut.h5", "Hits", parts, HITS_DTYPE)
         if remove:
-            for r in range(size):
-                os.remove(part_path(folder, name, r))
+            for p in parts:
+                os.remove(p)
 
 
 def run_sharded(beam: dict, devices: list, materials: list, names: list, folder: str, seed: int, log=None,
-                chunk: int = 4_000_000) -> dict:
-    """Simulate this rank's index range on its GPU, write part files, merge on rank 0.  Returns this rank's totals."""
+                chunk: int = 4_000_000, keep: int | None = None) -> dict:
+    """Simulate this rank's index range on its GPU, stream the rows into per-rank part files, merge on rank 0.
+
+    keep: write only the rows of particles [0, keep) to the files (BASELINE config 5: 1e10 electrons are 1.3 TB of
+    rows; the rest only counts).  Returns this rank's totals."""
     from .engine import Simulator
-    from .main.device import _packed_rows
+    from .main.device import FileSink, stream_fused
     rank, size = world()
     n_total = int(beam["nmb_particles"])
     lo, n = shard_range(n_total, rank, size)
@@ -65,27 +68,19 @@ def run_sharded(beam: dict, devices: list, materials: list, names: list, folder:
     acc, tsum = sim.prefix(lo, n, seed=seed) if n else (0, 0)
     ev_base, t_base = exchange_bases(acc, tsum, device=sim.device if dist.is_initialized()
                                      and dist.get_backend() == "nccl" else None)
-    bases = sim.new_bases()
-    host = torch.zeros_like(bases, device="cpu")
-    host[0], host[1] = ev_base, t_base
-    bases.copy_(host)
-    parts = [[] for _ in devices]
+    n_keep = n if keep is None else max(0, min(lo + n, int(keep)) - lo)
+    sink = FileSink([part_path(folder, name, rank) for name in names])
     hits = [0] * len(devices)
-    for c0 in range(lo, lo + n, chunk):
-        m = min(chunk, lo + n - c0)
-        r = sim.run(c0, m, seed=seed, bases_in=bases, capacities=sim.default_capacities(m),
-                        scratch_rows=sim.default_scratch_rows(m))
-        bases = r.bases_out
-        for d in range(len(devices)):
-            parts[d].append(_packed_rows(sim, r.slabs[d]))
-            hits[d] += r.totals["hits"][d]
-    for d, name in enumerate(names):
-        table = np.concatenate(parts[d]) if parts[d] else np.zeros(0, dtype=HITS_DTYPE)
-        h5min.write_table(part_path(folder, name, rank), "Hits", table)
+    try:
+        if n_keep:
+            tot = stream_fused(sim, lo, n_keep, seed, sink, ev_base, t_base, chunk=chunk)
+            hits = tot["hits"]
+    finally:
+        sink.close()
     if size > 1:
         dist.barrier()
     if rank == 0:
         merge_part_files(folder, names, size)
     if size > 1:
         dist.barrier()
-    return {"rank": rank, "first": lo, "n": n, "event_base": ev_base, "time_base": t_base, "hits": hits}
+    return {"rank": rank, "first": lo, "n": n, "kept": n_keep, "event_base": ev_base, "time_base": t_base, "hits": hits}

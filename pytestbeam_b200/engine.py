@@ -81,9 +81,23 @@ class RunResult:
     slabs: list = field(default_factory=list)      # per plane: dict of device tensors trimmed to the rows produced
     tracks: dict | None = None                     # device tensors, layout of the reference's hit_tables
     bases_out: torch.Tensor | None = None
+    compact: dict | None = None                    # PTB_COMPACT: device tensors of the PtbCompactOut
+    event_base: int = 0
+
+    def compact_host(self) -> dict:
+        """The PtbCompactOut on the host: per-plane uint64 rows, uint8 counts [D, n], uint32 trigger words."""
+        D, hits = len(self.totals["hits"]), self.totals["hits"]
+        flat = self.compact["hits"][:sum(hits)].cpu().numpy().view(np.uint64)
+        offs = np.concatenate([[0], np.cumsum(hits)]).astype(np.int64)
+        return {"hits": [flat[offs[d]:offs[d + 1]] for d in range(D)],
+                "counts": self.compact["counts"].cpu().numpy().reshape(D, self.n),
+                "accepted": self.compact["accepted"].cpu().numpy().view(np.uint32)}
 
     def hits_numpy(self, plane: int) -> np.ndarray:
         """Rows of one plane as the reference's structured array (main/device.py:20-28)."""
+        if self.compact is not None:
+            c = self.compact_host()
+            return expand_compact(N.load(), c["hits"][plane], c["counts"][plane], c["accepted"], self.n, self.event_base)
         s = self.slabs[plane]
         out = np.zeros(int(s["event"].numel()), dtype=HITS_DTYPE)
         out["event_number"] = s["event"].cpu().numpy()
@@ -152,6 +166,12 @@ class Simulator:
             slabs.append(s)
         return slabs
 
+    def alloc_compact(self, n, capacity):
+        """Device buffers of a PtbCompactOut for n particles and `capacity` rows over all planes."""
+        return {"hits": torch.empty(int(capacity), dtype=torch.int64, device=self.device),
+                "counts": torch.empty(self.D * int(n), dtype=torch.uint8, device=self.device),
+                "accepted": torch.empty((int(n) + 31) // 32, dtype=torch.int32, device=self.device)}
+
     def alloc_tracks(self, n):
         D = self.D
         f8 = lambda m: torch.empty(m, dtype=torch.float64, device=self.device)  # noqa: E731
@@ -190,7 +210,8 @@ class Simulator:
 
     # -- one call of ptb_simulate --------------------------------------------------------------------
     def launch(self, first, n, *, seed=0, injected: Injected | None = None, flags=N.PTB_DIGITISE, slabs=None,
-               tracks=None, bases_in=None, bases_out=None, totals=None, workspace=None, scratch_rows=None):
+               tracks=None, bases_in=None, bases_out=None, totals=None, workspace=None, scratch_rows=None,
+               compact=None):
         """Enqueue one ptb_simulate call on the current stream (no synchronisation)."""
         run = N.PtbRun()
         run.first, run.n, run.seed, run.flags = int(first), int(n), int(seed) & (2**64 - 1), int(flags)
@@ -210,6 +231,9 @@ class Simulator:
                                             s["charge"].data_ptr(),
                                             s["charge64"].data_ptr() if "charge64" in s else None,
                                             int(s["event"].numel()))
+        if compact is not None:
+            run.compact = N.PtbCompactOut(compact["hits"].data_ptr(), compact["counts"].data_ptr(),
+                                          compact["accepted"].data_ptr(), int(compact["hits"].numel()))
         run.bases_in = bases_in.data_ptr() if bases_in is not None else None
         run.bases_out = bases_out.data_ptr() if bases_out is not None else None
         run.totals = totals.data_ptr()
@@ -231,7 +255,8 @@ class Simulator:
                 "reserved": [int(v) for v in u[38:38 + D]]}
 
     def run(self, first, n, *, seed=0, injected=None, digitise=True, write_tracks=False, tracks_in=None,
-            keep_charge64=False, capacities=None, bases_in=None, zero_radius=False, scratch_rows=None) -> RunResult:
+            keep_charge64=False, capacities=None, bases_in=None, zero_radius=False, scratch_rows=None,
+            compact=False) -> RunResult:
         """Simulate particles [first, first+n), synchronise and return trimmed device buffers.
 
         Retries with exact slab / scratch sizes when the device reports an overflow (its totals stay exact).
@@ -248,21 +273,28 @@ class Simulator:
             flags |= N.PTB_KEEP_CHARGE64
         if zero_radius:
             flags |= N.PTB_ZERO_RADIUS
+        if compact:
+            flags |= N.PTB_COMPACT
         if capacities is None:
             capacities = [4 * n + 4096] * self.D if digitise else [0] * self.D
         for attempt in range(8):
-            slabs = self.alloc_slabs(capacities, keep_charge64) if digitise else None
+            slabs = self.alloc_slabs(capacities, keep_charge64) if (digitise and not compact) else None
+            cmp_out = self.alloc_compact(n, sum(int(c) for c in capacities)) if compact else None
+            if compact and scratch_rows is None:
+                scratch_rows = [N.default_scratch_rows(int(c)) for c in capacities]
             tracks = tracks_in if tracks_in is not None else (self.alloc_tracks(n) if write_tracks else None)
             totals = torch.zeros(_TOTALS_WORDS, dtype=torch.int64, device=self.device)
             bases_out = self.new_bases()
             ws = torch.empty(self.workspace_bytes(n, capacities, flags, scratch_rows), dtype=torch.uint8,
                              device=self.device)
             self.launch(first, n, seed=seed, injected=injected, flags=flags, slabs=slabs, tracks=tracks,
-                        bases_in=bases_in, bases_out=bases_out, totals=totals, workspace=ws, scratch_rows=scratch_rows)
+                        bases_in=bases_in, bases_out=bases_out, totals=totals, workspace=ws, scratch_rows=scratch_rows,
+                        compact=cmp_out)
             torch.cuda.synchronize(self.device)
             tot = self.decode_totals(totals, self.D)
             err = tot["error"]
-            if err & ~(N.PTB_DEV_BOX_TOO_LARGE | N.PTB_DEV_SLAB_OVERFLOW | N.PTB_DEV_SCRATCH_OVERFLOW):
+            if err & ~(N.PTB_DEV_BOX_TOO_LARGE | N.PTB_DEV_SLAB_OVERFLOW | N.PTB_DEV_SCRATCH_OVERFLOW |
+                       N.PTB_DEV_COUNT_OVERFLOW):
                 raise PtbError(f"device reported an internal consistency failure (error bits {err:#x})")
             if err & N.PTB_DEV_BOX_TOO_LARGE:
                 raise PtbError("a cluster bounding box exceeded 2^20 pixels (check pitch / geometry)")
@@ -270,9 +302,12 @@ class Simulator:
                 capacities = [max(int(h), 1) for h in tot["hits"]]
                 scratch_rows = [max(int(r), 1) for r in tot["reserved"]]
                 continue
-            if digitise:
+            if err & N.PTB_DEV_COUNT_OVERFLOW:
+                raise PtbError("a particle left more than 255 rows on one plane: run this range without compact=True")
+            if digitise and not compact:
                 slabs = [{k: v[:tot["hits"][d]] for k, v in s.items()} for d, s in enumerate(slabs)]
-            return RunResult(first, n, tot, slabs or [], tracks, bases_out)
+            ev0 = int(bases_in[0].item()) if bases_in is not None else 0
+            return RunResult(first, n, tot, slabs or [], tracks, bases_out, cmp_out, ev0)
         raise PtbError("ptb_simulate kept overflowing its buffers")
 
     def timing(self, on: bool):
@@ -297,6 +332,17 @@ class Simulator:
         a = out.cpu().numpy()
         return int(a[0]), int(a[1])
 
+    def digest(self, slab: dict, n: int, row_base: int, out: torch.Tensor):
+        """Add the checksums of rows [0, n) of a slab to out (7 int64 on the device); see ptb_digest in include/ptb.h."""
+        if n:
+            s = N.PtbHitSlab(slab["event"].data_ptr(), slab["col"].data_ptr(), slab["row"].data_ptr(),
+                             slab["charge"].data_ptr(), None, int(slab["event"].numel()))
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            with torch.cuda.device(self.device):
+                rc = self.lib.ptb_digest(C.byref(s), int(n), int(row_base) & (2**64 - 1), out.data_ptr(), C.c_void_p(stream))
+            if rc != 0:
+                raise PtbError(f"ptb_digest failed ({rc})")
+
     def pack_hits(self, slab: dict, n: int | None = None) -> torch.Tensor:
         """SoA slab -> device tensor of packed 18-byte reference records (uint8 [n*18])."""
         n = int(slab["event"].numel() if n is None else n)
@@ -310,3 +356,22 @@ class Simulator:
             if rc != 0:
                 raise PtbError(f"ptb_pack_hits failed ({rc})")
         return out
+
+
+def expand_compact(lib, hits: np.ndarray, counts: np.ndarray, accepted: np.ndarray, n: int, event_base: int,
+                   out: np.ndarray | None = None, threads: int = 0) -> np.ndarray:
+    """One plane of a PtbCompactOut (host arrays) -> the reference's 18-byte records (``ptb_expand_hits``).
+
+    hits: the plane's uint64 rows; counts: uint8 [n]; accepted: uint32 [(n+31)//32]; out: optional destination
+    (any writable buffer of len(hits) records, e.g. a slice of a memory-mapped HDF5 dataset)."""
+    rows = int(hits.shape[0])
+    if out is None:
+        out = np.empty(rows, dtype=HITS_DTYPE)
+    if out.shape[0] != rows or out.dtype.itemsize != 18 or not out.flags["C_CONTIGUOUS"]:
+        raise ValueError("destination must be a contiguous array of len(hits) 18-byte records")
+    counts = np.ascontiguousarray(counts, dtype=np.uint8)
+    got = lib.ptb_expand_hits(hits.ctypes.data if rows else None, counts.ctypes.data, accepted.ctypes.data, int(n),
+                              int(event_base), rows, out.ctypes.data if rows else None, int(threads))
+    if got != rows:
+        raise PtbError(f"ptb_expand_hits: counts add up to something else than {rows} rows ({got})")
+    return out

@@ -2,6 +2,16 @@
 
 ``calculate_device_hit`` (reference ``main/device.py:7-88``) writes one ``<folder><name>_dut.h5`` per device with
 table ``/Hits`` (event_number <i8, frame <u2, column <u2, row <u2, charge <f4; rows in particle order).
+
+Two routes, chosen by what arrives as ``hit_data``:
+
+* the untouched ``HitTables`` object of ``pytestbeam_b200.main.hit.tracks``: tracks and digitisation run fused on the GPU
+  (``ChunkPipeline.run_to_host``: no per-chunk allocation or synchronisation, the compressed-row tables cross PCIe while
+  the next chunk computes) and every chunk's rows are expanded straight into the memory-mapped dataset region of the
+  output files -- the tables are never held in host memory as a whole;
+* anything else that looks like the reference's 8-tuple (``main/hit.py:138``: a ``HitTables`` that has been
+  materialised, the reference's own typed Lists, plain numpy arrays): ``calc_position`` alone, reading ``x =
+  hit_data[3]``, ``y = hit_data[4]``, ``energy_lost = hit_data[7]`` exactly as ``main/device.py:132-138`` does.
 """
 from __future__ import annotations
 
@@ -10,6 +20,7 @@ import torch
 
 from .. import h5min
 from .. import native as N
+from ..config import SILICON
 from ..engine import HITS_DTYPE, Simulator
 from ..pipeline import ChunkPipeline
 from .hit import CHUNK, HitTables, _seed_of
@@ -23,67 +34,157 @@ def create_hit_file(hit_data: np.ndarray, folder: str, index: str) -> str:
     return path
 
 
-def _packed_rows(sim: Simulator, slab: dict) -> np.ndarray:
-    packed = sim.pack_hits(slab)
-    return np.frombuffer(packed.cpu().numpy().tobytes(), dtype=HITS_DTYPE)
+# ---------------------------------------------------------------------------------------------------
+# sinks: where the rows of every chunk go
+# ---------------------------------------------------------------------------------------------------
+
+class MemorySink:
+    """Keeps every plane's rows in host memory (``device_hits``)."""
+
+    def __init__(self, D: int):
+        self.parts = [[] for _ in range(D)]
+
+    def room(self, plane: int, rows: int) -> np.ndarray:
+        out = np.empty(rows, dtype=HITS_DTYPE)
+        self.parts[plane].append(out)
+        return out
+
+    def done(self, plane: int, view) -> None:
+        pass
+
+    def tables(self) -> list:
+        return [np.concatenate(p) if p else np.zeros(0, dtype=HITS_DTYPE) for p in self.parts]
+
+    def close(self) -> None:
+        pass
 
 
-def device_hits(beam: dict, devices: list, hit_data, log=None) -> list:
-    """The hit table of every device (structured arrays), i.e. calculate_device_hit without the file writing."""
-    n = int(beam["nmb_particles"])
-    D = len(devices)
-    parts = [[] for _ in range(D)]
-    if isinstance(hit_data, HitTables) and not hit_data.materialised:
-        # fused: tracks + digitisation in one pass per chunk, nothing but hit rows leaves the GPU
-        sim, seed = hit_data.sim, hit_data.seed
-        bases = None
-        for lo in range(0, n, CHUNK):
-            m = min(CHUNK, n - lo)
-            r = sim.run(lo, m, seed=seed, bases_in=bases, capacities=sim.default_capacities(m),
-                        scratch_rows=sim.default_scratch_rows(m))
-            bases = r.bases_out
-            for d in range(D):
-                parts[d].append(_packed_rows(sim, r.slabs[d]))
-    else:
-        # calc_position alone, fed from the caller's tuple exactly as main/device.py:132-138 reads it
-        if isinstance(hit_data, HitTables):
-            sim, seed = hit_data.sim, hit_data.seed
-        else:
-            raise TypeError("hit_data must come from pytestbeam_b200.main.hit.tracks (use device_hits_from_arrays "
-                            "for foreign tables)")
-        x, y, eloss = np.asarray(hit_data[3]), np.asarray(hit_data[4]), np.asarray(hit_data[7])
-        parts = device_hits_from_arrays(sim, x, y, eloss, seed)
-        return parts
-    return [np.concatenate(p) if p else np.zeros(0, dtype=HITS_DTYPE) for p in parts]
+class FileSink:
+    """One streamed ``/Hits`` table per device: rows are written in place through the mapped dataset region."""
+
+    def __init__(self, paths: list):
+        self.writers = [h5min.TableWriter(p, "Hits", HITS_DTYPE) for p in paths]
+
+    def room(self, plane: int, rows: int) -> np.ndarray:
+        return self.writers[plane].reserve(rows)
+
+    def done(self, plane: int, view) -> None:
+        if isinstance(view, np.memmap):
+            view.flush()
+
+    def close(self) -> None:
+        for w in self.writers:
+            w.close()
 
 
-def device_hits_from_arrays(sim: Simulator, x, y, eloss, seed: int, accepted=None) -> list:
-    """Digitise given track positions: x, y flat particle-major [N*D], eloss [D, N] (after the acceptance zeroing)."""
+def _consume_into(sink):
+    def consume(chunk):
+        for d in range(chunk.D):
+            out = sink.room(d, chunk.rows[d])
+            chunk.records(d, out=out)
+            sink.done(d, out)
+    return consume
+
+
+def stream_fused(sim: Simulator, first: int, n: int, seed: int, sink, event_base: int = 0, time_base: int = 0,
+                 chunk: int = CHUNK) -> dict:
+    """Particles [first, first+n) through the fused GPU path into `sink`.  Returns the summed counters."""
+    chunk = max(32, min(int(chunk), n))
+    pipe = ChunkPipeline(sim, chunk, host=True, seed=seed)
+    pipe.set_bases(event_base, time_base)
+    tot = {"hits": [0] * sim.D, "accepted": 0, "time_sum": 0}
+    inner = _consume_into(sink)
+
+    def consume(c):
+        inner(c)
+        for d in range(sim.D):
+            tot["hits"][d] += c.totals["hits"][d]
+        tot["accepted"] += c.totals["accepted"]
+        tot["time_sum"] += c.totals["time_sum"]
+
+    rows, nbytes = pipe.run_to_host(first, 0, consume=consume, n_total=n)
+    tot.update(rows=rows, d2h_bytes=nbytes, retries=pipe.retries)
+    return tot
+
+
+def stream_from_arrays(sim: Simulator, x, y, eloss, seed: int, sink, accepted=None, chunk: int = CHUNK) -> None:
+    """calc_position alone: x, y flat particle-major [N*D] sequences, eloss [D][N] (after the acceptance zeroing), read
+    chunk by chunk so that the reference's typed Lists are never converted as a whole."""
     D = sim.D
     n = len(x) // D
-    parts = [[] for _ in range(D)]
-    bases = None
+    eloss = eloss if isinstance(eloss, np.ndarray) else np.asarray(eloss, dtype=np.float64)
     dev = sim.device
-    for lo in range(0, n, CHUNK):
-        m = min(CHUNK, n - lo)
-        tin = {"x": torch.from_numpy(np.ascontiguousarray(x[lo * D:(lo + m) * D], dtype=np.float64)).to(dev),
-               "y": torch.from_numpy(np.ascontiguousarray(y[lo * D:(lo + m) * D], dtype=np.float64)).to(dev),
+    bases = None
+
+    def piece(seq, lo, hi):
+        a = seq[lo:hi] if isinstance(seq, np.ndarray) else np.fromiter((seq[i] for i in range(lo, hi)), np.float64, hi - lo)
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+
+    for lo in range(0, n, chunk):
+        m = min(chunk, n - lo)
+        tin = {"x": piece(x, lo * D, (lo + m) * D), "y": piece(y, lo * D, (lo + m) * D),
                "eloss": torch.from_numpy(np.ascontiguousarray(eloss[:, lo:lo + m], dtype=np.float64)).to(dev)}
         if accepted is not None:
             tin["accepted"] = torch.from_numpy(np.ascontiguousarray(accepted[lo:lo + m], dtype=np.uint8)).to(dev)
         r = sim.run(lo, m, seed=seed, tracks_in=tin, bases_in=bases, capacities=sim.default_capacities(m),
-                        scratch_rows=sim.default_scratch_rows(m))
+                    scratch_rows=sim.default_scratch_rows(m))
         bases = r.bases_out
         for d in range(D):
-            parts[d].append(_packed_rows(sim, r.slabs[d]))
-    return [np.concatenate(p) if p else np.zeros(0, dtype=HITS_DTYPE) for p in parts]
+            rows = r.totals["hits"][d]
+            out = sink.room(d, rows)
+            if rows:
+                packed = sim.pack_hits(r.slabs[d]).cpu().numpy()
+                out.view(np.uint8).reshape(-1)[:] = packed
+            sink.done(d, out)
+
+
+def _is_hit_tuple(hit_data) -> bool:
+    try:
+        return len(hit_data) == 8 and len(hit_data[3]) == len(hit_data[4])
+    except TypeError:
+        return False
+
+
+def _run(beam: dict, devices: list, hit_data, sink) -> None:
+    n, D = int(beam["nmb_particles"]), len(devices)
+    if isinstance(hit_data, HitTables) and not hit_data.materialised:
+        stream_fused(hit_data.sim, 0, n, hit_data.seed, sink)
+        return
+    if not _is_hit_tuple(hit_data):
+        raise TypeError("hit_data must be the 8-tuple of hit.tracks: (energy, anglex, angley, x, y, z, time_stamp, "
+                        "energy_lost), main/hit.py:138")
+    if len(hit_data[3]) != n * D:
+        raise ValueError(f"hit_data holds {len(hit_data[3])} track records, expected nmb_particles * devices = {n * D}")
+    if isinstance(hit_data, HitTables):
+        sim, seed = hit_data.sim, hit_data.seed
+    else:
+        # a foreign tuple: the digitisation needs the device geometry only, the material entries stay unused
+        sim, seed = Simulator(beam, devices, [dict(SILICON) for _ in devices]), _seed_of(beam)
+    stream_from_arrays(sim, hit_data[3], hit_data[4], hit_data[7], seed, sink)
+
+
+def device_hits(beam: dict, devices: list, hit_data, log=None) -> list:
+    """The hit table of every device (structured arrays), i.e. calculate_device_hit without the file writing."""
+    sink = MemorySink(len(devices))
+    _run(beam, devices, hit_data, sink)
+    return sink.tables()
+
+
+def device_hits_from_arrays(sim: Simulator, x, y, eloss, seed: int, accepted=None) -> list:
+    """Digitise given track positions: x, y flat particle-major [N*D], eloss [D, N] (after the acceptance zeroing)."""
+    sink = MemorySink(sim.D)
+    stream_from_arrays(sim, x, y, eloss, seed, sink, accepted=accepted)
+    return sink.tables()
 
 
 def calculate_device_hit(beam: dict, devices: list, hit_data, names: list, folder: str, log) -> None:
     """Create the HDF5 hit tables from the particle table and the device configuration (reference ``main/device.py:7``)."""
     log.info("Calculating particle hit positions")
-    tables = device_hits(beam, devices, hit_data, log)
-    for dut, name in enumerate(names):
-        log.info("Hit positions of %s" % name)
+    sink = FileSink([folder + name + "_dut.h5" for name in names])
+    try:
+        _run(beam, devices, hit_data, sink)
+    finally:
         log.info("Saving Data...")
-        create_hit_file(tables[dut], folder, name)
+        sink.close()
+    for name in names:
+        log.info("Hit positions of %s" % name)

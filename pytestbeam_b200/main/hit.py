@@ -39,22 +39,35 @@ class HitTables:
     def materialised(self) -> bool:
         return self._arrays is not None
 
-    def _materialise(self):
-        if self._arrays is not None:
-            return
-        D, n = self.sim.D, self.n
+    def chunks(self, n: int | None = None, chunk: int = CHUNK):
+        """The track records of the first n particles (default: all), chunk by chunk: yields (first particle, count,
+        dict of numpy arrays in the layout of the tuple) without ever holding more than one chunk."""
+        D, n = self.sim.D, self.n if n is None else min(int(n), self.n)
+        bases = None
+        for lo in range(0, n, chunk):
+            m = min(chunk, n - lo)
+            r = self.sim.run(lo, m, seed=self.seed, digitise=False, write_tracks=True, bases_in=bases)
+            bases = r.bases_out
+            piece = {k: r.tracks[k].cpu().numpy() for k in self._NAMES[:7]}
+            piece["eloss"] = r.tracks["eloss"].cpu().numpy().reshape(D, m)
+            yield lo, m, piece
+
+    def head(self, n_events: int) -> tuple:
+        """The 8-tuple restricted to the first n_events particles -- all that the reference's plot_default reads
+        (main/plotting.py:41-76 slices the first <= 1e5 events) -- without materialising the rest."""
+        D, n = self.sim.D, min(int(n_events), self.n)
         out = {k: np.empty(n * D, dtype=np.float64) for k in self._NAMES[:6]}
         out["time_stamp"] = np.empty(n * D, dtype=np.int64)
         out["eloss"] = np.empty((D, n), dtype=np.float64)
-        bases = None
-        for lo in range(0, n, CHUNK):
-            m = min(CHUNK, n - lo)
-            r = self.sim.run(lo, m, seed=self.seed, digitise=False, write_tracks=True, bases_in=bases)
-            bases = r.bases_out
+        for lo, m, piece in self.chunks(n):
             for k in self._NAMES[:7]:
-                out[k][lo * D:(lo + m) * D] = r.tracks[k].cpu().numpy()
-            out["eloss"][:, lo:lo + m] = r.tracks["eloss"].cpu().numpy().reshape(D, m)
-        self._arrays = tuple(out[k] for k in self._NAMES)
+                out[k][lo * D:(lo + m) * D] = piece[k]
+            out["eloss"][:, lo:lo + m] = piece["eloss"]
+        return tuple(out[k] for k in self._NAMES)
+
+    def _materialise(self):
+        if self._arrays is None:
+            self._arrays = self.head(self.n)
 
     def __len__(self):
         return 8
@@ -79,9 +92,21 @@ def tracks(beam: dict, devices: list, materials: list, log) -> HitTables:
 
 def create_output_tracks(hit_table, folder: str) -> None:
     """Write ``<folder>particle_tracks.h5`` with table ``/Tracks`` (reference ``main/hit.py:434-468``)."""
+    fields = (("energy", "energy"), ("x_angle", "angle_x"), ("y_angle", "angle_y"), ("x", "x"), ("y", "y"), ("z", "z"))
+    if isinstance(hit_table, HitTables) and not hit_table.materialised:
+        # straight from the GPU into the file, chunk by chunk: the N*D records are never held in host memory
+        with h5min.TableWriter(folder + "particle_tracks.h5", "Tracks", TRACKS_DTYPE) as w:
+            for _lo, m, piece in hit_table.chunks():
+                out = w.reserve(m * hit_table.sim.D)
+                for field, key in fields:
+                    out[field] = piece[key]
+                out["time_stamp"] = piece["time_stamp"].astype(np.uint16)     # wraps, as in the reference (Q19)
+                if isinstance(out, np.memmap):
+                    out.flush()
+        return
     numb = len(hit_table[0])
     out = np.zeros(numb, dtype=TRACKS_DTYPE)
-    for field, i in (("energy", 0), ("x_angle", 1), ("y_angle", 2), ("x", 3), ("y", 4), ("z", 5)):
+    for i, (field, _key) in enumerate(fields):
         out[field] = np.asarray(hit_table[i])
     out["time_stamp"] = np.asarray(hit_table[6]).astype(np.uint16)     # wraps, as in the reference (Q19)
     h5min.write_table(folder + "particle_tracks.h5", "Tracks", out)

@@ -16,10 +16,12 @@ PTB_WRITE_TRACKS = 4
 PTB_KEEP_CHARGE64 = 8
 PTB_RECYCLE_SLABS = 16
 PTB_ZERO_RADIUS = 32
+PTB_COMPACT = 64
 
 PTB_DEV_SCRATCH_OVERFLOW = 1
 PTB_DEV_SLAB_OVERFLOW = 2
 PTB_DEV_BOX_TOO_LARGE = 4
+PTB_DEV_COUNT_OVERFLOW = 8
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PTB_LIB_PATH") or os.path.join(_HERE, "_lib", "libptb_b200.so")   # env: developer builds
@@ -60,6 +62,10 @@ class PtbHitSlab(C.Structure):
                 ("charge64", C.c_void_p), ("capacity", C.c_uint64)]
 
 
+class PtbCompactOut(C.Structure):
+    _fields_ = [("hits", C.c_void_p), ("counts", C.c_void_p), ("accepted", C.c_void_p), ("capacity", C.c_uint64)]
+
+
 class PtbBases(C.Structure):
     _fields_ = [("event", C.c_int64), ("time", C.c_int64), ("hits", C.c_uint64 * PTB_MAX_PLANES)]
 
@@ -75,12 +81,12 @@ class PtbRun(C.Structure):
                 ("_pad", C.c_uint32), ("injected", C.POINTER(PtbInjected)), ("tracks", PtbTrackTable),
                 ("slabs", PtbHitSlab * PTB_MAX_PLANES), ("bases_in", C.c_void_p), ("bases_out", C.c_void_p),
                 ("totals", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
-                ("scratch_rows", C.c_uint64 * PTB_MAX_PLANES)]
+                ("scratch_rows", C.c_uint64 * PTB_MAX_PLANES), ("compact", PtbCompactOut)]
 
 
 EXPORTS = ("ptb_create", "ptb_destroy", "ptb_last_error", "ptb_n_planes", "ptb_workspace_bytes",
            "ptb_prefix", "ptb_simulate", "ptb_pack_hits", "ptb_launch_count", "ptb_measure_fp64_peak",
-           "ptb_timing_enable", "ptb_timing_read", "ptb_correlate")
+           "ptb_timing_enable", "ptb_timing_read", "ptb_correlate", "ptb_digest", "ptb_expand_hits")
 
 _lib = None
 
@@ -125,6 +131,11 @@ def load() -> C.CDLL:
     L.ptb_correlate.argtypes = [C.c_void_p] * 3 + [C.c_uint64] + [C.c_void_p] * 3 + [C.c_uint64, C.c_int64, C.c_int64,
                                 C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
     L.ptb_correlate.restype = C.c_int
+    L.ptb_digest.argtypes = [C.POINTER(PtbHitSlab), C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+    L.ptb_digest.restype = C.c_int
+    L.ptb_expand_hits.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64, C.c_uint64, C.c_void_p,
+                                  C.c_int32]
+    L.ptb_expand_hits.restype = C.c_int64
     L.ptb_launch_count.argtypes = []
     L.ptb_launch_count.restype = C.c_uint64
     L.ptb_measure_fp64_peak.argtypes = [C.c_void_p]

@@ -2,8 +2,11 @@
 buffers (1e10 electrons produce 1.3 TB of hits, far more than fits in HBM at once).
 
 ``ChunkPipeline.run`` keeps everything on the device (throughput measurements, digest sink);
-``ChunkPipeline.run_to_host`` additionally copies every chunk's hit slabs into pinned host memory on a
-second stream, double-buffered so that the copy of chunk i overlaps the kernels of chunk i+1.
+``ChunkPipeline.run_to_host`` additionally lands every chunk's hit tables in pinned host memory on a second stream,
+double-buffered so that the copy of chunk i overlaps the kernels of chunk i+1.  What travels over PCIe is the
+compressed-row form of the tables (``PtbCompactOut`` in include/ptb.h: 8-byte rows, one count byte per particle and
+plane, the trigger mask -- 66 instead of 118 bytes per electron on the default telescope); ``HostChunk.records``
+expands it to the reference's 18-byte rows (``ptb_expand_hits``), straight into the caller's buffer if it names one.
 """
 from __future__ import annotations
 
@@ -11,7 +14,9 @@ import numpy as np
 import torch
 
 from . import native as N
-from .engine import _TOTALS_WORDS, PtbError, Simulator
+from .engine import _BASES_WORDS, _TOTALS_WORDS, HITS_DTYPE, PtbError, Simulator, expand_compact
+
+_RETRY = N.PTB_DEV_SLAB_OVERFLOW | N.PTB_DEV_SCRATCH_OVERFLOW | N.PTB_DEV_COUNT_OVERFLOW
 
 
 def bind_host_to_gpu(index: int) -> bool:
@@ -30,93 +35,200 @@ def bind_host_to_gpu(index: int) -> bool:
         return False
 
 
+class HostChunk:
+    """One chunk's hit tables in host memory.  The arrays are views of the pipeline's pinned buffers: valid until the
+    consumer returns (copy what must live longer)."""
+
+    def __init__(self, lib, index, first, n, D, totals, event_base, time_base, compact=None, slabs=None):
+        self.lib, self.index, self.first, self.n, self.D = lib, index, first, n, D
+        self.totals, self.event_base, self.time_base = totals, event_base, time_base
+        self.compact, self.slabs = compact, slabs
+
+    @property
+    def rows(self):
+        return self.totals["hits"]
+
+    def records(self, plane: int, out: np.ndarray | None = None, threads: int = 0) -> np.ndarray:
+        """The plane's rows as the reference's records (main/device.py:20-28), written to `out` when given."""
+        m = self.totals["hits"][plane]
+        if self.compact is not None:
+            c = self.compact
+            return expand_compact(self.lib, c["hits"][plane], c["counts"][plane], c["accepted"], self.n,
+                                  self.event_base, out=out, threads=threads)
+        s = self.slabs[plane]
+        if out is None:
+            out = np.empty(m, dtype=HITS_DTYPE)
+        out["event_number"] = s["event"].numpy()
+        out["frame"] = 0
+        out["column"] = s["col"].numpy().view(np.uint16)
+        out["row"] = s["row"].numpy().view(np.uint16)
+        out["charge"] = s["charge"].numpy()
+        return out
+
+
 class ChunkPipeline:
     def __init__(self, sim: Simulator, chunk: int, *, n_buffers: int = 2, capacities=None, host: bool = False,
-                 seed: int = 0, scratch_rows=None):
+                 seed: int = 0, scratch_rows=None, compact: bool | None = None):
         self.sim, self.chunk, self.seed = sim, int(chunk), int(seed)
-        self.flags = N.PTB_DIGITISE | N.PTB_RECYCLE_SLABS
+        self.compact = bool(host) if compact is None else bool(compact)
+        if self.compact and not host:
+            raise PtbError("the compressed-row output exists for the trip to the host: use host=True")
+        self.flags = N.PTB_DIGITISE | N.PTB_RECYCLE_SLABS | (N.PTB_COMPACT if self.compact else 0)
         self.caps = list(capacities) if capacities is not None else sim.default_capacities(self.chunk)
         self.rows = list(scratch_rows) if scratch_rows is not None else sim.default_scratch_rows(self.chunk)
-        dev = sim.device
+        dev, D = sim.device, sim.D
         self.sets = []
         for _ in range(n_buffers):
-            s = {"slabs": sim.alloc_slabs(self.caps),
-                 "ws": torch.empty(sim.workspace_bytes(self.chunk, self.caps, self.flags, self.rows),
+            s = {"ws": torch.empty(sim.workspace_bytes(self.chunk, self.caps, self.flags, self.rows),
                                    dtype=torch.uint8, device=dev),
                  "totals": torch.zeros(_TOTALS_WORDS, dtype=torch.int64, device=dev),
                  "done": torch.cuda.Event(), "copied": torch.cuda.Event()}
+            if self.compact:
+                s["cmp"] = sim.alloc_compact(self.chunk, sum(self.caps))
+                s["h_cmp"] = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in s["cmp"].items()}
+            else:
+                s["slabs"] = sim.alloc_slabs(self.caps)
+                if host:
+                    s["h_slabs"] = [{k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in sl.items()}
+                                    for sl in s["slabs"]]
             if host:
                 s["h_totals"] = torch.zeros(_TOTALS_WORDS, dtype=torch.int64).pin_memory()
-                s["h_slabs"] = [{k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in sl.items()}
-                                for sl in s["slabs"]]
             self.sets.append(s)
         self.bases = sim.new_bases()
+        self._base0 = (0, 0)
         self.copy_stream = torch.cuda.Stream(device=dev) if host else None
+        self.retries = 0
 
     def set_bases(self, event: int = 0, time: int = 0):
         """Global prefixes of the first particle of this pipeline's range (multi-GPU shards)."""
         b = torch.zeros_like(self.bases, device="cpu")
         b[0], b[1] = int(event), int(time)
         self.bases.copy_(b)
+        self._base0 = (int(event), int(time))
 
-    def _launch(self, s, first, n):
-        self.sim.launch(first, n, seed=self.seed, flags=self.flags, slabs=s["slabs"], bases_in=self.bases,
-                        bases_out=self.bases, totals=s["totals"], workspace=s["ws"], scratch_rows=self.rows)
+    def _launch(self, s, first, n, bases_in=None, bases_out=None):
+        self.sim.launch(first, n, seed=self.seed, flags=self.flags, slabs=s.get("slabs"),
+                        bases_in=self.bases if bases_in is None else bases_in,
+                        bases_out=self.bases if bases_out is None else bases_out, totals=s["totals"], workspace=s["ws"],
+                        scratch_rows=self.rows, compact=s.get("cmp"))
 
     # -- device-resident -------------------------------------------------------------------------------
-    def run(self, first: int, n_chunks: int):
-        """Enqueue n_chunks chunks starting at particle `first`; no synchronisation, hits stay on the device."""
+    def run(self, first: int, n_chunks: int, after_chunk=None):
+        """Enqueue n_chunks chunks starting at particle `first`; no synchronisation, hits stay on the device.
+        after_chunk(index, set) is called right after a chunk's kernels are enqueued (same stream: digests)."""
         for i in range(n_chunks):
-            self._launch(self.sets[i % len(self.sets)], first + i * self.chunk, self.chunk)
+            s = self.sets[i % len(self.sets)]
+            self._launch(s, first + i * self.chunk, self.chunk)
+            if after_chunk is not None:
+                after_chunk(i, s)
 
     def totals(self, idx: int = -1) -> dict:
         torch.cuda.synchronize(self.sim.device)
         return Simulator.decode_totals(self.sets[idx]["totals"], self.sim.D)
 
-    # -- with host sink --------------------------------------------------------------------------------
-    def run_to_host(self, first: int, n_chunks: int, consume=None):
-        """Run n_chunks chunks and land every chunk's hits in pinned host memory.
+    def errors(self) -> int:
+        """OR of the device error words of all buffer sets (each holds the word of the last chunk it served)."""
+        torch.cuda.synchronize(self.sim.device)
+        e = 0
+        for s in self.sets:
+            e |= Simulator.decode_totals(s["totals"], self.sim.D)["error"]
+        return e
 
-        consume(chunk_index, totals: dict, host_slabs: list[dict of pinned tensors trimmed to the row counts])
-        is called once per chunk while later chunks are already computing.  Returns (rows, bytes) copied.
+    # -- with host sink --------------------------------------------------------------------------------
+    def _retry(self, i, first, n, ev_base, t_base, tot):
+        """Chunk i overflowed a buffer (its counters are exact): once more, alone, with buffers of the sizes it
+        reported, as structure-of-arrays slabs (which also covers a saturated count byte)."""
+        self.retries += 1
+        sim = self.sim
+        b_in = sim.new_bases()
+        host = torch.zeros(_BASES_WORDS, dtype=torch.int64)
+        host[0], host[1] = int(ev_base), int(t_base)
+        b_in.copy_(host)
+        r = sim.run(first, n, seed=self.seed, bases_in=b_in, capacities=[max(h, 1) for h in tot["hits"]],
+                    scratch_rows=[max(h, 1) for h in tot["reserved"]])
+        slabs = [{k: v.cpu() for k, v in sl.items()} for sl in r.slabs]
+        return HostChunk(sim.lib, i, first, n, sim.D, r.totals, ev_base, t_base, slabs=slabs)
+
+    def run_to_host(self, first: int, n_chunks: int, consume=None, n_total: int | None = None):
+        """Run n_chunks chunks (or, with n_total, the particles [first, first+n_total) in chunks) and land every chunk's
+        hit tables in pinned host memory.
+
+        consume(chunk: HostChunk) is called once per chunk, in order, while later chunks are already computing.
+        Returns (rows, bytes) copied from the device.
         """
         if self.copy_stream is None:
             raise PtbError("pipeline was created without host buffers")
-        compute = torch.cuda.current_stream(self.sim.device)
+        if n_total is None:
+            n_total = n_chunks * self.chunk
+        n_chunks = (n_total + self.chunk - 1) // self.chunk
+        sim, D = self.sim, self.sim.D
+        compute = torch.cuda.current_stream(sim.device)
         rows = nbytes = 0
+        ev_base, t_base = self._base0
         pending = None
 
+        def size_of(i):
+            return min(self.chunk, n_total - i * self.chunk)
+
         def finish(i):
-            nonlocal rows, nbytes
+            nonlocal rows, nbytes, ev_base, t_base
             s = self.sets[i % len(self.sets)]
+            n_i, first_i = size_of(i), first + i * self.chunk
             with torch.cuda.stream(self.copy_stream):
                 self.copy_stream.wait_event(s["done"])
                 s["h_totals"].copy_(s["totals"], non_blocking=True)
                 self.copy_stream.synchronize()
-                tot = Simulator.decode_totals(s["h_totals"], self.sim.D)
-                if tot["error"]:
-                    raise PtbError(f"device reported error bits {tot['error']:#x} in chunk {i}")
-                views = []
-                for d, (sl, hs) in enumerate(zip(s["slabs"], s["h_slabs"])):
-                    m = tot["hits"][d]
-                    v = {}
-                    for k in sl:
-                        hs[k][:m].copy_(sl[k][:m], non_blocking=True)
-                        v[k] = hs[k][:m]
-                        nbytes += m * sl[k].element_size()
-                    rows += m
-                    views.append(v)
-                s["copied"].record(self.copy_stream)
-            nbytes += _TOTALS_WORDS * 8
+                tot = Simulator.decode_totals(s["h_totals"], D)
+                nbytes += _TOTALS_WORDS * 8
+                err = tot["error"]
+                if err & ~_RETRY:
+                    raise PtbError(f"device reported error bits {err:#x} in chunk {i}")
+                chunk = None
+                if err:
+                    chunk = self._retry(i, first_i, n_i, ev_base, t_base, tot)
+                elif self.compact:
+                    c, h = s["cmp"], s["h_cmp"]
+                    m = sum(tot["hits"])
+                    h["hits"][:m].copy_(c["hits"][:m], non_blocking=True)
+                    h["counts"][:D * n_i].copy_(c["counts"][:D * n_i], non_blocking=True)
+                    w = (n_i + 31) // 32
+                    h["accepted"][:w].copy_(c["accepted"][:w], non_blocking=True)
+                    nbytes += 8 * m + D * n_i + 4 * w
+                    s["copied"].record(self.copy_stream)
+                    if consume is not None:
+                        flat = h["hits"].numpy().view(np.uint64)
+                        offs = np.concatenate([[0], np.cumsum(tot["hits"])]).astype(np.int64)
+                        chunk = HostChunk(sim.lib, i, first_i, n_i, D, tot, ev_base, t_base, compact={
+                            "hits": [flat[offs[d]:offs[d + 1]] for d in range(D)],
+                            "counts": h["counts"].numpy()[:D * n_i].reshape(D, n_i),
+                            "accepted": h["accepted"].numpy().view(np.uint32)[:w]})
+                else:
+                    views = []
+                    for d, (sl, hs) in enumerate(zip(s["slabs"], s["h_slabs"])):
+                        m = tot["hits"][d]
+                        v = {}
+                        for k in sl:
+                            hs[k][:m].copy_(sl[k][:m], non_blocking=True)
+                            v[k] = hs[k][:m]
+                            nbytes += m * sl[k].element_size()
+                        views.append(v)
+                    s["copied"].record(self.copy_stream)
+                    if consume is not None:
+                        chunk = HostChunk(sim.lib, i, first_i, n_i, D, tot, ev_base, t_base, slabs=views)
+                if err:
+                    s["copied"].record(self.copy_stream)
+            rows += sum(tot["hits"])
             if consume is not None:
                 s["copied"].synchronize()
-                consume(i, tot, views)
+                consume(chunk)
+            ev_base += tot["accepted"]
+            t_base += tot["time_sum"]
 
         for i in range(n_chunks):
             s = self.sets[i % len(self.sets)]
             if i >= len(self.sets):
                 compute.wait_event(s["copied"])      # the set's previous copy must have drained
-            self._launch(s, first + i * self.chunk, self.chunk)
+            self._launch(s, first + i * self.chunk, size_of(i))
             s["done"].record(compute)
             if pending is not None:
                 finish(pending)

@@ -1,0 +1,64 @@
+"""ptb_expand_hits (host code of libptb_b200, no GPU needed): the compressed-row form of a hit table (PtbCompactOut in
+include/ptb.h) back into the reference's 18-byte records (main/device.py:20-28, 156-165)."""
+import numpy as np
+import pytest
+
+from pytestbeam_b200 import native
+from pytestbeam_b200.engine import HITS_DTYPE, PtbError, expand_compact
+
+
+def _case(n, seed, max_count=5, p_accept=0.7):
+    rs = np.random.RandomState(seed)
+    counts = rs.randint(0, max_count + 1, n).astype(np.uint8)
+    counts[rs.uniform(size=n) < 0.3] = 0
+    acc = rs.uniform(size=n) < p_accept
+    words = np.zeros((n + 31) // 32, dtype=np.uint32)
+    for j in range(32):
+        sel = acc[j::32]
+        words[:len(sel)] |= sel.astype(np.uint32) << np.uint32(j)
+    rows = int(counts.sum())
+    col = rs.randint(1, 1153, rows).astype(np.uint64)
+    row = rs.randint(1, 577, rows).astype(np.uint64)
+    q = rs.uniform(0.1, 30, rows).astype(np.float32)
+    hits = col | (row << np.uint64(16)) | (q.view(np.uint32).astype(np.uint64) << np.uint64(32))
+    return counts, acc, words, hits, (col, row, q)
+
+
+def _expected(counts, acc, cols, event_base):
+    # event number of particle k: 1 + accepted particles before k (main/device.py:159,164-165)
+    ev_k = event_base + 1 + np.concatenate([[0], np.cumsum(acc)[:-1]]) if len(acc) else np.zeros(0, np.int64)
+    out = np.zeros(int(counts.sum()), dtype=HITS_DTYPE)
+    out["event_number"] = np.repeat(ev_k, counts)
+    out["column"], out["row"], out["charge"] = cols
+    return out
+
+
+@pytest.mark.parametrize("n,threads", [(0, 0), (1, 1), (31, 0), (32, 0), (33, 2), (1000, 0), (600_001, 0), (600_001, 5)])
+def test_expand_matches_the_reference_numbering(n, threads):
+    lib = native.load()
+    counts, acc, words, hits, cols = _case(n, seed=n + 1)
+    got = expand_compact(lib, hits, counts, words, n, event_base=12345, threads=threads)
+    want = _expected(counts, acc, cols, 12345)
+    assert got.tobytes() == want.tobytes()
+
+
+def test_bits_beyond_the_range_do_not_count_and_mismatch_is_refused():
+    lib = native.load()
+    n = 70
+    counts, acc, words, hits, cols = _case(n, seed=5)
+    words = words.copy()
+    words[-1] |= np.uint32(0xFFFFFFFF) << np.uint32(n - 64)      # garbage above particle n-1
+    got = expand_compact(lib, hits, counts, words, n, event_base=0)
+    assert got.tobytes() == _expected(counts, acc, cols, 0).tobytes()
+    with pytest.raises(PtbError):
+        expand_compact(lib, hits[:-1], counts, words, n, event_base=0)
+
+
+def test_expand_into_a_caller_buffer():
+    lib = native.load()
+    counts, acc, words, hits, cols = _case(5000, seed=9)
+    dest = np.zeros(len(hits) + 10, dtype=HITS_DTYPE)
+    view = dest[3:3 + len(hits)]
+    expand_compact(lib, hits, counts, words, 5000, event_base=7, out=view)
+    assert view.tobytes() == _expected(counts, acc, cols, 7).tobytes()
+    assert dest[:3].tobytes() == bytes(54) and dest[3 + len(hits):].tobytes() == bytes(7 * 18)

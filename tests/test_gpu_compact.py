@@ -1,0 +1,293 @@
+"""The compressed-row output (PTB_COMPACT / PtbCompactOut), the host pipeline built on it, ptb_digest, and the advisor's
+round-1 findings (NaN positions, reservations that did not fit)."""
+import logging
+import os
+
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _sim(setup, **kw):
+    from pytestbeam_b200.engine import Simulator
+    beam, devices, materials, names = setup
+    return Simulator(beam, devices, materials, **kw)
+
+
+@pytest.mark.parametrize("name,first,n", [("c1", 0, 50_003), ("c3", 77, 40_000), ("c4", 1_000_000_007, 33_333),
+                                          ("c1", 5, 1), ("c1", 0, 31)])
+def test_compact_tables_equal_the_slab_tables(name, first, n):
+    """Production mode: the same particles through both output forms; the expanded rows must be byte-identical, the
+    count bytes must add up to the rows of every plane, the trigger words to the accepted particles."""
+    sim = _sim(H.setup(name, n))
+    a = sim.run(first, n, seed=2024)
+    b = sim.run(first, n, seed=2024, compact=True)
+    assert a.totals["hits"] == b.totals["hits"] and b.totals["error"] == 0
+    c = b.compact_host()
+    assert [int(x.sum()) for x in c["counts"]] == b.totals["hits"]
+    mask = np.unpackbits(c["accepted"].view(np.uint8), bitorder="little")[:n]
+    assert int(mask.sum()) == b.totals["accepted"]
+    for d in range(sim.D):
+        assert b.hits_numpy(d).tobytes() == a.hits_numpy(d).tobytes(), d
+
+
+def test_compact_deterministic_vs_oracle_with_event_base():
+    """Injected variates, second half of a range with a non-zero event base: event numbers rebuilt on the host from
+    counts + trigger mask must be the oracle's (main/device.py:159,164-165)."""
+    n = 12_000
+    setup, run = H.oracle_run("c4", n, 51, 52)
+    sim = _sim(setup)
+    lo = 5000
+    first = sim.run(0, lo, injected=H.injected_for(sim, run, 0, lo))
+    second = sim.run(lo, n - lo, injected=H.injected_for(sim, run, lo, n - lo), bases_in=first.bases_out, compact=True)
+    assert second.event_base == int(run.variates.accepted[:lo].sum())
+    for d in range(sim.D):
+        want = run.hits[d][len(first.hits_numpy(d)):]
+        got = second.hits_numpy(d)
+        for f in ("event_number", "column", "row", "frame"):
+            assert np.array_equal(got[f], want[f]), (d, f)
+
+
+def test_compact_with_pool_rounds_wide_clusters_and_count_overflow():
+    """4 um pixels (dozens of rows per particle, several pool rounds), then 0.25 um pixels: thousands of rows per
+    particle saturate the count byte, which the device must report instead of delivering a wrong table."""
+    from pytestbeam_b200 import config as cfg
+    from pytestbeam_b200.engine import PtbError, Simulator
+    n = 3000
+    setup = cfg.c1(n)
+    setup["devices"]["mimosa26_p3"].update(column=5000, row=2500, column_pitch=4.0, row_pitch=4.0, threshold=0)
+    beam, devices, materials, names = cfg.flatten(setup)
+    for pool in (0, 96):
+        sim = Simulator(beam, devices, materials, pool_entries=pool)
+        caps = [64 * n] * len(devices)
+        a = sim.run(0, n, seed=9, capacities=caps)
+        b = sim.run(0, n, seed=9, capacities=caps, compact=True)
+        assert a.totals["hits"][2] > 20 * n
+        for d in range(len(devices)):
+            assert b.hits_numpy(d).tobytes() == a.hits_numpy(d).tobytes(), (pool, d)
+    setup = cfg.c1(600)
+    setup["beam"].update(sigma_x=1500.0, sigma_y=1500.0)
+    setup["devices"]["mimosa26_p2"].update(column=60000, row=40000, column_pitch=0.25, row_pitch=0.25, threshold=0)
+    setup["devices"]["mimosa26_p4"].update(column=20000, row=10000, column_pitch=1.0, row_pitch=1.0, threshold=0)
+    beam, devices, materials, names = cfg.flatten(setup)
+    sim = Simulator(beam, devices, materials)
+    with pytest.raises(PtbError, match="255"):
+        sim.run(0, 600, seed=5, compact=True)          # (the undersized default buffers are retried first)
+
+
+@pytest.mark.parametrize("chunk,n_total", [(20_000, 100_000), (30_000, 100_001), (64, 1000)])
+def test_pipeline_to_host_equals_one_call(chunk, n_total):
+    from pytestbeam_b200.pipeline import ChunkPipeline
+    sim = _sim(H.setup("c4", n_total))
+    first, seed = 12_345, 77
+    whole = sim.run(first, n_total, seed=seed)
+    for compact in (True, False):
+        pipe = ChunkPipeline(sim, chunk, host=True, seed=seed, compact=compact)
+        got = [[] for _ in range(sim.D)]
+        bases = []
+
+        def consume(c):
+            bases.append((c.first, c.n, c.event_base))
+            for d in range(sim.D):
+                got[d].append(c.records(d).copy())
+
+        rows, nbytes = pipe.run_to_host(first, 0, consume=consume, n_total=n_total)
+        assert rows == sum(whole.totals["hits"]) and nbytes > 0
+        assert [b[0] for b in bases] == list(range(first, first + n_total, chunk))
+        assert sum(b[1] for b in bases) == n_total
+        for d in range(sim.D):
+            assert np.concatenate(got[d]).tobytes() == whole.hits_numpy(d).tobytes(), (compact, d)
+
+
+def test_pipeline_retries_a_chunk_that_overflows_instead_of_raising():
+    """Buffers far too small for the chunk: the device reports the exact need, the pipeline runs that chunk again with
+    it and the tables still equal the one-call tables (round 1 raised here)."""
+    from pytestbeam_b200.pipeline import ChunkPipeline
+    n_total, chunk, seed = 60_000, 20_000, 5
+    sim = _sim(H.setup("c1", n_total))
+    whole = sim.run(0, n_total, seed=seed)
+    for compact in (True, False):
+        pipe = ChunkPipeline(sim, chunk, host=True, seed=seed, compact=compact, capacities=[500] * sim.D,
+                             scratch_rows=[700] * sim.D)
+        got = [[] for _ in range(sim.D)]
+        pipe.run_to_host(0, 3, consume=lambda c: [got[d].append(c.records(d).copy()) for d in range(sim.D)])
+        assert pipe.retries == 3
+        for d in range(sim.D):
+            assert np.concatenate(got[d]).tobytes() == whole.hits_numpy(d).tobytes(), (compact, d)
+    dev_pipe = ChunkPipeline(sim, chunk, seed=seed, capacities=[500] * sim.D, scratch_rows=[700] * sim.D)
+    dev_pipe.run(0, 3)
+    from pytestbeam_b200 import native as N
+    assert dev_pipe.errors() & (N.PTB_DEV_SCRATCH_OVERFLOW | N.PTB_DEV_SLAB_OVERFLOW)
+
+
+def test_scratch_overflow_leaves_no_uninitialised_rows():
+    """A reservation that does not fit writes nothing and nothing of it is gathered (advisor, round 1): every row of
+    the slab beyond what was really copied keeps its fill pattern, and the totals still hold the exact need."""
+    import torch
+    from pytestbeam_b200 import native as N
+    from pytestbeam_b200.engine import _TOTALS_WORDS, Simulator
+    n = 40_000
+    sim = _sim(H.setup("c1", n))
+    good = sim.run(0, n, seed=3)
+    caps = [int(h) + 64 for h in good.totals["hits"]]
+    rows = [max(int(r) // 2, 1) for r in good.totals["reserved"]]          # half of the groups cannot reserve
+    slabs = sim.alloc_slabs(caps)
+    for s in slabs:
+        s["event"].fill_(-7)
+    totals = torch.zeros(_TOTALS_WORDS, dtype=torch.int64, device=sim.device)
+    flags = N.PTB_DIGITISE | N.PTB_RECYCLE_SLABS
+    ws = torch.empty(sim.workspace_bytes(n, caps, flags, rows), dtype=torch.uint8, device=sim.device)
+    sim.launch(0, n, seed=3, flags=flags, slabs=slabs, totals=totals, workspace=ws, scratch_rows=rows)
+    torch.cuda.synchronize()
+    tot = Simulator.decode_totals(totals, sim.D)
+    assert tot["error"] & N.PTB_DEV_SCRATCH_OVERFLOW
+    assert tot["hits"] == good.totals["hits"] and tot["reserved"] == good.totals["reserved"]
+    for d in range(sim.D):
+        ev = slabs[d]["event"].cpu().numpy()[:tot["hits"][d]]
+        want = good.slabs[d]["event"].cpu().numpy()
+        written = ev != -7
+        assert 0 < written.sum() < len(ev)                                  # some groups fitted, some did not
+        assert np.array_equal(ev[written], want[written])                   # and what was copied is right
+
+
+def test_digest_matches_numpy_and_adds_up_over_pieces():
+    import torch
+    n = 30_000
+    sim = _sim(H.setup("c4", n))
+    r = sim.run(0, n, seed=11)
+    M64 = (1 << 64) - 1
+
+    def mix(ev, col, row, q):
+        h = (ev.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15))
+        h ^= col.astype(np.uint64) | (row.astype(np.uint64) << np.uint64(16)) | (q.astype(np.uint64) << np.uint64(32))
+        h ^= h >> np.uint64(29)
+        h *= np.uint64(0xBF58476D1CE4E5B9)
+        h ^= h >> np.uint64(32)
+        return h
+
+    for d in (1, 6):
+        t = r.hits_numpy(d)
+        m = mix(t["event_number"], t["column"], t["row"], t["charge"].view(np.uint32))
+        idx = np.arange(1, len(t) + 1, dtype=np.uint64)
+        with np.errstate(over="ignore"):
+            want = [len(t), int(t["event_number"].astype(np.uint64).sum()), int(t["column"].astype(np.uint64).sum()),
+                    int(t["row"].astype(np.uint64).sum()), int(t["charge"].view(np.uint32).astype(np.uint64).sum()),
+                    int(m.sum()), int((idx * m).sum())]
+        out = torch.zeros(7, dtype=torch.int64, device=sim.device)
+        sim.digest(r.slabs[d], len(t), 0, out)
+        got = [int(v) & M64 for v in out.cpu().tolist()]
+        assert got == [w & M64 for w in want]
+        # two pieces, the second digested with its global row base: the words add up to the whole table's
+        cut = len(t) // 3
+        out2 = torch.zeros(7, dtype=torch.int64, device=sim.device)
+        sim.digest({k: v[:cut] for k, v in r.slabs[d].items()}, cut, 0, out2)
+        sim.digest({k: v[cut:] for k, v in r.slabs[d].items()}, len(t) - cut, cut, out2)
+        assert [int(v) & M64 for v in out2.cpu().tolist()] == got
+        # and the order matters: swapping two different rows changes S2 only
+        sw = {k: v.clone() for k, v in r.slabs[d].items()}
+        i, j = 0, len(t) - 1
+        for k in sw:
+            sw[k][i], sw[k][j] = r.slabs[d][k][j], r.slabs[d][k][i]
+        out3 = torch.zeros(7, dtype=torch.int64, device=sim.device)
+        sim.digest(sw, len(t), 0, out3)
+        g3 = [int(v) & M64 for v in out3.cpu().tolist()]
+        assert g3[:6] == got[:6] and g3[6] != got[6]
+
+
+def test_energy_below_the_electron_mass_leaves_no_hits_like_the_reference():
+    """Q17: the Highland width is NaN below 0.511 MeV, the track position turns NaN one plane later.  Numba's int(nan)
+    is INT64_MIN, which fails the matrix test, so the reference writes no hit there; the conversion on the GPU saturates
+    to 0 instead and must not be taken for pixel 1 (advisor, round 1)."""
+    from oracle import cpu_oracle as co
+    from pytestbeam_b200 import config as cfg
+    from pytestbeam_b200.engine import Simulator
+    n = 4000
+    setup = cfg.c1(n)
+    setup["beam"]["energy"] = 0.60                      # two planes of ~0.03 MeV loss push most tracks below the mass
+    for d in setup["devices"].values():
+        d["threshold"] = 0                              # the seed fallback would fire on every spurious seed pixel
+    beam, devices, materials, names = cfg.flatten(setup)
+    rs = np.random.RandomState(5)
+    table = rs.uniform(0.02, 0.06, size=(len(devices), n))
+    run = co.run(beam, devices, materials, n, 61, 62, table_override=table)
+    x = run.tracks[3].reshape(n, len(devices))
+    assert np.isnan(x[:, -1]).mean() > 0.5 and np.isfinite(x[:, 1]).all()
+    sim = Simulator(beam, devices, materials)
+    res = sim.run(0, n, injected=H.injected_for(sim, run, 0, n), write_tracks=True)
+    gx = res.tracks["x"].cpu().numpy().reshape(n, len(devices))
+    assert np.array_equal(np.isnan(gx), np.isnan(x))
+    for d in range(sim.D):
+        got, want = res.hits_numpy(d), run.hits[d]
+        assert len(got) == len(want), (d, len(got), len(want))
+        for f in ("event_number", "column", "row"):
+            assert np.array_equal(got[f], want[f]), (d, f)
+    assert len(run.hits[-1]) < len(run.hits[1])
+
+
+def test_calculate_device_hit_accepts_the_reference_tuple(tmp_path, golden_dir):
+    """main/device.py:132-138 reads x = hit_data[3], y = hit_data[4], energy_lost = hit_data[7] of a plain 8-tuple: the
+    drop-in must take the oracle's tuple and the reference's own (golden) tuple, not only its own HitTables."""
+    from pytestbeam_b200 import h5min
+    from pytestbeam_b200.main import device
+    log = logging.getLogger("test")
+    n = 6000
+    setup, run = H.oracle_run("c4", n, 5, 6)
+    beam, devices, materials, names = setup
+    beam = dict(beam, seed=99)
+    tup = tuple(list(a) if i in (3, 4) else a for i, a in enumerate(run.tracks[:7])) + (run.eloss,)   # lists, like typed Lists
+    folder = str(tmp_path) + "/"
+    device.calculate_device_hit(beam, devices, tup, names, folder, log)
+    sim = _sim((beam, devices, materials, names))
+    want = device.device_hits_from_arrays(sim, run.tracks[3], run.tracks[4], run.eloss, 99)
+    for d, name in enumerate(names):
+        got = h5min.read_table(folder + name + "_dut.h5", "Hits")
+        assert got.tobytes() == want[d].tobytes(), name
+        assert abs(len(got) - len(run.hits[d])) <= 0.1 * len(run.hits[d]) + 50        # same physics, other variates
+        assert h5min.read_attrs(folder + name + "_dut.h5", "Hits")["NROWS"] == len(got)
+    gold = np.load(os.path.join(golden_dir, "full_c1_n1000_s11_22.npz"))
+    b1, d1, m1, n1 = H.setup("c1", 1000)
+    b1 = dict(b1, seed=3)
+    gtup = (gold["energy"], gold["anglex"], gold["angley"], gold["x"], gold["y"], gold["z"],
+            gold["time_stamp"], gold["eloss"])
+    tables = device.device_hits(b1, d1, gtup)
+    for d, name in enumerate(n1):
+        assert abs(len(tables[d]) - len(gold["hits_" + name])) <= 0.15 * len(gold["hits_" + name]) + 30
+    with pytest.raises(TypeError):
+        device.device_hits(b1, d1, (1, 2, 3))
+    with pytest.raises(ValueError):
+        device.device_hits(dict(b1, nmb_particles=999), d1, gtup)
+
+
+def test_entry_point_streams_files_equal_to_one_call(tmp_path):
+    """hit.tracks -> calculate_device_hit (fused, streamed through the mapped dataset region) and create_output_tracks
+    (streamed) against one ptb_simulate call of the whole range."""
+    from pytestbeam_b200 import h5min
+    from pytestbeam_b200.main import device, hit
+    log = logging.getLogger("test")
+    n = 70_001
+    beam, devices, materials, names = H.setup("c1", n)
+    beam["seed"] = 4242
+    folder = str(tmp_path) + "/"
+    old = hit.CHUNK, device.CHUNK
+    hit.CHUNK = device.CHUNK = 16_000               # several chunks, a ragged last one
+    try:
+        tables = hit.tracks(beam, devices, materials, log)
+        hit.create_output_tracks(tables, folder)
+        assert not tables.materialised
+        device.calculate_device_hit(beam, devices, tables, names, folder, log)
+        assert not tables.materialised
+    finally:
+        hit.CHUNK, device.CHUNK = old
+    sim = _sim((beam, devices, materials, names))
+    one = sim.run(0, n, seed=4242, write_tracks=True)
+    for d, name in enumerate(names):
+        assert h5min.read_table(folder + name + "_dut.h5", "Hits").tobytes() == one.hits_numpy(d).tobytes(), name
+    trk = h5min.read_table(folder + "particle_tracks.h5", "Tracks")
+    assert len(trk) == n * sim.D
+    assert np.array_equal(trk["x"], one.tracks["x"].cpu().numpy())
+    assert np.array_equal(trk["time_stamp"], one.tracks["time_stamp"].cpu().numpy().astype(np.uint16))
+    head = tables.head(1000)
+    assert np.array_equal(head[3], one.tracks["x"].cpu().numpy()[:1000 * sim.D]) and head[7].shape == (sim.D, 1000)
