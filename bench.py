@@ -60,6 +60,8 @@ class ClockSampler:
         self.t_begin = self.t_end = None
 
     def start(self):
+        if os.environ.get("PTB_BENCH_NO_SAMPLER"):      # developer switch: is the sampling itself visible in the timing?
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
@@ -232,6 +234,7 @@ class Job:
         import torch
         import torch.distributed as dist
         from pytestbeam_b200 import config as cfg
+        from pytestbeam_b200 import distributed as _dist_mod   # noqa: F401  (imported here, not inside the timed region)
         from pytestbeam_b200.engine import Simulator
         from pytestbeam_b200.pipeline import bind_host_to_gpu, shard_range
         self.torch, self.dist = torch, dist
@@ -440,7 +443,8 @@ def run_gpu(args):
     sampler.end()
     ms = e0.elapsed_time(e1)
     launches = lib.ptb_launch_count() - launches0
-    trk_ms, dig_ms, sim_launches = sim.timing_read()
+    stages, sim_launches = sim.timing_read_stages()
+    trk_ms, dig_ms = stages[0], stages[1]
     sim.timing(False)
     launch_ms = dig_ms / max(sim_launches, 1)        # dominant kernel: k_digitise
     tracks_launch_ms = trk_ms / max(sim_launches, 1)
@@ -494,6 +498,9 @@ def run_gpu(args):
                 "peak_source": "in-job DFMA probe (ptb_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
                 "flops_per_electron": F, "flops_per_electron_whole_path": F_all, "launch_ms": launch_ms,
                 "k_tracks_launch_ms": tracks_launch_ms, "launches_timed": sim_launches,
+                "stage_ms_per_step": {"k_tracks": stages[0] / max(sim_launches, 1), "k_digitise": stages[1] / max(sim_launches, 1),
+                                      "k_digitise_big+scans": stages[2] / max(sim_launches, 1),
+                                      "k_gather": stages[3] / max(sim_launches, 1)},
                 "share_of_step": launch_ms / (ms / K), "traffic": traffic, "traffic_over_algorithmic":
                     traffic / alg_bytes if traffic else None, "ncu": ncu,
                 "binding": "instruction issue (see ncu.issue_active_pct; FP64 pipe about a quarter busy): profiles/README.md",

@@ -237,6 +237,8 @@ int ptb_digest(const PtbHitSlab *slab, uint64_t n, uint64_t row_base, uint64_t *
  */
 int ptb_timing_enable(PtbHandle h, int32_t on);
 int ptb_timing_read(PtbHandle h, double *tracks_ms, double *digitise_ms, uint64_t *calls);
+/* the same record by stage: stage_ms[0..3] = k_tracks, k_digitise, k_digitise_big + the two scan kernels, k_gather */
+int ptb_timing_read_stages(PtbHandle h, double *stage_ms /*[4]*/, uint64_t *calls);
 
 /* number of kernels this library has launched on the calling process since load (bench bookkeeping) */
 uint64_t ptb_launch_count(void);

@@ -115,6 +115,18 @@ __host__ __device__ __forceinline__ U4 philox4x32_10(U4 c, const PhiloxKeys &key
     return c;
 }
 
+// Philox2x32-10 (same paper): 64-bit counter, 32-bit key.  Used for the one variate that is drawn per pixel rather than
+// per particle (the pixel noise), where a four-word block would be three quarters wasted.
+__device__ __forceinline__ void philox2x32_10(uint32_t &c0, uint32_t &c1, uint32_t key)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi = __umulhi(0xD256D193u, c0), lo = 0xD256D193u * c0;
+        c0 = hi ^ (key + (uint32_t)r * 0x9E3779B9u) ^ c1;
+        c1 = lo;
+    }
+}
+
 // draw sites of one particle; plane-dependent sites are SITE_PLANE + 4*plane + {STEP,DIG,PIX}
 enum : uint32_t { SITE_EVENT = 0, SITE_START = 1, SITE_PLANE = 4, SUB_STEP = 0, SUB_DIG = 1, SUB_PIX = 2 };
 
@@ -276,16 +288,32 @@ struct PhiloxSource {
         double e = p.lan_loc + p.lan_scale * lam;
         return fmin(fmax(e, 0.0), 0.5);
     }
-    __device__ void dig(uint64_t k, int d, double &zrx, double &zry, double &zseed) const
+    // pixkey: key of the pair's pixel-noise stream (below); a function of (seed, particle, plane) like everything else here
+    __device__ void dig(uint64_t k, int d, double &zrx, double &zry, double &zseed, uint32_t &pixkey) const
     {
         U4     w = philox_at(seed, k, SITE_PLANE + 4 * d + SUB_DIG, 0);
         double spare;
         normal_pair_f32(w.x, w.y, zrx, zry);
         normal_pair_f32(w.z, w.w, zseed, spare);
+        pixkey = w.z ^ __funnelshift_l(w.w, w.w, 16);
     }
-    // noise normal of the p-th candidate pixel of particle k on plane d: four consecutive pixels share one Philox
-    // block, every lane works out the one normal it needs
-    __device__ double pixel(uint64_t k, int d, uint32_t p, int /*jf*/) const
+    static constexpr bool kPixelKeyed = true;
+#ifndef PTB_PIXEL_PHILOX4
+    // Noise normal of the p-th candidate pixel of particle k on plane d: Philox2x32-10 under the pair's key, counter =
+    // (particle id, plane, pixel index) -- 34 + 5 + 20 bits, so no two pixels of a run share a counter whatever their
+    // keys -- and the cosine branch of a Box-Muller pair (the sine branch would belong to no pixel).
+    __device__ double pixel(uint64_t k, int d, uint32_t p, uint32_t key) const
+    {
+        uint32_t a = (uint32_t)k, b = p | ((uint32_t)d << 20) | ((uint32_t)(k >> 32) << 25);
+        philox2x32_10(a, b, key);
+        const float u = fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // as normal_pair_f32
+        const float v = fmaf((float)b, 1.4629180792671596e-09f, 7.3145903963357980e-10f);
+        return (double)(sqrt_sfu(-1.3862943611198906f * lg2_sfu(u)) * __cosf(v));
+    }
+#else
+    // (round-1 scheme, kept for A/B timing: four consecutive pixels share one Philox4x32 block, every lane works out the
+    // one normal it needs)
+    __device__ double pixel(uint64_t k, int d, uint32_t p, uint32_t /*key*/) const
     {
         const U4       w = philox_at(seed, k, SITE_PLANE + 4 * d + SUB_PIX, p >> 2);
         const uint32_t a = (p & 2u) ? w.z : w.x, b = (p & 2u) ? w.w : w.y;
@@ -296,6 +324,7 @@ struct PhiloxSource {
         __sincosf(v, &s, &c);
         return (double)(r * ((p & 1u) ? s : c));
     }
+#endif
 };
 
 struct InjectedSource {
@@ -321,13 +350,15 @@ struct InjectedSource {
     {
         return (k + 1 == first) ? v.eloss0_prev : v.eloss[(uint64_t)d * n + (k - first)];
     }
-    __device__ void dig(uint64_t k, int d, double &zrx, double &zry, double &zseed) const
+    __device__ void dig(uint64_t k, int d, double &zrx, double &zry, double &zseed, uint32_t &pixkey) const
     {
         const double *p = v.dig_z + v.dig_off[(uint64_t)d * (n + 1) + (k - first)];
         zrx = p[0]; zry = p[1]; zseed = p[2];
+        pixkey = 0;
     }
     // jf: index of the pixel in the reference's walk over its full bounding box = draw order
-    __device__ double pixel(uint64_t k, int d, uint32_t /*p*/, int jf) const
+    static constexpr bool kPixelKeyed = false;
+    __device__ double pixel(uint64_t k, int d, uint32_t /*p*/, uint32_t jf) const
     {
         return v.dig_z[v.dig_off[(uint64_t)d * (n + 1) + (k - first)] + 3 + jf];
     }

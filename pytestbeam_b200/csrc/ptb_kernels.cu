@@ -321,7 +321,11 @@ __device__ __forceinline__ Cluster describe(const ConfigK &cfg, const PlaneK &pl
     Cluster      out{0, 0, 0, false, false};
     const double sig = cloud_sigma(cfg, eloss);
     double       zrx, zry, zseed;
-    src.dig(k, d, zrx, zry, zseed);
+    uint32_t     pixkey;
+    src.dig(k, d, zrx, zry, zseed, pixkey);
+    // What selects a pixel's noise variate: the key of the pair's stream (Philox; stored at once, it need not live on),
+    // or the position of the trimmed box inside the reference's box (injected variates come in the reference's draw order)
+    if (Src::kPixelKeyed) W.jbase[lane] = (int)pixkey;
     const bool   injected_charge = (flags & PTB_ZERO_RADIUS) != 0;   // threshold scan: radius 0
     const double rx = injected_charge ? 0.0 : fabs(0.0 + sig * zrx);
     const double ry = injected_charge ? 0.0 : fabs(0.0 + sig * zry);
@@ -378,7 +382,8 @@ __device__ __forceinline__ Cluster describe(const ConfigK &cfg, const PlaneK &pl
         W.pos[0][lane] = x; W.pos[1][lane] = y; W.rad[0][lane] = rx; W.rad[1][lane] = ry;
         W.ye[0][lane] = yx; W.ye[1][lane] = yy;
         W.lo[0][lane] = c_lo + ca; W.lo[1][lane] = r_lo + ra; W.ncols[lane] = (uint16_t)ncT; W.nrows[lane] = (uint16_t)nrT;
-        W.jbase[lane] = ca * (int)nr + ra; W.nrfull[lane] = (int)nr;
+        if (!Src::kPixelKeyed) W.jbase[lane] = ca * (int)nr + ra;
+        W.nrfull[lane] = (int)nr;
         W.rnr[lane] = __fdividef(1.0f, (float)max(nrT, 1));
     }
     return out;
@@ -401,9 +406,9 @@ __device__ __forceinline__ void profile_entry(const AxisK &ax, int idx, double p
 // k_tracks' park or, with PTB_TRACKS_FROM_TABLE, from the caller's hit_tables arrays exactly as
 // main/device.py:132-138 reads them.
 // ---------------------------------------------------------------------------------------------------
-// PC = profile-pool entries, KEEP64 = also carry the f8 charge: compile-time, so that every shared-memory address
+// PC = profile-pool entries, MODE = output form (0: slabs, 1: slabs + f8 charge, 2: compressed rows): compile-time, so that every shared-memory address
 // is base + immediate (as run-time values their re-derivation was 7 % of the executed instructions).
-template <class Src, int PC, bool KEEP64>
+template <class Src, int PC, int MODE>
 __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __grid_constant__ ConfigK cfg,
                                                                     const __grid_constant__ KParams P, const Src src)
 {
@@ -414,9 +419,8 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
     if (group >= P.n_groups) return;  // whole warps leave; no block-wide barrier is used anywhere below
 
     const int    D = cfg.n_planes;
-    constexpr bool   keep64 = KEEP64;
+    constexpr bool   keep64 = MODE == 1, compact = MODE == 2;
     const bool       from_table = (P.flags & PTB_TRACKS_FROM_TABLE) != 0;
-    const bool       compact = (P.flags & PTB_COMPACT) != 0;
     constexpr size_t wbytes = warp_shared_bytes(PC);
 
     unsigned char *wbase = smem_raw + wbytes * wib;
@@ -628,8 +632,8 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
                                       po + ncl + nrw <= PC);
                         // index of the pixel in the reference's (column-major) walk over its full box: the injected
                         // noise variates are keyed by it
-                        const int    jf = W.jbase[own] + ci * W.nrfull[own] + ri;
-                        const double zn = src.pixel(P.first + group * 32 + own, d, (uint32_t)p, jf);
+                        const int    jf = Src::kPixelKeyed ? W.jbase[own] : W.jbase[own] + ci * W.nrfull[own] + ri;
+                        const double zn = src.pixel(P.first + group * 32 + own, d, (uint32_t)p, (uint32_t)jf);
                         const double noise = 0.0 + pl.noise_sigma * zn;
                         const double signal = W.q[own] * (pool_g[po + ci] * pool_g[po + ncl + ri]);
                         hq = (signal + noise) * 1e-3 * pl.pitch_c * pl.pitch_r;   // device.py:275-288
@@ -781,7 +785,8 @@ __global__ void __launch_bounds__(32 * BIG_WARPS) k_digitise_big(const __grid_co
                     double    gc, ec, gr, er;
                     profile_entry(pl.ax[0], W.lo[0][b] + ci, px, rx, W.nrm[0][b], W.ye[0][b], gc, ec);
                     profile_entry(pl.ax[1], W.lo[1][b] + ri, py, ry, W.nrm[1][b], W.ye[1][b], gr, er);
-                    const double zn = src.pixel(P.first + group * 32 + b, d, (uint32_t)p, W.jbase[b] + ci * W.nrfull[b] + ri);
+                    const double zn = src.pixel(P.first + group * 32 + b, d, (uint32_t)p,
+                                                (uint32_t)(Src::kPixelKeyed ? W.jbase[b] : W.jbase[b] + ci * W.nrfull[b] + ri));
                     const double noise = 0.0 + pl.noise_sigma * zn;
                     const double signal = q * (gc * gr);
                     hq = (signal + noise) * 1e-3 * pl.pitch_c * pl.pitch_r;   // device.py:275-288
@@ -1205,23 +1210,32 @@ __global__ void __launch_bounds__(256) k_dfma(double *out, int iters, double a, 
 
 }  // namespace ptb
 
-template <class Src, int PC, bool KEEP64>
+template <class Src, int PC, int MODE>
 static cudaError_t launch_digitise(unsigned blocks, cudaStream_t st, const ptb::ConfigK &c, const ptb::KParams &P,
                                    const Src &src)
 {
     using namespace ptb;
     constexpr size_t smem = warp_shared_bytes(PC) * WARPS_PER_BLOCK;
-    k_digitise<Src, PC, KEEP64><<<blocks, BLOCK, smem, st>>>(c, P, src);
+    k_digitise<Src, PC, MODE><<<blocks, BLOCK, smem, st>>>(c, P, src);
     return cudaGetLastError();
+}
+
+template <class Src, int PC>
+static cudaError_t launch_digitise_mode(int mode, unsigned blocks, cudaStream_t st, const ptb::ConfigK &c,
+                                        const ptb::KParams &P, const Src &src)
+{
+    return mode == 2 ? launch_digitise<Src, PC, 2>(blocks, st, c, P, src)
+         : mode == 1 ? launch_digitise<Src, PC, 1>(blocks, st, c, P, src)
+                     : launch_digitise<Src, PC, 0>(blocks, st, c, P, src);
 }
 
 // Shared-memory carve-out of every k_digitise variant: asked for once per handle (ptb_create), not per launch.  The
 // dynamic shared memory stays below the 48 KB that need no opt-in.
-template <class Src, int PC, bool KEEP64>
+template <class Src, int PC, int MODE>
 static cudaError_t prefer_shared()
 {
     static_assert(ptb::warp_shared_bytes(PC) * ptb::WARPS_PER_BLOCK <= 48 * 1024, "k_digitise needs the shared-memory opt-in");
-    return cudaFuncSetAttribute(ptb::k_digitise<Src, PC, KEEP64>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    return cudaFuncSetAttribute(ptb::k_digitise<Src, PC, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                 cudaSharedmemCarveoutMaxShared);
 }
 
@@ -1230,14 +1244,18 @@ static cudaError_t prefer_shared_all()
     using namespace ptb;
     cudaError_t e = cudaSuccess;
     auto also = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
-    also(prefer_shared<PhiloxSource, POOL_ENTRIES, false>());
-    also(prefer_shared<PhiloxSource, POOL_ENTRIES, true>());
-    also(prefer_shared<PhiloxSource, SMALL_POOL, false>());
-    also(prefer_shared<PhiloxSource, SMALL_POOL, true>());
-    also(prefer_shared<InjectedSource, POOL_ENTRIES, false>());
-    also(prefer_shared<InjectedSource, POOL_ENTRIES, true>());
-    also(prefer_shared<InjectedSource, SMALL_POOL, false>());
-    also(prefer_shared<InjectedSource, SMALL_POOL, true>());
+    also(prefer_shared<PhiloxSource, POOL_ENTRIES, 0>());
+    also(prefer_shared<PhiloxSource, POOL_ENTRIES, 1>());
+    also(prefer_shared<PhiloxSource, POOL_ENTRIES, 2>());
+    also(prefer_shared<PhiloxSource, SMALL_POOL, 0>());
+    also(prefer_shared<PhiloxSource, SMALL_POOL, 1>());
+    also(prefer_shared<PhiloxSource, SMALL_POOL, 2>());
+    also(prefer_shared<InjectedSource, POOL_ENTRIES, 0>());
+    also(prefer_shared<InjectedSource, POOL_ENTRIES, 1>());
+    also(prefer_shared<InjectedSource, POOL_ENTRIES, 2>());
+    also(prefer_shared<InjectedSource, SMALL_POOL, 0>());
+    also(prefer_shared<InjectedSource, SMALL_POOL, 1>());
+    also(prefer_shared<InjectedSource, SMALL_POOL, 2>());
     return e;
 }
 
@@ -1253,7 +1271,8 @@ struct PtbContext {
     int     sm_count;
     int     may_be_big;   // a production-mode cluster can outgrow the profile pool (sizes k_digitise_big's grid)
     int     timing;
-    std::vector<cudaEvent_t> ev;   // (start, after k_tracks, after k_digitise) per ptb_simulate, when timing is enabled
+    std::vector<cudaEvent_t> ev;   // TIMING_EVENTS per ptb_simulate (start, after k_tracks, after k_digitise, after
+                                   // k_digitise_big + scans, after k_gather), when timing is enabled
     size_t  ev_used;
     char    err[512];
 };
@@ -1478,40 +1497,51 @@ int ptb_timing_enable(PtbHandle h, int32_t on)
     return PTB_OK;
 }
 
-int ptb_timing_read(PtbHandle h, double *tracks_ms, double *digitise_ms, uint64_t *calls)
+constexpr size_t TIMING_EVENTS = 5;
+
+int ptb_timing_read_stages(PtbHandle h, double *stage_ms, uint64_t *calls)
 {
-    if (!h || !tracks_ms || !digitise_ms || !calls) return PTB_E_INVALID;
-    double st = 0, sd = 0;
-    for (size_t i = 0; i + 2 < h->ev_used; i += 3) {
-        cudaError_t e = cudaEventSynchronize(h->ev[i + 2]);
+    if (!h || !stage_ms || !calls) return PTB_E_INVALID;
+    for (size_t j = 0; j + 1 < TIMING_EVENTS; ++j) stage_ms[j] = 0;
+    for (size_t i = 0; i + TIMING_EVENTS <= h->ev_used; i += TIMING_EVENTS) {
+        cudaError_t e = cudaEventSynchronize(h->ev[i + TIMING_EVENTS - 1]);
         if (e != cudaSuccess) return fail_cuda(h, e, "cudaEventSynchronize");
-        float a = 0, b = 0;
-        e = cudaEventElapsedTime(&a, h->ev[i], h->ev[i + 1]);
-        if (e == cudaSuccess) e = cudaEventElapsedTime(&b, h->ev[i + 1], h->ev[i + 2]);
-        if (e != cudaSuccess) return fail_cuda(h, e, "cudaEventElapsedTime");
-        st += a;
-        sd += b;
+        for (size_t j = 0; j + 1 < TIMING_EVENTS; ++j) {
+            float a = 0;
+            e = cudaEventElapsedTime(&a, h->ev[i + j], h->ev[i + j + 1]);
+            if (e != cudaSuccess) return fail_cuda(h, e, "cudaEventElapsedTime");
+            stage_ms[j] += a;
+        }
     }
-    *tracks_ms = st;
-    *digitise_ms = sd;
-    *calls = h->ev_used / 3;
+    *calls = h->ev_used / TIMING_EVENTS;
     h->ev_used = 0;
     return PTB_OK;
 }
 
-// next (start, mid, stop) event triple of the timing record, or nullptr when timing is off
+int ptb_timing_read(PtbHandle h, double *tracks_ms, double *digitise_ms, uint64_t *calls)
+{
+    if (!tracks_ms || !digitise_ms) return PTB_E_INVALID;
+    double    st[TIMING_EVENTS - 1];
+    const int rc = ptb_timing_read_stages(h, st, calls);
+    if (rc != PTB_OK) return rc;
+    *tracks_ms = st[0];
+    *digitise_ms = st[1];
+    return PTB_OK;
+}
+
+// next group of events of the timing record, or nullptr when timing is off
 static cudaEvent_t *timing_pair(PtbHandle h)
 {
     if (!h->timing) return nullptr;
-    if (h->ev_used + 3 > h->ev.size()) {
-        for (int i = 0; i < 3; ++i) {
+    if (h->ev_used + TIMING_EVENTS > h->ev.size()) {
+        for (size_t i = 0; i < TIMING_EVENTS; ++i) {
             cudaEvent_t e;
             if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
             h->ev.push_back(e);
         }
     }
     cudaEvent_t *p = &h->ev[h->ev_used];
-    h->ev_used += 3;
+    h->ev_used += TIMING_EVENTS;
     return p;
 }
 
@@ -1637,22 +1667,15 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
     if (flags & PTB_DIGITISE) {
         const unsigned blocks = (unsigned)((P.n_groups + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
         const bool     small = c.pool_entries == SMALL_POOL;
+        const int mode = compact ? 2 : keep64 ? 1 : 0;
         if (run->injected) {
             InjectedSource src{*run->injected, run->first, run->n};
-            if (small)
-                e = keep64 ? launch_digitise<InjectedSource, SMALL_POOL, true>(blocks, st, c, P, src)
-                           : launch_digitise<InjectedSource, SMALL_POOL, false>(blocks, st, c, P, src);
-            else
-                e = keep64 ? launch_digitise<InjectedSource, POOL_ENTRIES, true>(blocks, st, c, P, src)
-                           : launch_digitise<InjectedSource, POOL_ENTRIES, false>(blocks, st, c, P, src);
+            e = small ? launch_digitise_mode<InjectedSource, SMALL_POOL>(mode, blocks, st, c, P, src)
+                      : launch_digitise_mode<InjectedSource, POOL_ENTRIES>(mode, blocks, st, c, P, src);
         } else {
             PhiloxSource src{philox_keys(run->seed)};
-            if (small)
-                e = keep64 ? launch_digitise<PhiloxSource, SMALL_POOL, true>(blocks, st, c, P, src)
-                           : launch_digitise<PhiloxSource, SMALL_POOL, false>(blocks, st, c, P, src);
-            else
-                e = keep64 ? launch_digitise<PhiloxSource, POOL_ENTRIES, true>(blocks, st, c, P, src)
-                           : launch_digitise<PhiloxSource, POOL_ENTRIES, false>(blocks, st, c, P, src);
+            e = small ? launch_digitise_mode<PhiloxSource, SMALL_POOL>(mode, blocks, st, c, P, src)
+                      : launch_digitise_mode<PhiloxSource, POOL_ENTRIES>(mode, blocks, st, c, P, src);
         }
         ++g_launches;
         if (e != cudaSuccess) return fail_cuda(h, e, "k_digitise launch");
@@ -1662,6 +1685,10 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
         // a pair k_digitise defers can never stay unserved; a small grid when no such cluster is expected
         {
             const bool               expected = run->injected || (flags & PTB_TRACKS_FROM_TABLE) || h->may_be_big;
+#ifdef PTB_BIG_ONLY_IF_EXPECTED
+            if (expected)
+#endif
+            {
             const unsigned long long items = P.n_groups * (unsigned long long)D;
             const unsigned bb = (unsigned)std::min<unsigned long long>((items + BIG_WARPS - 1) / BIG_WARPS,
                                                                        (unsigned long long)h->sm_count * (expected ? 16 : 2));
@@ -1677,6 +1704,7 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
             ++g_launches;
             e = cudaGetLastError();
             if (e != cudaSuccess) return fail_cuda(h, e, "k_digitise_big launch");
+            }
         }
     }
     if (tp && !(flags & PTB_DIGITISE)) cudaEventRecord(tp[2], st);
@@ -1686,6 +1714,7 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
     g_launches += 2;
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda(h, e, "k_scan launch");
+    if (tp) cudaEventRecord(tp[3], st);
 
     if ((flags & PTB_DIGITISE) || (flags & PTB_WRITE_TRACKS)) {
         GatherParams G;
@@ -1704,6 +1733,7 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
         e = cudaGetLastError();
         if (e != cudaSuccess) return fail_cuda(h, e, "k_gather launch");
     }
+    if (tp) cudaEventRecord(tp[4], st);
     return PTB_OK;
 }
 

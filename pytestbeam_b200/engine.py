@@ -320,6 +320,12 @@ class Simulator:
         self._check(self.lib.ptb_timing_read(self._h, C.byref(a), C.byref(b), C.byref(n)), "ptb_timing_read")
         return float(a.value), float(b.value), int(n.value)
 
+    def timing_read_stages(self):
+        """([k_tracks, k_digitise, k_digitise_big + scans, k_gather] ms, calls) summed since the last read."""
+        st, n = (C.c_double * 4)(), C.c_uint64()
+        self._check(self.lib.ptb_timing_read_stages(self._h, C.byref(st), C.byref(n)), "ptb_timing_read_stages")
+        return [float(v) for v in st], int(n.value)
+
     # -- helpers -------------------------------------------------------------------------------------
     def prefix(self, first, n, *, seed=0, injected: Injected | None = None):
         """(accepted particles, sum of time gaps) of a particle range."""

@@ -86,7 +86,7 @@ class PtbRun(C.Structure):
 
 EXPORTS = ("ptb_create", "ptb_destroy", "ptb_last_error", "ptb_n_planes", "ptb_workspace_bytes",
            "ptb_prefix", "ptb_simulate", "ptb_pack_hits", "ptb_launch_count", "ptb_measure_fp64_peak",
-           "ptb_timing_enable", "ptb_timing_read", "ptb_correlate", "ptb_digest", "ptb_expand_hits")
+           "ptb_timing_enable", "ptb_timing_read", "ptb_timing_read_stages", "ptb_correlate", "ptb_digest", "ptb_expand_hits")
 
 _lib = None
 
@@ -128,6 +128,8 @@ def load() -> C.CDLL:
     L.ptb_timing_enable.restype = C.c_int
     L.ptb_timing_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.ptb_timing_read.restype = C.c_int
+    L.ptb_timing_read_stages.argtypes = [C.c_void_p, C.POINTER(C.c_double * 4), C.POINTER(C.c_uint64)]
+    L.ptb_timing_read_stages.restype = C.c_int
     L.ptb_correlate.argtypes = [C.c_void_p] * 3 + [C.c_uint64] + [C.c_void_p] * 3 + [C.c_uint64, C.c_int64, C.c_int64,
                                 C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
     L.ptb_correlate.restype = C.c_int

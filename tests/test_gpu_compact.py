@@ -52,20 +52,20 @@ def test_compact_deterministic_vs_oracle_with_event_base():
 
 
 def test_compact_with_pool_rounds_wide_clusters_and_count_overflow():
-    """4 um pixels (dozens of rows per particle, several pool rounds), then 0.25 um pixels: thousands of rows per
+    """8 um pixels (a dozen rows per particle, several pool rounds per group), then 0.25 um pixels: thousands of rows per
     particle saturate the count byte, which the device must report instead of delivering a wrong table."""
     from pytestbeam_b200 import config as cfg
     from pytestbeam_b200.engine import PtbError, Simulator
     n = 3000
     setup = cfg.c1(n)
-    setup["devices"]["mimosa26_p3"].update(column=5000, row=2500, column_pitch=4.0, row_pitch=4.0, threshold=0)
+    setup["devices"]["mimosa26_p3"].update(column=2500, row=1250, column_pitch=8.0, row_pitch=8.0, threshold=0)
     beam, devices, materials, names = cfg.flatten(setup)
     for pool in (0, 96):
         sim = Simulator(beam, devices, materials, pool_entries=pool)
         caps = [64 * n] * len(devices)
         a = sim.run(0, n, seed=9, capacities=caps)
         b = sim.run(0, n, seed=9, capacities=caps, compact=True)
-        assert a.totals["hits"][2] > 20 * n
+        assert a.totals["hits"][2] > 5 * n
         for d in range(len(devices)):
             assert b.hits_numpy(d).tobytes() == a.hits_numpy(d).tobytes(), (pool, d)
     setup = cfg.c1(600)
@@ -206,7 +206,7 @@ def test_energy_below_the_electron_mass_leaves_no_hits_like_the_reference():
     from pytestbeam_b200.engine import Simulator
     n = 4000
     setup = cfg.c1(n)
-    setup["beam"]["energy"] = 0.60                      # two planes of ~0.03 MeV loss push most tracks below the mass
+    setup["beam"]["energy"] = 0.50                      # below the mass from the start: NaN kicks at plane 1, NaN x from plane 2
     for d in setup["devices"].values():
         d["threshold"] = 0                              # the seed fallback would fire on every spurious seed pixel
     beam, devices, materials, names = cfg.flatten(setup)
@@ -214,7 +214,8 @@ def test_energy_below_the_electron_mass_leaves_no_hits_like_the_reference():
     table = rs.uniform(0.02, 0.06, size=(len(devices), n))
     run = co.run(beam, devices, materials, n, 61, 62, table_override=table)
     x = run.tracks[3].reshape(n, len(devices))
-    assert np.isnan(x[:, -1]).mean() > 0.5 and np.isfinite(x[:, 1]).all()
+    # a track inside plane 1's window takes a NaN kick there (outside, the kick is replaced by 0: main/hit.py:219-227)
+    assert 0.5 < np.isnan(x[:, 2]).mean() < 0.9 and np.isfinite(x[1:, :2]).all()
     sim = Simulator(beam, devices, materials)
     res = sim.run(0, n, injected=H.injected_for(sim, run, 0, n), write_tracks=True)
     gx = res.tracks["x"].cpu().numpy().reshape(n, len(devices))
@@ -224,7 +225,7 @@ def test_energy_below_the_electron_mass_leaves_no_hits_like_the_reference():
         assert len(got) == len(want), (d, len(got), len(want))
         for f in ("event_number", "column", "row"):
             assert np.array_equal(got[f], want[f]), (d, f)
-    assert len(run.hits[-1]) < len(run.hits[1])
+    assert len(run.hits[1]) > 0 and len(run.hits[2]) < 0.5 * len(run.hits[1])     # the NaN tracks are gone from plane 2 on
 
 
 def test_calculate_device_hit_accepts_the_reference_tuple(tmp_path, golden_dir):
