@@ -69,8 +69,7 @@ class FileSink:
         return self.writers[plane].reserve(rows)
 
     def done(self, plane: int, view) -> None:
-        if isinstance(view, np.memmap):
-            view.flush()
+        pass            # no msync: the page cache is coherent for every later reader, the kernel writes back on its own
 
     def close(self) -> None:
         for w in self.writers:

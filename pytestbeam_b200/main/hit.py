@@ -101,8 +101,6 @@ def create_output_tracks(hit_table, folder: str) -> None:
                 for field, key in fields:
                     out[field] = piece[key]
                 out["time_stamp"] = piece["time_stamp"].astype(np.uint16)     # wraps, as in the reference (Q19)
-                if isinstance(out, np.memmap):
-                    out.flush()
         return
     numb = len(hit_table[0])
     out = np.zeros(numb, dtype=TRACKS_DTYPE)

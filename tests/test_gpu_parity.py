@@ -328,6 +328,46 @@ def test_one_million_electrons_deterministic_in_chunks(torch_cuda):
     assert rows > 7_000_000 and charge_diff <= rows * 1e-4
 
 
+def test_ten_million_electrons_deterministic_in_parallel_runs(torch_cuda):
+    """The deterministic leg beyond what one sequential oracle pass affords: sixteen complete reference replays of
+    625 000 electrons each (own seeds; every one is exactly what the reference computes for those seeds, event 0 and
+    all), produced by the C oracle on all host cores at once (the oracle keeps no global state and its ctypes calls
+    release the GIL), each fed to CUDA with its recorded variates: 1e7 electrons, 7.4e7 hit rows.  IDs must be
+    identical everywhere; f4 charges that differ by one ulp are counted and reported."""
+    from concurrent.futures import ThreadPoolExecutor
+    import os
+    runs, n = int(os.environ.get("PTB_DET_RUNS", 16)), 625_000
+    setup = H.setup("c1", n)
+    sim = _sim(setup)
+    D = sim.D
+    rows = charge_diff = 0
+    with ThreadPoolExecutor(max_workers=min(runs, os.cpu_count() or 1)) as pool:
+        futures = [pool.submit(lambda s=s: co_run(setup, n, 5000 + 2 * s, 5001 + 2 * s)) for s in range(runs)]
+        for s, fut in enumerate(futures):
+            run = fut.result()
+            futures[s] = None
+            r = sim.run(0, n, injected=H.injected_for(sim, run, 0, n))
+            for d in range(D):
+                g, w = r.hits_numpy(d), run.hits[d]
+                assert len(g) == len(w), (s, d)
+                for f in ("event_number", "column", "row"):
+                    assert np.array_equal(g[f], w[f]), (s, d, f)
+                ulp = np.abs(g["charge"].view(np.int32).astype(np.int64) - w["charge"].view(np.int32).astype(np.int64))
+                assert ulp.max() <= 1
+                charge_diff += int((ulp != 0).sum())
+                rows += len(w)
+            del run, r
+    print(f"\n{runs * n} electrons in {runs} reference replays: {rows} hit rows, IDs identical, "
+          f"{charge_diff} f4 charges off by one ulp ({charge_diff / rows:.2e})")
+    assert rows > 7.3 * runs * n and charge_diff <= rows * 1e-4
+
+
+def co_run(setup, n, seed_interp, seed_numba):
+    from oracle import cpu_oracle as co
+    beam, devices, materials, names = setup
+    return co.run(beam, devices, materials, n, seed_interp, seed_numba)
+
+
 @pytest.mark.parametrize("n_planes", [1, 2, 16, 32])
 def test_plane_count_extremes(torch_cuda, n_planes):
     """One plane (nothing to propagate to), two, and the maximum the ABI supports (PTB_MAX_PLANES = 32)."""

@@ -80,74 +80,132 @@ def _first_rows(hits):
     return start
 
 
-@pytest.mark.parametrize("name,seed", [("c1", 2024), ("c3", 2025), ("c4", 2026)])
-def test_distributions_match_oracle(name, seed):
-    n = int(os.environ.get("PTB_KS_N", 100_000))      # the suite runs 1e5; larger values for one-off checks
+def _plane_pool(job):
+    args, n, seed = job
+    rs = np.random.RandomState(seed)
+    got, need = [], n
+    while need > 0:
+        p = co.accept_pool(rs, args, 4_000_000)
+        got.append(p[:need])
+        need -= len(got[-1])
+    return np.concatenate(got)
+
+
+def _pool_table_parallel(beam, devices, materials, n, seed):
+    """_pool_table with one process per plane (the accept/reject pass keeps 0.8 % of its candidates: 1e6 values per plane
+    are minutes on one core).  The argument of plane d uses the mean loss of plane d-1 (main/hit.py:91), which for this
+    purpose is taken from a 2e5-value pilot of that plane."""
+    import multiprocessing as mp
+    D = len(devices)
+    means, args = [0.0], []
+    for d in range(D):
+        a = co.landau_args(devices[d]["thickness"], materials[d]["Z"], materials[d]["A"], materials[d]["rho"],
+                           beam["energy"] - means[-1])
+        args.append(a)
+        means.append(float(np.mean(_plane_pool((a, min(n, 20_000), seed + 1000 + d)))))
+    with mp.get_context("fork").Pool(min(D, os.cpu_count() or 1)) as pool:
+        rows = pool.map(_plane_pool, [(args[d], n, seed + d) for d in range(D)])
+    return np.stack(rows)
+
+
+def _north_star_report(name, n, seed):
+    """p-values of the north star's quantities (per-plane hit position, cluster size, energy deposit, scattering angle;
+    plus the event-level draws) for one configuration and one seed: CUDA production mode against the CPU oracle.
+
+    Every comparison looks at the randomness that is NEW at its plane, so that the comparisons are independent of one
+    another: the scattering angle enters as the kick a particle takes at the plane (angle after minus angle before; the
+    track position downstream is a deterministic function of the kicks upstream, main/hit.py:212-215, and is therefore
+    covered by them and by the hit positions), positions as one value per cluster (the rows of one cluster are not
+    independent samples)."""
     beam, devices, materials, names = H.setup(name, n)
     D = len(devices)
-    table = _pool_table(beam, devices, materials, n, seed + 7)
+    table = _pool_table_parallel(beam, devices, materials, n, seed + 7)
     run = co.run(beam, devices, materials, n, seed, seed + 1, table_override=table)
     sim = _sim((beam, devices, materials, names))
     res = sim.run(0, n, seed=seed + 2, write_tracks=True)
-    report = []
-
-    def check(label, p):
-        report.append((label, float(p)))
-
+    report = {}
     g = {k: res.tracks[k].cpu().numpy().reshape(n, D) for k in ("energy", "angle_x", "angle_y", "x", "y")}
     o = {k: run.tracks[i].reshape(n, D) for i, k in enumerate(("energy", "angle_x", "angle_y", "x", "y"))}
     g_el = res.tracks["eloss"].cpu().numpy().reshape(D, n)
     g_acc = res.tracks["accepted"].cpu().numpy().astype(bool)
+    ks = lambda a, b: float(stats.ks_2samp(a, b).pvalue)      # noqa: E731
+    # the source: position and angle of every particle but event 0 (Q3)
+    for k in ("x", "y", "angle_x", "angle_y"):
+        report[f"source.{k}"] = ks(g[k][1:, 0], o[k][1:, 0])
     for d in range(D):
-        for k in ("x", "y", "angle_x", "angle_y", "energy"):
-            check(f"{names[d]}.{k}", stats.ks_2samp(g[k][1:, d], o[k][1:, d]).pvalue)
-        a, b = g_el[d][g_el[d] > 0], run.eloss[d][run.eloss[d] > 0]
-        check(f"{names[d]}.eloss", stats.ks_2samp(a, b).pvalue)
-        # fraction of particles inside the acceptance (eloss zeroed otherwise), planes >= 1
+        nm = names[d]
         if d > 0:
-            cnt = np.array([[len(a), n - len(a)], [len(b), n - len(b)]])
+            for k in ("angle_x", "angle_y"):
+                gk, ok = g[k][1:, d] - g[k][1:, d - 1], o[k][1:, d] - o[k][1:, d - 1]
+                gk, ok = gk[gk != 0], ok[ok != 0]            # outside the acceptance window the kick is replaced by 0
+                if min(len(gk), len(ok)) > 50:
+                    report[f"{nm}.kick_{k[-1]}"] = ks(gk, ok)
+            a_in, b_in = int((g_el[d] > 0).sum()), int((run.eloss[d] > 0).sum())
+            cnt = np.array([[a_in, n - a_in], [b_in, n - b_in]])
             if cnt.min() > 5:
-                check(f"{names[d]}.in_acceptance", stats.chi2_contingency(cnt)[1])
+                report[f"{nm}.in_acceptance"] = float(stats.chi2_contingency(cnt)[1])
+        a, b = g_el[d][g_el[d] > 0], run.eloss[d][run.eloss[d] > 0]
+        if min(len(a), len(b)) > 50:
+            report[f"{nm}.energy_deposit"] = ks(a, b)
         gh, oh = res.hits_numpy(d), run.hits[d]
         if len(oh) > 50 and len(gh) > 50:
-            check(f"{names[d]}.charge", stats.ks_2samp(gh["charge"], oh["charge"]).pvalue)
+            report[f"{nm}.charge"] = ks(gh["charge"], oh["charge"])
             gs, os_ = _first_rows(gh), _first_rows(oh)
-            check(f"{names[d]}.cluster_col", stats.ks_2samp(gh["column"][gs], oh["column"][os_]).pvalue)
-            check(f"{names[d]}.cluster_row", stats.ks_2samp(gh["row"][gs], oh["row"][os_]).pvalue)
-            # cluster-size histogram (discrete): chi-square on counts, sizes >= 6 pooled
+            report[f"{nm}.hit_column"] = ks(gh["column"][gs], oh["column"][os_])
+            report[f"{nm}.hit_row"] = ks(gh["row"][gs], oh["row"][os_])
             gsz = np.diff(np.append(np.nonzero(gs)[0], len(gh)))
             osz = np.diff(np.append(np.nonzero(os_)[0], len(oh)))
-            hist = np.array([np.bincount(np.minimum(gsz, 6), minlength=7)[1:],
-                             np.bincount(np.minimum(osz, 6), minlength=7)[1:]])
+            hist = np.array([np.bincount(np.minimum(gsz, 8), minlength=9)[1:],
+                             np.bincount(np.minimum(osz, 8), minlength=9)[1:]])
             hist = hist[:, hist.min(axis=0) > 5]
             if hist.shape[1] > 1:
-                check(f"{names[d]}.cluster_size", stats.chi2_contingency(hist)[1])
-            # hits per digitised particle
+                report[f"{nm}.cluster_size"] = float(stats.chi2_contingency(hist)[1])
             nd_g = n if not devices[d]["trigger"] == "triggered" else int(g_acc.sum())
             nd_o = n if not devices[d]["trigger"] == "triggered" else int(run.variates.accepted.sum())
             cnt = np.array([[gs.sum(), nd_g - gs.sum()], [os_.sum(), nd_o - os_.sum()]])
-            check(f"{names[d]}.clusters_per_particle", stats.chi2_contingency(cnt)[1])
-    # trigger mask and time gaps
+            report[f"{nm}.clusters_per_particle"] = float(stats.chi2_contingency(cnt)[1])
     cnt = np.array([[g_acc.sum(), n - g_acc.sum()], [run.variates.accepted.sum(), n - run.variates.accepted.sum()]])
-    check("accepted_fraction", stats.chi2_contingency(cnt)[1])
-    g_t = res.tracks["time_stamp"].cpu().numpy().reshape(n, D)[:, 0]
-    o_t = run.tracks[6].reshape(n, D)[:, 0]
-    g_gap, o_gap = np.diff(g_t), np.diff(o_t)
+    report["accepted_fraction"] = float(stats.chi2_contingency(cnt)[1])
+    g_gap = np.diff(res.tracks["time_stamp"].cpu().numpy().reshape(n, D)[:, 0])
+    o_gap = np.diff(run.tracks[6].reshape(n, D)[:, 0])
     if beam["particle_rate"] < 1e7:
-        check("time_gap", stats.ks_2samp(g_gap, o_gap).pvalue)
+        report["time_gap"] = ks(g_gap, o_gap)
     else:   # few distinct values: compare the histograms
         m = int(max(g_gap.max(), o_gap.max())) + 1
         hist = np.array([np.bincount(g_gap, minlength=m), np.bincount(o_gap, minlength=m)])
         hist = hist[:, hist.min(axis=0) > 5]
-        check("time_gap", stats.chi2_contingency(hist)[1])
+        report["time_gap"] = float(stats.chi2_contingency(hist)[1])
     assert abs(g_gap.mean() / o_gap.mean() - 1) < 0.01
-    bad = [(k, p) for k, p in report if not (p > P_MIN)]
-    print("\n".join(f"{k:40s} p={p:.4f}" for k, p in report))
-    # with ~100 independent tests per configuration a couple below 0.01 are expected by chance alone; the gate
-    # is therefore the north star's p > 0.01 applied with a Bonferroni-Holm style allowance: no p below
-    # 0.01/len(report), and at most 3 % of the tests below 0.01
-    assert all(p > P_MIN / len(report) for _, p in report), bad
-    assert len(bad) <= max(1, int(0.03 * len(report))), bad
+    return report
+
+
+# the committed seed list: two independent seeds per configuration
+KS_SEEDS = {"c1": (2024, 3024), "c3": (2025, 3025), "c4": (2026, 3026)}
+
+
+@pytest.mark.parametrize("name", ["c1", "c3", "c4"])
+def test_distributions_match_oracle(name):
+    """North star, mode (b): two-sample KS / chi-square at p > 0.01 for every listed quantity, 1e6 electrons.
+
+    A correct implementation still sees p < 0.01 in 1 % of its comparisons (the p-value of a true null is uniform), and
+    there are ~60 of them per configuration, so "every p of one run above 0.01" would reject a correct kernel four times
+    out of ten.  The gate applies p > 0.01 per comparison in the only way that does not depend on luck: every
+    comparison must reach p > 0.01 with at least one of the two committed seeds (a true deviation fails with both; a
+    correct kernel fails both with probability 1e-4 per comparison), and no single p may lie below 0.01 / m (Holm's
+    bound for the m comparisons of a run: family-wise error 1 %)."""
+    n = int(os.environ.get("PTB_KS_N", 1_000_000))
+    reports = [_north_star_report(name, n, s) for s in KS_SEEDS[name]]
+    keys = sorted(set(reports[0]) & set(reports[1]))
+    print(f"\n{name}: {len(keys)} comparisons x 2 seeds at {n} electrons")
+    for k in keys:
+        print(f"{k:44s} p = {reports[0][k]:.4f}  {reports[1][k]:.4f}")
+    for s, rep in zip(KS_SEEDS[name], reports):
+        low = {k: p for k, p in rep.items() if not (p > P_MIN / len(rep))}
+        assert not low, (name, s, low)
+    both = {k: (reports[0][k], reports[1][k]) for k in keys if not (max(reports[0][k], reports[1][k]) > P_MIN)}
+    assert not both, (name, both)
+    once = sum(1 for rep in reports for p in rep.values() if not (p > P_MIN))
+    assert once <= 0.05 * 2 * len(keys) + 2, (name, once)       # and chance level overall (expected: 1 % of them)
 
 
 def test_source_draws_follow_their_exact_laws():
