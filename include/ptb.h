@@ -69,6 +69,8 @@ extern "C" {
                                     instead of being drawn, so only the seed-pixel fallback of calc_cluster_hits fires */
 #define PTB_RECYCLE_SLABS 16u    /* rows start at 0 of each slab: ignore bases_in->hits and write bases_out->hits = 0 */
 #define PTB_COMPACT 64u          /* with PTB_DIGITISE: write PtbRun.compact instead of PtbRun.slabs (always recycled) */
+#define PTB_CLASSIC_GATHER 128u  /* collect the rows with the separate gather pass even where the digitisation kernel could
+                                    put them in place itself (production mode, default outputs); same results, slower */
 
 /* beam block of setup.yml; lengths um, angles rad, energy MeV, rate Hz */
 typedef struct PtbBeam {
@@ -129,16 +131,17 @@ typedef struct PtbHitSlab {
 
 /*
  * Compressed-row form of the hit tables of particles [first, first+n) (PTB_COMPACT), device memory owned by the caller.
- * Plane d's rows sit at hits[sum(totals.hits[0..d-1]) ...], in the reference's order (particle, column, row).  Row i of
- * plane d belongs to the particle k whose running count range covers i:  sum(counts[d][0..k-1]) <= i < ... + counts[d][k];
- * its event number is  bases_in->event + 1 + (accepted particles among first .. first+k-1)  (main/device.py:159,164-165),
- * frame is 0.  66 instead of 118 bytes per electron on the default telescope: this is what travels over PCIe.
+ * Plane d's totals.hits[d] rows sit at hits[plane_first[d] ...], in the reference's order (particle, column, row); the
+ * plane's region ends at plane_first[d+1].  Row i of plane d belongs to the particle k whose running count range covers
+ * i:  sum(counts[d][0..k-1]) <= i < ... + counts[d][k];  its event number is  bases_in->event + 1 + (accepted particles
+ * among first .. first+k-1)  (main/device.py:159,164-165), frame is 0.  66 instead of 118 bytes per electron on the
+ * default telescope: this is what travels over PCIe.
  */
 typedef struct PtbCompactOut {
-    uint64_t *hits;     /* [capacity] column | row << 16 | (f32 charge bits) << 32 */
+    uint64_t *hits;     /* column | row << 16 | (f32 charge bits) << 32 */
     uint8_t  *counts;   /* [D][n] rows of particle k on plane d */
     uint32_t *accepted; /* [(n+31)/32] trigger mask, bit j of word g = particle first + 32 g + j */
-    uint64_t  capacity; /* rows over all planes */
+    uint64_t  plane_first[PTB_MAX_PLANES + 1]; /* first row of every plane's region in hits; [D] = rows of hits in all */
 } PtbCompactOut;
 
 /* running prefixes carried from one particle range to the next (device memory) */
@@ -176,7 +179,8 @@ typedef struct PtbRun {
     size_t             workspace_bytes;
     uint64_t           scratch_rows[PTB_MAX_PLANES]; /* rows of the workspace's scratch slab per plane; 0 = the default
                                                         rule.  On PTB_DEV_SCRATCH_OVERFLOW retry with totals.reserved */
-    PtbCompactOut      compact;    /* used with PTB_COMPACT; scratch_rows[d] = 0 then means the default rule on compact.capacity */
+    PtbCompactOut      compact;    /* used with PTB_COMPACT; scratch_rows[d] = 0 then means the default rule on the
+                                      rows of plane d's region */
 } PtbRun;
 
 typedef struct PtbContext *PtbHandle;

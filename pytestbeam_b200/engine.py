@@ -86,10 +86,8 @@ class RunResult:
 
     def compact_host(self) -> dict:
         """The PtbCompactOut on the host: per-plane uint64 rows, uint8 counts [D, n], uint32 trigger words."""
-        D, hits = len(self.totals["hits"]), self.totals["hits"]
-        flat = self.compact["hits"][:sum(hits)].cpu().numpy().view(np.uint64)
-        offs = np.concatenate([[0], np.cumsum(hits)]).astype(np.int64)
-        return {"hits": [flat[offs[d]:offs[d + 1]] for d in range(D)],
+        D, hits, pf = len(self.totals["hits"]), self.totals["hits"], self.compact["plane_first"]
+        return {"hits": [self.compact["hits"][pf[d]:pf[d] + hits[d]].cpu().numpy().view(np.uint64) for d in range(D)],
                 "counts": self.compact["counts"].cpu().numpy().reshape(D, self.n),
                 "accepted": self.compact["accepted"].cpu().numpy().view(np.uint32)}
 
@@ -166,9 +164,11 @@ class Simulator:
             slabs.append(s)
         return slabs
 
-    def alloc_compact(self, n, capacity):
-        """Device buffers of a PtbCompactOut for n particles and `capacity` rows over all planes."""
-        return {"hits": torch.empty(int(capacity), dtype=torch.int64, device=self.device),
+    def alloc_compact(self, n, capacities):
+        """Device buffers of a PtbCompactOut for n particles and the given rows per plane."""
+        first = np.concatenate([[0], np.cumsum([int(c) for c in capacities])]).astype(np.int64)
+        return {"plane_first": [int(v) for v in first],
+                "hits": torch.empty(int(first[-1]), dtype=torch.int64, device=self.device),
                 "counts": torch.empty(self.D * int(n), dtype=torch.uint8, device=self.device),
                 "accepted": torch.empty((int(n) + 31) // 32, dtype=torch.int32, device=self.device)}
 
@@ -232,8 +232,10 @@ class Simulator:
                                             s["charge64"].data_ptr() if "charge64" in s else None,
                                             int(s["event"].numel()))
         if compact is not None:
-            run.compact = N.PtbCompactOut(compact["hits"].data_ptr(), compact["counts"].data_ptr(),
-                                          compact["accepted"].data_ptr(), int(compact["hits"].numel()))
+            run.compact.hits, run.compact.counts = compact["hits"].data_ptr(), compact["counts"].data_ptr()
+            run.compact.accepted = compact["accepted"].data_ptr()
+            for d, v in enumerate(compact["plane_first"]):
+                run.compact.plane_first[d] = int(v)
         run.bases_in = bases_in.data_ptr() if bases_in is not None else None
         run.bases_out = bases_out.data_ptr() if bases_out is not None else None
         run.totals = totals.data_ptr()
@@ -256,7 +258,7 @@ class Simulator:
 
     def run(self, first, n, *, seed=0, injected=None, digitise=True, write_tracks=False, tracks_in=None,
             keep_charge64=False, capacities=None, bases_in=None, zero_radius=False, scratch_rows=None,
-            compact=False) -> RunResult:
+            compact=False, classic_gather=False) -> RunResult:
         """Simulate particles [first, first+n), synchronise and return trimmed device buffers.
 
         Retries with exact slab / scratch sizes when the device reports an overflow (its totals stay exact).
@@ -275,11 +277,13 @@ class Simulator:
             flags |= N.PTB_ZERO_RADIUS
         if compact:
             flags |= N.PTB_COMPACT
+        if classic_gather:
+            flags |= N.PTB_CLASSIC_GATHER
         if capacities is None:
             capacities = [4 * n + 4096] * self.D if digitise else [0] * self.D
         for attempt in range(8):
             slabs = self.alloc_slabs(capacities, keep_charge64) if (digitise and not compact) else None
-            cmp_out = self.alloc_compact(n, sum(int(c) for c in capacities)) if compact else None
+            cmp_out = self.alloc_compact(n, capacities) if compact else None
             if compact and scratch_rows is None:
                 scratch_rows = [N.default_scratch_rows(int(c)) for c in capacities]
             tracks = tracks_in if tracks_in is not None else (self.alloc_tracks(n) if write_tracks else None)

@@ -17,6 +17,7 @@ PTB_KEEP_CHARGE64 = 8
 PTB_RECYCLE_SLABS = 16
 PTB_ZERO_RADIUS = 32
 PTB_COMPACT = 64
+PTB_CLASSIC_GATHER = 128
 
 PTB_DEV_SCRATCH_OVERFLOW = 1
 PTB_DEV_SLAB_OVERFLOW = 2
@@ -63,7 +64,8 @@ class PtbHitSlab(C.Structure):
 
 
 class PtbCompactOut(C.Structure):
-    _fields_ = [("hits", C.c_void_p), ("counts", C.c_void_p), ("accepted", C.c_void_p), ("capacity", C.c_uint64)]
+    _fields_ = [("hits", C.c_void_p), ("counts", C.c_void_p), ("accepted", C.c_void_p),
+                ("plane_first", C.c_uint64 * (PTB_MAX_PLANES + 1))]
 
 
 class PtbBases(C.Structure):

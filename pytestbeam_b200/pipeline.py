@@ -68,12 +68,13 @@ class HostChunk:
 
 class ChunkPipeline:
     def __init__(self, sim: Simulator, chunk: int, *, n_buffers: int = 2, capacities=None, host: bool = False,
-                 seed: int = 0, scratch_rows=None, compact: bool | None = None):
+                 seed: int = 0, scratch_rows=None, compact: bool | None = None, classic_gather: bool = False):
         self.sim, self.chunk, self.seed = sim, int(chunk), int(seed)
         self.compact = bool(host) if compact is None else bool(compact)
         if self.compact and not host:
             raise PtbError("the compressed-row output exists for the trip to the host: use host=True")
-        self.flags = N.PTB_DIGITISE | N.PTB_RECYCLE_SLABS | (N.PTB_COMPACT if self.compact else 0)
+        self.flags = (N.PTB_DIGITISE | N.PTB_RECYCLE_SLABS | (N.PTB_COMPACT if self.compact else 0) |
+                      (N.PTB_CLASSIC_GATHER if classic_gather else 0))
         self.caps = list(capacities) if capacities is not None else sim.default_capacities(self.chunk)
         self.rows = list(scratch_rows) if scratch_rows is not None else sim.default_scratch_rows(self.chunk)
         dev, D = sim.device, sim.D
@@ -84,8 +85,9 @@ class ChunkPipeline:
                  "totals": torch.zeros(_TOTALS_WORDS, dtype=torch.int64, device=dev),
                  "done": torch.cuda.Event(), "copied": torch.cuda.Event()}
             if self.compact:
-                s["cmp"] = sim.alloc_compact(self.chunk, sum(self.caps))
-                s["h_cmp"] = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in s["cmp"].items()}
+                s["cmp"] = sim.alloc_compact(self.chunk, self.caps)
+                s["h_cmp"] = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in s["cmp"].items()
+                              if k != "plane_first"}
             else:
                 s["slabs"] = sim.alloc_slabs(self.caps)
                 if host:
@@ -188,8 +190,10 @@ class ChunkPipeline:
                     chunk = self._retry(i, first_i, n_i, ev_base, t_base, tot)
                 elif self.compact:
                     c, h = s["cmp"], s["h_cmp"]
-                    m = sum(tot["hits"])
-                    h["hits"][:m].copy_(c["hits"][:m], non_blocking=True)
+                    pf, m = c["plane_first"], sum(tot["hits"])
+                    for d in range(D):                       # every plane's rows from its own region
+                        h["hits"][pf[d]:pf[d] + tot["hits"][d]].copy_(c["hits"][pf[d]:pf[d] + tot["hits"][d]],
+                                                                      non_blocking=True)
                     h["counts"][:D * n_i].copy_(c["counts"][:D * n_i], non_blocking=True)
                     w = (n_i + 31) // 32
                     h["accepted"][:w].copy_(c["accepted"][:w], non_blocking=True)
@@ -197,9 +201,8 @@ class ChunkPipeline:
                     s["copied"].record(self.copy_stream)
                     if consume is not None:
                         flat = h["hits"].numpy().view(np.uint64)
-                        offs = np.concatenate([[0], np.cumsum(tot["hits"])]).astype(np.int64)
                         chunk = HostChunk(sim.lib, i, first_i, n_i, D, tot, ev_base, t_base, compact={
-                            "hits": [flat[offs[d]:offs[d + 1]] for d in range(D)],
+                            "hits": [flat[pf[d]:pf[d] + tot["hits"][d]] for d in range(D)],
                             "counts": h["counts"].numpy()[:D * n_i].reshape(D, n_i),
                             "accepted": h["accepted"].numpy().view(np.uint32)[:w]})
                 else:
