@@ -69,8 +69,6 @@ extern "C" {
                                     instead of being drawn, so only the seed-pixel fallback of calc_cluster_hits fires */
 #define PTB_RECYCLE_SLABS 16u    /* rows start at 0 of each slab: ignore bases_in->hits and write bases_out->hits = 0 */
 #define PTB_COMPACT 64u          /* with PTB_DIGITISE: write PtbRun.compact instead of PtbRun.slabs (always recycled) */
-#define PTB_CLASSIC_GATHER 128u  /* collect the rows with the separate gather pass even where the digitisation kernel could
-                                    put them in place itself (production mode, default outputs); same results, slower */
 
 /* beam block of setup.yml; lengths um, angles rad, energy MeV, rate Hz */
 typedef struct PtbBeam {

@@ -5,7 +5,7 @@
 //   k_tracks    one lane per particle, one warp per group of 32 consecutive particles: beam draw, plane-by-
 //               plane propagation, Highland kick, Landau loss, acceptance test.  Hands the per-plane
 //               (x, y, energy loss) of the group to k_digitise through a coalesced, L2-resident park.
-//   k_digitise  one warp per group, warp-cooperative: the 32 particles' pixel boxes are flattened into work
+//   k_digitise  a persistent grid whose warps take one group after the other, warp-cooperative: the 32 particles' pixel boxes are flattened into work
 //               lists that the lanes walk 32 items at a time (first the separable per-column / per-row
 //               profiles, then the pixels, one per lane), and hits are compacted in reference order (particle,
 //               column, row) with ballots.  Only the box pixels that can pass the ellipse test and lie on the
@@ -52,9 +52,6 @@ constexpr int      SMALL_POOL = 96;
 constexpr int      TRACK_BLOCK = 128;                   // k_tracks
 constexpr unsigned FULL = 0xffffffffu;
 constexpr unsigned long long NO_SEGMENT = ~0ull;      // table entry of a group whose scratch reservation did not fit
-constexpr uint32_t KFLAG_FUSED = 1u << 31;            // internal flag: k_digitise puts its own rows in their final place
-// status words of the ordered flush (one per counter column and group): flag bits + a 62-bit count
-constexpr unsigned long long ST_PREFIX = 1ull << 63, ST_AGGREGATE = 1ull << 62, ST_VALUE = ST_AGGREGATE - 1;
 constexpr int ALLOC_LINES = PTB_MAX_PLANES + 2;       // counters of Workspace::alloc, one per 128-byte line
 constexpr int ALLOC_DEFERRED = PTB_MAX_PLANES, ALLOC_TICKET = PTB_MAX_PLANES + 1;
 constexpr int      SCAN_SEGMENTS = 16;                  // every counter column is scanned by this many blocks
@@ -80,9 +77,7 @@ static unsigned long long g_launches = 0;
 // ---------------------------------------------------------------------------------------------------
 struct Workspace {
     unsigned long long *alloc;      // [ALLOC_LINES * 16] one counter per 128-byte line: scratch rows handed out per plane;
-                                    // then the deferred (group, plane) items and the block tickets of the ordered flush
-    unsigned long long *status;     // [(D+1)][n_groups] ordered flush: per-group rows of every plane and accepted particles,
-                                    // first as the group's own count (aggregate), then as inclusive prefix
+                                    // then the deferred (group, plane) items and the group tickets of k_digitise
     unsigned long long *deferred;   // [n_groups * D] (group << 8 | plane) of the pairs k_digitise left to k_digitise_big
     unsigned long long *table;      // [(2D+5)][n_groups]: hits[D], accepted, tsum, pairs, inside, pixels, base[D]
     unsigned long long *prefix;     // [(D+2)][n_groups]
@@ -104,9 +99,6 @@ struct KParams {
     Workspace          ws;
     PtbTotals         *totals;
     PtbCompactOut      cmp;   // PTB_COMPACT
-    // ordered flush (KFLAG_FUSED): where the rows finally go
-    const PtbBases    *bases_in;
-    PtbHitSlab         slabs[PTB_MAX_PLANES];
 };
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -124,8 +116,6 @@ static size_t carve_workspace(int D, unsigned long long n, const unsigned long l
     char *p;
     p = take(sizeof(unsigned long long) * ALLOC_LINES * 16);
     if (ws) ws->alloc = (unsigned long long *)p;
-    p = take((flags & PTB_DIGITISE) ? sizeof(unsigned long long) * (size_t)(D + 1) * ng : 0);
-    if (ws) ws->status = (unsigned long long *)p;
     p = take((flags & PTB_DIGITISE) ? sizeof(unsigned long long) * (size_t)D * ng : 0);
     if (ws) ws->deferred = (unsigned long long *)p;
     p = take(sizeof(unsigned long long) * (size_t)(2 * D + 5) * ng);
@@ -172,7 +162,6 @@ struct WarpShared {
     uint32_t seedcr[32];
     uint8_t  evoff[32], accb[32];
     uint8_t  cnt[32];                              // PTB_COMPACT: rows of every particle on the current plane (saturating)
-    uint32_t pending;                              // KFLAG_FUSED: the group this warp digitised last and has not flushed yet
     unsigned long long census;                     // census of the group (packed), kept by lane 0
 };
 
@@ -192,18 +181,6 @@ __device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-// status words travel between thread blocks through L2; the word itself is the whole message (flag and count together)
-__device__ __forceinline__ void st_relaxed_gpu(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_relaxed_gpu(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 
 __device__ __forceinline__ unsigned lanemask_lt()
 {
@@ -727,100 +704,10 @@ __device__ __forceinline__ void digitise_group(const ConfigK &cfg, const KParams
     }
 }
 
-// Ordered flush of one finished group (KFLAG_FUSED): its rows go from the scratch segments to their final, particle-
-// ordered place.  Lane c owns counter column c (rows of plane c; column D: accepted particles): it walks back over the
-// groups before this one until it meets one whose inclusive prefix is known (decoupled look-back; the columns advance
-// independently, one per lane) and publishes the group's own inclusive prefix.  Called one group late (the warp has
-// digitised its next group in the meantime), so that the groups before it have published at least their counts by
-// now and nobody waits.
-template <int MODE>
-__device__ __forceinline__ void flush_group(const ConfigK &cfg, const KParams &P, const unsigned long long group,
-                                            const int lane)
-{
-    constexpr bool compact = MODE == 2;
-    const int      D = cfg.n_planes;
-    unsigned long long n_l = 0, src_l = 0, dst_l = 0, excl = 0;
-    const unsigned     accm = P.ws.accmask[group];
-    if (lane < D) {
-        n_l = P.ws.table[(unsigned long long)lane * P.n_groups + group];
-        src_l = P.ws.table[(unsigned long long)(D + 5 + lane) * P.n_groups + group];
-    }
-    if (lane <= D) {
-        const unsigned long long agg = lane < D ? n_l : (unsigned long long)__popc(accm);
-        unsigned long long      *st = P.ws.status + (unsigned long long)lane * P.n_groups;
-#ifndef PTB_FUSED_NO_LOOKBACK
-        if (group != 0) {
-            for (unsigned long long g = group - 1;;) {
-                const unsigned long long v = ld_relaxed_gpu(st + g);
-                if (v & ST_PREFIX) {
-                    excl += v & ST_VALUE;
-                    break;
-                }
-                if (v & ST_AGGREGATE) {   // that group has counted but not resolved its own prefix yet: take its count, go on
-                    excl += v & ST_VALUE;
-                    if (g == 0) break;    // nothing before the first group
-                    --g;
-                } else {
-                    __nanosleep(64);
-                }
-            }
-        }
-#endif
-        st_relaxed_gpu(st + group, ST_PREFIX | (excl + agg));
-    }
-    __syncwarp();
-    if (lane < D) {
-        const bool keep_rows = !compact && !(P.flags & PTB_RECYCLE_SLABS) && P.bases_in != nullptr;
-        dst_l = (keep_rows ? P.bases_in->hits[lane] : 0ull) + excl;
-        const unsigned long long room_l = compact ? P.cmp.plane_first[lane + 1] - P.cmp.plane_first[lane]
-                                                  : P.slabs[lane].capacity;
-        if (n_l != 0 && (dst_l + n_l > room_l || src_l == NO_SEGMENT)) {   // totals stay exact; the host retries
-            atomicOr(&P.totals->error, dst_l + n_l > room_l ? PTB_DEV_SLAB_OVERFLOW : PTB_DEV_SCRATCH_OVERFLOW);
-            n_l = 0;
-        }
-    }
-    const long long ev_base = (P.bases_in ? P.bases_in->event : 0) + (long long)__shfl_sync(FULL, excl, D) + 1;
-    if (compact && lane == 0) P.cmp.accepted[group] = accm;
-    // the segments of all planes as one work list, 32 rows per step (as k_gather does for the unfused path)
-    int cum = (int)n_l;
-#pragma unroll
-    for (int sft = 1; sft < 32; sft <<= 1) {
-        int o = __shfl_up_sync(FULL, cum, sft);
-        if (lane >= sft) cum += o;
-    }
-#ifdef PTB_FUSED_NO_COPY
-    const int total = 0;
-#else
-    const int total = __shfl_sync(FULL, cum, 31);
-#endif
-    for (int w0 = 0; w0 < total; w0 += 32) {
-        const int w = w0 + lane;
-        int       d = 0;
-        for (int p = 0; p < D; ++p) d += (__shfl_sync(FULL, cum, p) <= w) ? 1 : 0;   // plane of row w
-        d = min(d, D - 1);
-        const int                before = __shfl_sync(FULL, cum, max(d - 1, 0));      // all lanes take part
-        const unsigned long long src = __shfl_sync(FULL, src_l, d), dst = __shfl_sync(FULL, dst_l, d);
-        if (w < total) {
-            const unsigned long long i = (unsigned long long)(w - (d ? before : 0));
-            const uint2              hit = P.ws.s_hit[d][src + i];
-            if (compact) {
-                P.cmp.hits[P.cmp.plane_first[d] + dst + i] = (unsigned long long)hit.x | ((unsigned long long)hit.y << 32);
-            } else {
-                const PtbHitSlab &sl = P.slabs[d];
-                sl.event[dst + i] = ev_base + (long long)P.ws.s_ev[d][src + i];
-                sl.col[dst + i] = (uint16_t)(hit.x & 0xffffu);
-                sl.row[dst + i] = (uint16_t)(hit.x >> 16);
-                sl.charge[dst + i] = __uint_as_float(hit.y);
-            }
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------
-// k_digitise.  Unfused: one warp per group, one launch of ceil(n_groups / warps per block) blocks; the rows stay in
-// the scratch segments for k_gather.  Fused (KFLAG_FUSED): a persistent grid, every warp takes group after group by
-// ticket, publishes each group's counts as soon as it has digitised it and flushes it one group later (flush_group).
-// Tickets are handed out in running order, so whoever a flush waits for is running or has finished.
+// k_digitise: a persistent grid (one wave of blocks); every warp takes group after group by ticket, so that the warps
+// of an SM drift apart instead of marching through the phases in step and the last wave has no ragged tail (1.3 %
+// against one block per four groups).  The rows stay in the scratch segments for k_gather.
 // ---------------------------------------------------------------------------------------------------
 template <class Src, int PC, int MODE>
 __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __grid_constant__ ConfigK cfg,
@@ -834,33 +721,13 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
     WarpShared      &W = *reinterpret_cast<WarpShared *>(wbase);
     double          *pool_g = reinterpret_cast<double *>(wbase + sizeof(WarpShared));
     double          *pool_e = pool_g + PC;
-    const bool fused = (P.flags & KFLAG_FUSED) != 0;
-    const int  D = cfg.n_planes;
-    if (lane == 0) W.pending = 0xffffffffu;
-    unsigned long long group = (unsigned long long)blockIdx.x * WARPS_PER_BLOCK + wib;   // unfused: the one group of this warp
     for (;;) {
-        if (fused) {
-            if (lane == 0) group = atomicAdd(&P.ws.alloc[ALLOC_TICKET * 16], 1ull);
-            group = __shfl_sync(FULL, group, 0);
-        }
-        const bool have = group < P.n_groups;   // warp-uniform; no block-wide barrier is used anywhere
-        if (have) digitise_group<Src, PC, MODE>(cfg, P, src, group, W, pool_g, pool_e, lane);
-        if (!fused) return;
-        // the group's counts, visible to the flushes of the groups behind it from now on
-        if (have && lane <= D) {
-            const unsigned long long agg = lane < D ? P.ws.table[(unsigned long long)lane * P.n_groups + group]
-                                                    : (unsigned long long)__popc(P.ws.accmask[group]);
-            st_relaxed_gpu(P.ws.status + (unsigned long long)lane * P.n_groups + group, ST_AGGREGATE | agg);
-        }
-        // the group digitised before this one is flushed now, one group late (after the last group: at once)
-        const unsigned pending = W.pending;
+        unsigned long long group = 0;
+        if (lane == 0) group = atomicAdd(&P.ws.alloc[ALLOC_TICKET * 16], 1ull);
+        group = __shfl_sync(FULL, group, 0);
+        if (group >= P.n_groups) return;   // whole warps leave; no block-wide barrier is used anywhere
+        digitise_group<Src, PC, MODE>(cfg, P, src, group, W, pool_g, pool_e, lane);
         __syncwarp();
-#ifndef PTB_FUSED_NO_FLUSH
-        if (pending != 0xffffffffu) flush_group<MODE>(cfg, P, pending, lane);
-#endif
-        if (lane == 0) W.pending = have ? (unsigned)group : 0xffffffffu;
-        __syncwarp();
-        if (!have) return;
     }
 }
 
@@ -1799,20 +1666,6 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
     cudaError_t e;
     e = cudaMemsetAsync(P.ws.alloc, 0, sizeof(unsigned long long) * ALLOC_LINES * 16, st);
     if (e != cudaSuccess) return fail_cuda(h, e, "memset alloc");
-    // Ordered flush inside k_digitise (no k_gather pass) whenever every (group, plane) pair is certain to be served by
-    // k_digitise itself and nothing else needs the gather: production variates, tracks generated here, no f8 charges, no
-    // track table, no geometry whose clusters can outgrow the profile pool.  PTB_CLASSIC_GATHER switches it off.
-    const bool fused = (flags & PTB_DIGITISE) && !run->injected && !h->may_be_big && P.n_groups < 0xffffffffull &&
-                       !(flags & (PTB_TRACKS_FROM_TABLE | PTB_WRITE_TRACKS | PTB_KEEP_CHARGE64 | PTB_CLASSIC_GATHER));
-    if (fused) {
-        e = cudaMemsetAsync(P.ws.status, 0, sizeof(unsigned long long) * (size_t)(D + 1) * P.n_groups, st);
-        if (e != cudaSuccess) return fail_cuda(h, e, "memset status");
-        P.flags |= KFLAG_FUSED;
-        P.bases_in = run->bases_in;
-        for (int d = 0; d < D; ++d) P.slabs[d] = run->slabs[d];
-    }
-    e = cudaMemsetAsync(run->totals, 0, sizeof(PtbTotals), st);
-    if (e != cudaSuccess) return fail_cuda(h, e, "memset totals");
 
     const bool keep64 = (flags & PTB_KEEP_CHARGE64) != 0;
     cudaEvent_t *tp = timing_pair(h);
@@ -1829,8 +1682,8 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
     }
     if (tp) cudaEventRecord(tp[1], st);
     if (flags & PTB_DIGITISE) {
-        unsigned blocks = (unsigned)((P.n_groups + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-        if (fused) blocks = std::min(blocks, (unsigned)(h->sm_count * DIGI_MIN_BLOCKS));   // persistent: one wave of blocks
+        const unsigned blocks = (unsigned)std::min<unsigned long long>((P.n_groups + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK,
+                                                                       (unsigned long long)h->sm_count * DIGI_MIN_BLOCKS);   // one wave
         const bool     small = c.pool_entries == SMALL_POOL;
         const int mode = compact ? 2 : keep64 ? 1 : 0;
         if (run->injected) {
@@ -1881,7 +1734,7 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
     if (e != cudaSuccess) return fail_cuda(h, e, "k_scan launch");
     if (tp) cudaEventRecord(tp[3], st);
 
-    if (((flags & PTB_DIGITISE) && !fused) || (flags & PTB_WRITE_TRACKS)) {
+    if ((flags & PTB_DIGITISE) || (flags & PTB_WRITE_TRACKS)) {
         GatherParams G;
         memset(&G, 0, sizeof(G));
         G.D = D;

@@ -258,7 +258,7 @@ class Simulator:
 
     def run(self, first, n, *, seed=0, injected=None, digitise=True, write_tracks=False, tracks_in=None,
             keep_charge64=False, capacities=None, bases_in=None, zero_radius=False, scratch_rows=None,
-            compact=False, classic_gather=False) -> RunResult:
+            compact=False) -> RunResult:
         """Simulate particles [first, first+n), synchronise and return trimmed device buffers.
 
         Retries with exact slab / scratch sizes when the device reports an overflow (its totals stay exact).
@@ -277,8 +277,6 @@ class Simulator:
             flags |= N.PTB_ZERO_RADIUS
         if compact:
             flags |= N.PTB_COMPACT
-        if classic_gather:
-            flags |= N.PTB_CLASSIC_GATHER
         if capacities is None:
             capacities = [4 * n + 4096] * self.D if digitise else [0] * self.D
         for attempt in range(8):

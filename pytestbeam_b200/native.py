@@ -17,7 +17,6 @@ PTB_KEEP_CHARGE64 = 8
 PTB_RECYCLE_SLABS = 16
 PTB_ZERO_RADIUS = 32
 PTB_COMPACT = 64
-PTB_CLASSIC_GATHER = 128
 
 PTB_DEV_SCRATCH_OVERFLOW = 1
 PTB_DEV_SLAB_OVERFLOW = 2

@@ -68,13 +68,12 @@ class HostChunk:
 
 class ChunkPipeline:
     def __init__(self, sim: Simulator, chunk: int, *, n_buffers: int = 2, capacities=None, host: bool = False,
-                 seed: int = 0, scratch_rows=None, compact: bool | None = None, classic_gather: bool = False):
+                 seed: int = 0, scratch_rows=None, compact: bool | None = None):
         self.sim, self.chunk, self.seed = sim, int(chunk), int(seed)
         self.compact = bool(host) if compact is None else bool(compact)
         if self.compact and not host:
             raise PtbError("the compressed-row output exists for the trip to the host: use host=True")
-        self.flags = (N.PTB_DIGITISE | N.PTB_RECYCLE_SLABS | (N.PTB_COMPACT if self.compact else 0) |
-                      (N.PTB_CLASSIC_GATHER if classic_gather else 0))
+        self.flags = N.PTB_DIGITISE | N.PTB_RECYCLE_SLABS | (N.PTB_COMPACT if self.compact else 0)
         self.caps = list(capacities) if capacities is not None else sim.default_capacities(self.chunk)
         self.rows = list(scratch_rows) if scratch_rows is not None else sim.default_scratch_rows(self.chunk)
         dev, D = sim.device, sim.D

@@ -292,57 +292,3 @@ def test_entry_point_streams_files_equal_to_one_call(tmp_path):
     assert np.array_equal(trk["time_stamp"], one.tracks["time_stamp"].cpu().numpy().astype(np.uint16))
     head = tables.head(1000)
     assert np.array_equal(head[3], one.tracks["x"].cpu().numpy()[:1000 * sim.D]) and head[7].shape == (sim.D, 1000)
-
-
-@pytest.mark.parametrize("name,first,n", [("c1", 0, 200_003), ("c3", 123, 150_000), ("c4", 7_000_000_001, 180_000),
-                                          ("c1", 3, 1), ("c1", 0, 33), ("c1", 64, 129)])
-def test_ordered_flush_equals_the_gather_pass(name, first, n):
-    """Production mode puts the rows in place inside k_digitise (decoupled look-back over the groups' counts); the
-    separate gather pass (PTB_CLASSIC_GATHER) must give the very same tables, totals and bases -- slabs and compressed
-    rows, first call and chained call with non-zero bases."""
-    sim = _sim(H.setup(name, n))
-    for compact in (False, True):
-        a = sim.run(first, n, seed=31, compact=compact, classic_gather=True)
-        b = sim.run(first, n, seed=31, compact=compact)
-        assert a.totals == b.totals
-        assert np.array_equal(a.bases_out.cpu().numpy(), b.bases_out.cpu().numpy())
-        for d in range(sim.D):
-            assert a.hits_numpy(d).tobytes() == b.hits_numpy(d).tobytes(), (compact, d)
-        # chained: the next range starts from the bases of this one
-        a2 = sim.run(first + n, n, seed=31, compact=compact, bases_in=a.bases_out, classic_gather=True)
-        b2 = sim.run(first + n, n, seed=31, compact=compact, bases_in=b.bases_out)
-        for d in range(sim.D):
-            assert a2.hits_numpy(d).tobytes() == b2.hits_numpy(d).tobytes(), (compact, d)
-            if len(a2.hits_numpy(d)):
-                assert a2.hits_numpy(d)["event_number"][0] > a.totals["accepted"] - 40
-
-
-def test_ordered_flush_keeps_rows_of_earlier_calls_in_the_slab():
-    """Without PTB_RECYCLE_SLABS the rows of consecutive calls pile up in one slab (bases_in->hits): fused and gather
-    path must leave the same slab behind."""
-    import torch
-    from pytestbeam_b200 import native as N
-    from pytestbeam_b200.engine import _TOTALS_WORDS, Simulator
-    n = 50_000
-    sim = _sim(H.setup("c1", n))
-    out = []
-    for extra in (0, N.PTB_CLASSIC_GATHER):
-        caps = [4 * n] * sim.D
-        slabs = sim.alloc_slabs(caps)
-        flags = N.PTB_DIGITISE | extra
-        totals = torch.zeros(_TOTALS_WORDS, dtype=torch.int64, device=sim.device)
-        ws = torch.empty(sim.workspace_bytes(n, caps, flags), dtype=torch.uint8, device=sim.device)
-        bases = sim.new_bases()
-        for i in range(3):
-            sim.launch(i * n, n, seed=8, flags=flags, slabs=slabs, bases_in=bases, bases_out=bases, totals=totals, workspace=ws)
-        torch.cuda.synchronize()
-        b = bases.cpu().numpy()
-        assert Simulator.decode_totals(totals, sim.D)["error"] == 0
-        out.append((b.copy(), [{k: v[:int(b[2 + d])].cpu().numpy() for k, v in slabs[d].items()} for d in range(sim.D)]))
-    assert np.array_equal(out[0][0], out[1][0])
-    for d in range(sim.D):
-        for k in ("event", "col", "row", "charge"):
-            assert np.array_equal(out[0][1][d][k], out[1][1][d][k]), (d, k)
-    whole = sim.run(0, 3 * n, seed=8, classic_gather=True)
-    for d in range(sim.D):
-        assert np.array_equal(out[0][1][d]["event"], whole.slabs[d]["event"].cpu().numpy())
