@@ -13,12 +13,20 @@ import sys
 import tempfile
 
 
+def transparent_lines():
+    """Source lines whose only content is the call of an inlined group body: instructions are attributed to the line
+    inside that body (the next frame of the inline chain), not to the call."""
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "pytestbeam_b200", "csrc", "ptb_kernels.cu")
+    return {i + 1 for i, l in enumerate(open(src).read().split("\n")) if "digitise_group<Src, PC, MODE>(cfg" in l}
+
+
 def line_map(so, kernel_pat):
     tmp = tempfile.mkdtemp()
     subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL)
     cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
     txt = subprocess.run(["nvdisasm", "-gi", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
-    out, cur, inside, stack = {}, None, False, ""
+    skip = transparent_lines()
+    out, cur, inside, chain, fresh = {}, None, False, [], True
     for ln in txt.splitlines():
         if ln.startswith("\t.section\t.text."):
             inside = re.search(kernel_pat, ln) is not None
@@ -29,11 +37,18 @@ def line_map(so, kernel_pat):
             continue
         m = re.search(r'//## File "([^"]+)", line (\d+)(.*)', ln)
         if m:
-            cur = (os.path.basename(m.group(1)), int(m.group(2)), m.group(3).strip())
+            if fresh:
+                chain, fresh = [], False
+            chain.append((os.path.basename(m.group(1)), int(m.group(2)), m.group(3).strip()))
+            # the chain runs from the innermost frame to the outermost; the outermost wins unless it is a transparent call
+            cur = chain[-1]
+            if cur[0] == "ptb_kernels.cu" and cur[1] in skip and len(chain) > 1:
+                cur = chain[-2]
             continue
         m = re.match(r"\s+/\*([0-9a-f]{4,6})\*/\s+(.*)", ln)
         if m:
             out[int(m.group(1), 16)] = cur
+            fresh = True
     return out
 
 
@@ -41,7 +56,9 @@ def main():
     src_csv, so, pat = sys.argv[1:4]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
     lm = line_map(so, pat)
-    rows = list(csv.reader(open(src_csv)))
+    lines = open(src_csv).read().split("\n")
+    starts = [i for i, l in enumerate(lines) if l.startswith('"Kernel Name"')] + [len(lines)]
+    rows = list(csv.reader(lines[starts[0]:starts[1]]))
     hdr = rows[1]
     ia, ii, isamp = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("# Samples")
     ino = hdr.index("stall_no_inst")

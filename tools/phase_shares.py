@@ -15,11 +15,11 @@ def find(txt):
     for i, l in enumerate(src):
         if txt in l: return i + 1
 # (code inlined from describe() / profile_entry() is attributed to its call site in the kernel)
-marks = [('prolog', find('k_digitise(const __grid_constant__')), ('fetch', find('cp_async_wait_all();   //')),
+marks = [('prolog', find('__device__ __forceinline__ void digitise_group')), ('fetch', find('cp_async_wait_all();   //')),
          ('descriptors', find('// ---- cluster descriptors')), ('census+reserve', find('{   // census, one packed word')),
          ('rounds setup', find('// inclusive prefixes of the profile entries')), ('phase A', find('// ---- phase A')),
          ('phase B', find('// ---- phase B')), ('emit', find('// kept pixels of my particle in this step')),
-         ('plane end', find('if (o_end >= 32) break;')), ('epilog', find('// ---- per-group counters for k_scan'))]
+         ('plane end', find('if (o_end >= 32) break;')), ('epilog', find('// ---- per-group counters for k_scan')), ('ticket loop', find('k_digitise(const __grid_constant__'))]
 marks.sort(key=lambda m: m[1])
 lines = open(src_csv).read().split('\n')
 starts = [i for i, l in enumerate(lines) if l.startswith('"Kernel Name"')] + [len(lines)]
