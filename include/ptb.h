@@ -57,8 +57,9 @@ extern "C" {
 #define PTB_DEV_SCRATCH_OVERFLOW 1u /* the workspace's scratch rows of a plane ran out; PtbTotals.reserved is exact */
 #define PTB_DEV_SLAB_OVERFLOW 2u  /* a hit slab's capacity was exceeded; totals still hold the exact counts */
 #define PTB_DEV_BOX_TOO_LARGE 4u  /* a cluster bounding box exceeded 2^20 pixels */
-#define PTB_DEV_COUNT_OVERFLOW 8u /* PTB_COMPACT: one particle left more than 255 rows on a plane (the u8 count
-                                     saturated); rerun the range without PTB_COMPACT */
+#define PTB_DEV_COUNT_OVERFLOW 8u /* PTB_COMPACT: one particle left more than 255 rows on a plane (the count saturated),
+                                     or PTB_COMPACT_NARROW ran out of escape entries; rerun the range without
+                                     PTB_COMPACT */
 
 /* flags of PtbRun.flags */
 #define PTB_DIGITISE 1u          /* run the cluster digitisation and fill the hit slabs */
@@ -69,6 +70,7 @@ extern "C" {
                                     instead of being drawn, so only the seed-pixel fallback of calc_cluster_hits fires */
 #define PTB_RECYCLE_SLABS 16u    /* rows start at 0 of each slab: ignore bases_in->hits and write bases_out->hits = 0 */
 #define PTB_COMPACT 64u          /* with PTB_DIGITISE: write PtbRun.compact instead of PtbRun.slabs (always recycled) */
+#define PTB_COMPACT_NARROW 128u  /* with PTB_COMPACT: 7-byte rows in three arrays and 4-bit counts (PtbCompactOut) */
 
 /* beam block of setup.yml; lengths um, angles rad, energy MeV, rate Hz */
 typedef struct PtbBeam {
@@ -133,13 +135,26 @@ typedef struct PtbHitSlab {
  * plane's region ends at plane_first[d+1].  Row i of plane d belongs to the particle k whose running count range covers
  * i:  sum(counts[d][0..k-1]) <= i < ... + counts[d][k];  its event number is  bases_in->event + 1 + (accepted particles
  * among first .. first+k-1)  (main/device.py:159,164-165), frame is 0.  66 instead of 118 bytes per electron on the
- * default telescope: this is what travels over PCIe.
+ * default telescope.
+ *
+ * PTB_COMPACT_NARROW (matrices of at most 4095 x 4095 pixels): the rows of all planes lie back to back -- plane d's
+ * rows start at row  totals.hits[0] + ... + totals.hits[d-1]  of the three row arrays, whose common capacity is
+ * plane_first[n_planes] -- as  charge[i]  (f32),  pos_lo[i] | pos_hi[i] << 16 = column | row << 12;  counts holds 4 bits
+ * per (plane, particle): the count of particle k on plane d is nibble (k & 1) of counts[d * ((n + 1) / 2) + k / 2].
+ * A nibble of 15 means "15 or more": the exact count (up to 255) then stands in one of the totals.escapes entries of
+ * the escapes array, in no particular order, as  count << 48 | plane << 40 | (k - first).
+ * 55 bytes per electron on the default telescope: this is what travels over PCIe.
  */
 typedef struct PtbCompactOut {
-    uint64_t *hits;     /* column | row << 16 | (f32 charge bits) << 32 */
-    uint8_t  *counts;   /* [D][n] rows of particle k on plane d */
+    uint64_t *hits;     /* column | row << 16 | (f32 charge bits) << 32; unused with PTB_COMPACT_NARROW */
+    uint8_t  *counts;   /* [D][n] rows of particle k on plane d; [D][(n+1)/2] nibble pairs with PTB_COMPACT_NARROW */
     uint32_t *accepted; /* [(n+31)/32] trigger mask, bit j of word g = particle first + 32 g + j */
     uint64_t  plane_first[PTB_MAX_PLANES + 1]; /* first row of every plane's region in hits; [D] = rows of hits in all */
+    float    *charge;   /* PTB_COMPACT_NARROW: the three row arrays, plane_first[D] rows each */
+    uint16_t *pos_lo;
+    uint8_t  *pos_hi;
+    uint64_t *escapes;  /* PTB_COMPACT_NARROW: counts of 15 and more (see above), escape_capacity entries */
+    uint64_t  escape_capacity;
 } PtbCompactOut;
 
 /* running prefixes carried from one particle range to the next (device memory) */
@@ -155,7 +170,9 @@ typedef struct PtbTotals {
     uint64_t accepted;
     int64_t  time_sum;
     uint64_t pairs, inside, pixels; /* census: digitised (particle,plane) pairs, seed-in-matrix pairs, pixel evaluations */
-    uint32_t error, _pad;
+    uint32_t error;
+    uint32_t escapes;  /* PTB_COMPACT_NARROW: entries written to PtbCompactOut.escapes (more than its capacity: the
+                          rest was dropped and PTB_DEV_COUNT_OVERFLOW is set) */
     uint64_t reserved[PTB_MAX_PLANES]; /* scratch rows the call needs per plane (>= hits: every 32-particle group
                                           reserves room for all pixels that can still become hits) */
 } PtbTotals;
@@ -223,6 +240,11 @@ int ptb_pack_hits(const PtbHitSlab *slab, uint64_t n, void *out_dev, void *strea
  */
 int64_t ptb_expand_hits(const uint64_t *hits, const uint8_t *counts, const uint32_t *accepted, uint64_t n,
                         int64_t event_base, uint64_t n_rows_expected, void *out, int32_t threads);
+/* the same for plane `plane` of the PTB_COMPACT_NARROW form: the plane's slices of the three row arrays, its
+ * [(n+1)/2] nibble pairs, and the call's escape entries (all planes; the entries of other planes are skipped) */
+int64_t ptb_expand_hits_narrow(const float *charge, const uint16_t *pos_lo, const uint8_t *pos_hi, const uint8_t *counts4,
+                               const uint64_t *escapes, uint64_t n_escapes, int32_t plane, const uint32_t *accepted,
+                               uint64_t n, int64_t event_base, uint64_t n_rows_expected, void *out, int32_t threads);
 
 /*
  * Checksums of rows [0, n) of a hit table, added (modulo 2^64) to out_dev[0..6]:

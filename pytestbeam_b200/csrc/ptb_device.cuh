@@ -62,6 +62,7 @@ struct ConfigK {
     double  diff2, qe, c3mu, t90, cden;
     double  sigma0;                      // cloud width for a vanishing deposit
     double  rcp_3p6, rcp_cden;           // RN(1/3.6), RN(1/cden), for div_rcp
+    double  exp2_tab[64];                // RN(2^(j/64)), for exp_nonpos (copied to shared memory by the digitisation kernels)
     PlaneK  pl[PTB_MAX_PLANES];
 };
 
@@ -421,12 +422,56 @@ __device__ __forceinline__ double highland_theta0_dev(double energy, double hl_c
     return hl_c * num * rsqrt(num * den);
 }
 
+// 1 / x for a positive x of ordinary magnitude: the special-function-unit seed and the library's own refinement
+// (a cubic and a quadratic Newton step), without its detour for denormal / huge arguments.  A zero x gives NaN where
+// the division gives inf; the callers only ever compare the results, and both fail every comparison.
+__device__ __forceinline__ double rcp_pos(double x)
+{
+#ifdef PTB_LIBRARY_MATH
+    return 1.0 / x;
+#else
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    e = fma(e, e, e);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+#endif
+}
+
+__device__ __forceinline__ float ex2_sfu(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // width of the collected charge cloud in um, main/device.py:186-202.  np.cbrt under Numba is pow(x, 1/3).
 // pow(x, 1.0/3.0) for x > 0, i.e. with the exponent rounded to double as the reference evaluates it:
 // x^(1/3 + delta) = cbrt(x) * (1 + delta ln x), delta = double(1/3) - 1/3 = -1.85e-17 (the correction is a fraction
 // of an ulp, so a float logarithm is ample).  ~6x fewer instructions than the generic pow and no far call.
 __device__ __forceinline__ double pow_one_third(double x)
 {
+#ifndef PTB_LIBRARY_MATH
+    // Arguments here are 1e-19 .. 1e-13 (m^3): inside the float range, so the cube root's seed is 2^(lg2(x)/3) on the
+    // special-function unit (~2^-21 relative) and one Halley step in double brings it to the last bit or two -- the
+    // library routine's own scheme without its exponent split, and the logarithm serves the exponent correction too.
+    if (x > 1e-30 && x < 1e30) {
+        const float  lg = lg2_sfu((float)x);
+        const double y0 = (double)ex2_sfu(lg * 0.333333343f);
+        const double y2 = y0 * y0;
+        const double num = fma(-y0, y2, x);          // x - y0^3
+        const double den = fma(y0, y2 + y2, x);      // x + 2 y0^3
+        double       r;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+        double e = fma(-den, r, 1.0);
+        e = fma(e, e, e);
+        r = fma(r, e, r);
+        const double c = fma(y0, r * num, y0);       // y0 + y0 (x - y0^3) / (x + 2 y0^3)
+        return fma(c, -1.850371707708594e-17 * (double)(0.6931471805599453f * lg), c);
+    }
+#endif
     const double c = cbrt(x);
     // ln x to ~1e-6 relative is ample for a correction of a few ulp: lg2 on the special-function unit
     return fma(c, -1.850371707708594e-17 * (double)(0.6931471805599453f * __log2f((float)x)), c);
@@ -465,12 +510,39 @@ __device__ __forceinline__ double pixel_centre(int idx, double delta, double pit
 __device__ __forceinline__ double profile_radius(double r) { return r < 1.0 ? 1.0 / PTB_SQRT_2PI : r; }
 
 // 1/(sigma*sqrt(2 pi)), first factor of main/device.py:378
-__device__ __forceinline__ double profile_norm(double rc) { return 1.0 / (rc * PTB_SQRT_2PI); }
+__device__ __forceinline__ double profile_norm(double rc) { return rcp_pos(rc * PTB_SQRT_2PI); }
+
+// exp(x) for x <= 0 (the Gaussian profile's exponent): x = (64 m + j) ln2/64 + r with |r| <= ln2/128, so that
+//     exp(x) = 2^m * 2^(j/64) * (1 + r + r^2/2 + ... + r^5/120)          (the r^6 term is below 4e-17)
+// with 2^(j/64) from a 64-entry table in shared memory: about half the instructions of the library routine (whose
+// polynomial has eleven terms, each coefficient a pair of moves), ~1 ulp.  Arguments below -700 (profiles that vanish
+// against any charge) are clamped so that the result stays a normal number for the exponent arithmetic; a NaN argument
+// comes out as that tiny number too (the library gives NaN) -- no caller produces one from finite positions.
+__device__ __forceinline__ double exp_nonpos(double x, const double *tab)
+{
+#ifdef PTB_LIBRARY_MATH
+    return exp(x);
+#else
+    x = fmax(x, -700.0);
+    const double t = fma(x, 92.332482616893657, 6755399441055744.0);     // 64/ln2; 1.5 * 2^52: round to nearest integer
+    const int    k = __double2loint(t);
+    const double kd = t - 6755399441055744.0;
+    double       r = fma(kd, -1.0830424696249145e-02, x);                 // ln2/64, head ...
+    r = fma(kd, -3.623510646634843e-19, r);                               // ... and tail (ln2/64 - head)
+    double p = fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
+    p = fma(p, r, 1.6666666666666666e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r * r, r);                                                 // exp(r) - 1
+    const double T = tab[k & 63];
+    const double y = fma(T, p, T);
+    return __hiloint2double(__double2hiint(y) + ((k >> 6) << 20), __double2loint(y));
+#endif
+}
 
 // exp(-(d^2)/(2 sigma^2)), second factor of main/device.py:378; y2 = RN(1/(2 sigma^2))
-__device__ __forceinline__ double profile_shape(double d, double rc, double y2)
+__device__ __forceinline__ double profile_shape(double d, double rc, double y2, const double *tab)
 {
-    return exp(div_rcp(-(d * d), 2.0 * (rc * rc), y2));
+    return exp_nonpos(div_rcp(-(d * d), 2.0 * (rc * rc), y2), tab);
 }
 
 }  // namespace ptb

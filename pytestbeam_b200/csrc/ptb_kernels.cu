@@ -22,6 +22,7 @@
 // does not depend on block scheduling order.
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -361,7 +362,7 @@ __device__ __forceinline__ Cluster describe(const ConfigK &cfg, const PlaneK &pl
         // is clipped to the matrix, and its edge columns / rows -- the usual casualties, their centres lie up
         // to half a pitch outside x +- rx -- are dropped when they fail the very expression the pixel test
         // uses.  Whatever else fails is still rejected by the full test of every pixel.
-        const double yx = 1.0 / (rx * rx), yy = 1.0 / (ry * ry);
+        const double yx = rcp_pos(rx * rx), yy = rcp_pos(ry * ry);
         int ca = 0, cb = -1, ra = 0, rb = -1;      // box-relative, inclusive
         if (box > 0) {
             ca = max(0, 1 - c_lo); cb = min((int)nc - 1, pl.ncol - c_lo);
@@ -391,15 +392,25 @@ __device__ __forceinline__ Cluster describe(const ConfigK &cfg, const PlaneK &pl
     return out;
 }
 
+// PTB_COMPACT_NARROW: a count that does not fit its nibble goes to the escape list (include/ptb.h)
+__device__ __forceinline__ void escape_count(const KParams &P, int d, unsigned long long kl, unsigned count)
+{
+    const unsigned slot = atomicAdd(&P.totals->escapes, 1u);
+    if (slot < P.cmp.escape_capacity)
+        P.cmp.escapes[slot] = ((unsigned long long)count << 48) | ((unsigned long long)d << 40) | kl;
+    else
+        atomicOr(&P.totals->error, PTB_DEV_COUNT_OVERFLOW);
+}
+
 // The separable parts of a pixel's charge and ellipse test for one column (axis 0) or row (axis 1):
 //      g = 1/(sigma sqrt(2pi)) exp(-(d^2)/(2 sigma^2))  (main/device.py:378),   e = d^2 / r^2  (main/device.py:291-293)
 __device__ __forceinline__ void profile_entry(const AxisK &ax, int idx, double pos, double r, double nrm, double ye,
-                                              double &g, double &e)
+                                              const double *exp2_tab, double &g, double &e)
 {
     const double dd = pixel_centre(idx, ax.delta, ax.pitch, ax.half_n, ax.half_p) - pos;
     // 1/(2 rc^2): half of 1/r^2 (exact scaling) unless the radius is clamped (main/device.py:400-403)
     const double y2 = r < 1.0 ? PTB_RCP_2RC2_CLAMPED : 0.5 * ye;
-    g = nrm * profile_shape(dd, profile_radius(r), y2);
+    g = nrm * profile_shape(dd, profile_radius(r), y2, exp2_tab);
     e = div_rcp(dd * dd, r * r, ye);
 }
 
@@ -415,7 +426,7 @@ __device__ __forceinline__ void profile_entry(const AxisK &ax, int idx, double p
 template <class Src, int PC, int MODE>
 __device__ __forceinline__ void digitise_group(const ConfigK &cfg, const KParams &P, const Src &src,
                                                const unsigned long long group, WarpShared &W, double *pool_g,
-                                               double *pool_e, const int lane)
+                                               double *pool_e, const double *exp2_tab, const int lane)
 {
     const int    D = cfg.n_planes;
     constexpr bool   keep64 = MODE == 1, compact = MODE == 2;
@@ -578,8 +589,8 @@ __device__ __forceinline__ void digitise_group(const ConfigK &cfg, const KParams
                     const int    ncl = W.ncols[own];
                     const int    a = e >= ncl ? 1 : 0;            // axis of the entry: a column (x) or a row (y)
                     const int    idx = W.lo[a][own] + (e - (a ? ncl : 0));
-                    profile_entry(pl.ax[a], idx, W.pos[a][own], W.rad[a][own], W.nrm[a][own], W.ye[a][own], pool_g[t],
-                                  pool_e[t]);
+                    profile_entry(pl.ax[a], idx, W.pos[a][own], W.rad[a][own], W.nrm[a][own], W.ye[a][own], exp2_tab,
+                                  pool_g[t], pool_e[t]);
                 }
             }
             __syncwarp();
@@ -673,7 +684,16 @@ __device__ __forceinline__ void digitise_group(const ConfigK &cfg, const KParams
             o_begin = o_end;
         }
         __syncwarp();
-        if (compact && valid) P.cmp.counts[(unsigned long long)d * P.n + kl] = W.cnt[lane];
+        if (compact) {
+            if (P.flags & PTB_COMPACT_NARROW) {   // 4 bits per particle: the even lane stores the pair's byte
+                const unsigned full = W.cnt[lane], c = min(full, 15u);
+                if (full >= 15u) escape_count(P, d, kl, full);   // (invalid lanes count 0)
+                const unsigned pair = c | (__shfl_down_sync(FULL, c, 1) << 4);
+                if (valid && !(lane & 1)) P.cmp.counts[(unsigned long long)d * ((P.n + 1) / 2) + kl / 2] = (uint8_t)pair;
+            } else if (valid) {
+                P.cmp.counts[(unsigned long long)d * P.n + kl] = W.cnt[lane];
+            }
+        }
         // lane d keeps the plane's row count and segment start; the table is written once, after the last plane.  A group
         // whose reservation did not fit wrote nothing: its count stays exact (the host retries with it), its segment
         // start tells k_gather that there is nothing to copy
@@ -721,12 +741,16 @@ __global__ void __launch_bounds__(BLOCK, DIGI_MIN_BLOCKS) k_digitise(const __gri
     WarpShared      &W = *reinterpret_cast<WarpShared *>(wbase);
     double          *pool_g = reinterpret_cast<double *>(wbase + sizeof(WarpShared));
     double          *pool_e = pool_g + PC;
+    // the block's copy of the 2^(j/64) table (exp_nonpos), behind the warps' regions
+    double          *exp2_tab = reinterpret_cast<double *>(smem_raw + wbytes * WARPS_PER_BLOCK);
+    if (threadIdx.x < 64) exp2_tab[threadIdx.x] = cfg.exp2_tab[threadIdx.x];
+    __syncthreads();   // the only block-wide barrier: before the warps go their own ways
     for (;;) {
         unsigned long long group = 0;
         if (lane == 0) group = atomicAdd(&P.ws.alloc[ALLOC_TICKET * 16], 1ull);
         group = __shfl_sync(FULL, group, 0);
         if (group >= P.n_groups) return;   // whole warps leave; no block-wide barrier is used anywhere
-        digitise_group<Src, PC, MODE>(cfg, P, src, group, W, pool_g, pool_e, lane);
+        digitise_group<Src, PC, MODE>(cfg, P, src, group, W, pool_g, pool_e, exp2_tab, lane);
         __syncwarp();
     }
 }
@@ -745,6 +769,10 @@ __global__ void __launch_bounds__(32 * BIG_WARPS) k_digitise_big(const __grid_co
                                                                  const __grid_constant__ KParams P, const Src src)
 {
     __shared__ WarpShared Ws[BIG_WARPS];
+    __shared__ double     exp2_tab[64];
+    static_assert(32 * BIG_WARPS == 64, "one thread per table entry");
+    exp2_tab[threadIdx.x] = cfg.exp2_tab[threadIdx.x];   // 32 * BIG_WARPS = 64 threads
+    __syncthreads();
     const int                lane = threadIdx.x & 31;
     WarpShared              &W = Ws[threadIdx.x >> 5];
     const int                D = cfg.n_planes;
@@ -803,8 +831,8 @@ __global__ void __launch_bounds__(32 * BIG_WARPS) k_digitise_big(const __grid_co
                 if (p < box) {
                     const int ci = p / nrw, ri = p - ci * nrw;
                     double    gc, ec, gr, er;
-                    profile_entry(pl.ax[0], W.lo[0][b] + ci, px, rx, W.nrm[0][b], W.ye[0][b], gc, ec);
-                    profile_entry(pl.ax[1], W.lo[1][b] + ri, py, ry, W.nrm[1][b], W.ye[1][b], gr, er);
+                    profile_entry(pl.ax[0], W.lo[0][b] + ci, px, rx, W.nrm[0][b], W.ye[0][b], exp2_tab, gc, ec);
+                    profile_entry(pl.ax[1], W.lo[1][b] + ri, py, ry, W.nrm[1][b], W.ye[1][b], exp2_tab, gr, er);
                     const double zn = src.pixel(P.first + group * 32 + b, d, (uint32_t)p,
                                                 (uint32_t)(Src::kPixelKeyed ? W.jbase[b] : W.jbase[b] + ci * W.nrfull[b] + ri));
                     const double noise = 0.0 + pl.noise_sigma * zn;
@@ -832,8 +860,16 @@ __global__ void __launch_bounds__(32 * BIG_WARPS) k_digitise_big(const __grid_co
                 kept = 1;
             }
             if (compact && lane == 0) {
-                P.cmp.counts[(unsigned long long)d * P.n + group * 32 + b] = (uint8_t)min(kept, 255);
-                if (kept > 255) atomicOr(&P.totals->error, PTB_DEV_COUNT_OVERFLOW);
+                if (P.flags & PTB_COMPACT_NARROW) {   // the particle's nibble of the byte k_digitise left (zero) for the pair
+                    uint8_t  *byte = &P.cmp.counts[(unsigned long long)d * ((P.n + 1) / 2) + (group * 32 + b) / 2];
+                    const int sh = (b & 1) * 4;
+                    *byte = (uint8_t)((*byte & ~(15u << sh)) | ((unsigned)min(kept, 15) << sh));
+                    if (kept >= 15) escape_count(P, d, group * 32 + b, (unsigned)min(kept, 255));
+                    if (kept > 255) atomicOr(&P.totals->error, PTB_DEV_COUNT_OVERFLOW);
+                } else {
+                    P.cmp.counts[(unsigned long long)d * P.n + group * 32 + b] = (uint8_t)min(kept, 255);
+                    if (kept > 255) atomicOr(&P.totals->error, PTB_DEV_COUNT_OVERFLOW);
+                }
             }
             n_plane += kept;
         }
@@ -984,7 +1020,7 @@ struct GatherParams {
     PtbTotals         *totals;
 };
 
-__global__ void __launch_bounds__(256) k_gather(const __grid_constant__ GatherParams G)
+__global__ void __launch_bounds__(256, 8) k_gather(const __grid_constant__ GatherParams G)
 {
     // per-plane pointers in shared memory: lanes of one warp address different planes at the same time
     __shared__ const uint2    *s_hit[PTB_MAX_PLANES];
@@ -1008,6 +1044,20 @@ __global__ void __launch_bounds__(256) k_gather(const __grid_constant__ GatherPa
     if (group >= G.n_groups) return;
     const PtbBases &B = *G.ws.bases_used;
     if (G.flags & PTB_DIGITISE) {
+        // PTB_COMPACT_NARROW: the planes' rows lie back to back, plane d starts where the rows of planes 0..d-1 end
+        // (k_scan has written this call's totals)
+        const bool         narrow = (G.flags & PTB_COMPACT_NARROW) != 0;
+        unsigned long long dense_l = 0;
+        if (narrow) {
+            const unsigned long long mine = lane < D ? G.totals->hits[lane] : 0ull;
+            unsigned long long       incl = mine;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                const unsigned long long o = __shfl_up_sync(FULL, incl, s);
+                if (lane >= s) incl += o;
+            }
+            dense_l = incl - mine;
+        }
         // lane d fetches the segment descriptor of plane d: all table look-ups of the group are in flight at once
         unsigned long long n_l = 0, src_l = 0, dst_l = 0;
         if (lane < D) {
@@ -1018,8 +1068,10 @@ __global__ void __launch_bounds__(256) k_gather(const __grid_constant__ GatherPa
                                                       : G.slabs[lane].capacity;
             // a group whose scratch reservation did not fit wrote no rows (NO_SEGMENT): nothing of it may be copied
             const bool no_src = src_l == NO_SEGMENT || src_l + n_l > G.ws.cap[lane];
-            if (n_l != 0 && (dst_l + n_l > room_l || no_src)) {
-                atomicOr(&G.totals->error, dst_l + n_l > room_l ? PTB_DEV_SLAB_OVERFLOW : PTB_DEV_SCRATCH_OVERFLOW);
+            // (narrow form: a plane that outgrew its share pushes the later planes' rows towards the end of the arrays)
+            const bool no_room = dst_l + n_l > room_l || (narrow && dense_l + dst_l + n_l > G.cmp.plane_first[D]);
+            if (n_l != 0 && (no_room || no_src)) {
+                atomicOr(&G.totals->error, no_room ? PTB_DEV_SLAB_OVERFLOW : PTB_DEV_SCRATCH_OVERFLOW);
                 n_l = 0;
             }
         }
@@ -1035,26 +1087,43 @@ __global__ void __launch_bounds__(256) k_gather(const __grid_constant__ GatherPa
             if (lane >= s) cum += o;
         }
         const int total = __shfl_sync(FULL, cum, 31);
+        // The planes that have rows move to the low lanes, in order: lane r holds the r-th of them -- one past its last
+        // row in the work list, and its source / destination positions shifted by its first row, so that row w of the
+        // list is read at src + w and written at dst + w.  With the empty planes gone the ends are distinct, and the
+        // plane of a row is found as in k_digitise: count the planes that ended before the step (a ballot) plus those
+        // ending inside it below the row (one warp-wide OR of their end bits).
+        const unsigned nz = __ballot_sync(FULL, n_l != 0);
+        const int      R = __popc(nz);
+        const int      from = lane < R ? (int)__fns(nz, 0, lane + 1) : 0;
+        const int      endR = lane < R ? __shfl_sync(FULL, cum, from) : 0x7fffffff;
+        const int      firstR = endR - (int)__shfl_sync(FULL, (unsigned)n_l, from);
+        const unsigned long long dstAll = dst_l + (narrow ? dense_l : (compact && lane < D) ? G.cmp.plane_first[lane] : 0ull);
+        const unsigned long long srcR = __shfl_sync(FULL, src_l, from) - (unsigned long long)firstR;
+        const unsigned long long dstR = __shfl_sync(FULL, dstAll, from) - (unsigned long long)firstR;
         for (int w0 = 0; w0 < total; w0 += 32) {
-            const int w = w0 + lane;
-            int       d = 0;
-            for (int p = 0; p < D; ++p) d += (__shfl_sync(FULL, cum, p) <= w) ? 1 : 0;   // plane of row w
-            d = min(d, D - 1);
-            const int                before = __shfl_sync(FULL, cum, max(d - 1, 0));   // all lanes take part
-            const int                first = d ? before : 0;
-            const unsigned long long src = __shfl_sync(FULL, src_l, d), dst = __shfl_sync(FULL, dst_l, d);
-            if (w < total && compact) {
-                const unsigned long long i = (unsigned long long)(w - first);
-                const uint2              hit = s_hit[d][src + i];
-                G.cmp.hits[G.cmp.plane_first[d] + dst + i] = (unsigned long long)hit.x | ((unsigned long long)hit.y << 32);
-            } else if (w < total) {
-                const unsigned long long i = (unsigned long long)(w - first);
-                const uint2              hit = s_hit[d][src + i];
-                d_event[d][dst + i] = ev_base + (int64_t)s_ev[d][src + i];
-                d_col[d][dst + i] = (uint16_t)(hit.x & 0xffffu);
-                d_row[d][dst + i] = (uint16_t)(hit.x >> 16);
-                d_charge[d][dst + i] = __uint_as_float(hit.y);
-                if (keep64) d_q64[d][dst + i] = s_q64[d][src + i];
+            const int      w = w0 + lane;
+            const unsigned before = __ballot_sync(FULL, endR <= w0);
+            const int      rel = endR - w0;
+            const unsigned ends = __reduce_or_sync(FULL, (rel >= 1 && rel <= 31) ? 1u << rel : 0u);
+            const int      rank = min(__popc(before) + __popc(ends & ((2u << lane) - 1u)), R - 1);
+            const int      d = __shfl_sync(FULL, from, rank);
+            const unsigned long long si = __shfl_sync(FULL, srcR, rank) + (unsigned long long)w;
+            const unsigned long long o = __shfl_sync(FULL, dstR, rank) + (unsigned long long)w;
+            if (w >= total) continue;
+            const uint2 hit = s_hit[d][si];
+            if (narrow) {
+                const unsigned pos = (hit.x & 0xfffu) | ((hit.x >> 16) << 12);   // column | row << 12
+                G.cmp.charge[o] = __uint_as_float(hit.y);
+                G.cmp.pos_lo[o] = (uint16_t)pos;
+                G.cmp.pos_hi[o] = (uint8_t)(pos >> 16);
+            } else if (compact) {
+                G.cmp.hits[o] = (unsigned long long)hit.x | ((unsigned long long)hit.y << 32);
+            } else {
+                d_event[d][o] = ev_base + (int64_t)s_ev[d][si];
+                d_col[d][o] = (uint16_t)(hit.x & 0xffffu);
+                d_row[d][o] = (uint16_t)(hit.x >> 16);
+                d_charge[d][o] = __uint_as_float(hit.y);
+                if (keep64) d_q64[d][o] = s_q64[d][si];
             }
         }
     }
@@ -1231,7 +1300,7 @@ static cudaError_t launch_digitise(unsigned blocks, cudaStream_t st, const ptb::
                                    const Src &src)
 {
     using namespace ptb;
-    constexpr size_t smem = warp_shared_bytes(PC) * WARPS_PER_BLOCK;
+    constexpr size_t smem = warp_shared_bytes(PC) * WARPS_PER_BLOCK + 64 * sizeof(double);   // + the exp2 table
     k_digitise<Src, PC, MODE><<<blocks, BLOCK, smem, st>>>(c, P, src);
     return cudaGetLastError();
 }
@@ -1250,7 +1319,7 @@ static cudaError_t launch_digitise_mode(int mode, unsigned blocks, cudaStream_t 
 template <class Src, int PC, int MODE>
 static cudaError_t prefer_shared()
 {
-    static_assert(ptb::warp_shared_bytes(PC) * ptb::WARPS_PER_BLOCK <= 48 * 1024, "k_digitise needs the shared-memory opt-in");
+    static_assert(ptb::warp_shared_bytes(PC) * ptb::WARPS_PER_BLOCK + 512 <= 48 * 1024, "k_digitise needs the shared-memory opt-in");
     return cudaFuncSetAttribute(ptb::k_digitise<Src, PC, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                 cudaSharedmemCarveoutMaxShared);
 }
@@ -1315,6 +1384,71 @@ static double moyal_density(double delta, double loc, double scale)
 // F(lambda) = P(Lambda <= lambda) for the Moyal law = erfc(exp(-lambda/2)/sqrt 2)
 static double moyal_cdf(double lam) { return erfc(exp(-lam / 2) / sqrt(2.0)); }
 
+// Rows: how a compressed row is read (hit i of the plane -> column, row, charge bits); Counts: rows of particle k.
+template <class Rows, class Counts>
+static int64_t expand_rows(const Rows &rows_of, const Counts &count_of, const uint32_t *accepted, uint64_t n,
+                           int64_t event_base, uint64_t n_rows_expected, void *out, int32_t threads)
+{
+    int T = threads > 0 ? threads : (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+    const uint64_t words = (n + 31) / 32;
+    T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)T, (words + 4095) / 4096));   // >= 128k particles per thread
+    const uint64_t          per = (words + T - 1) / T;   // words per thread
+    std::vector<uint64_t>   rows(T + 1, 0), acc(T + 1, 0);
+    auto range = [&](int t, uint64_t &k0, uint64_t &k1) {
+        k0 = std::min<uint64_t>(n, per * 32 * (uint64_t)t);
+        k1 = std::min<uint64_t>(n, k0 + per * 32);
+    };
+    auto count_pass = [&](int t) {
+        uint64_t k0, k1, r = 0, a = 0;
+        range(t, k0, k1);
+        for (uint64_t k = k0; k < k1; ++k) r += count_of(k);
+        for (uint64_t w = k0 / 32; w < (k1 + 31) / 32; ++w) {
+            uint32_t m = accepted[w];
+            if ((w + 1) * 32 > n) m &= (uint32_t)((1ull << (n - w * 32)) - 1ull);   // bits beyond the range do not count
+            a += (uint64_t)__builtin_popcount(m);
+        }
+        rows[t + 1] = r;
+        acc[t + 1] = a;
+    };
+    auto run_threads = [&](auto fn) {
+        std::vector<std::thread> pool;
+        for (int t = 1; t < T; ++t) pool.emplace_back(fn, t);
+        fn(0);
+        for (auto &th : pool) th.join();
+    };
+    run_threads(count_pass);
+    for (int t = 0; t < T; ++t) {
+        rows[t + 1] += rows[t];
+        acc[t + 1] += acc[t];
+    }
+    if (rows[T] != n_rows_expected) return PTB_E_INVALID;
+    unsigned char *dst = (unsigned char *)out;
+    auto expand_pass = [&](int t) {
+        uint64_t k0, k1;
+        range(t, k0, k1);
+        uint64_t i = rows[t];
+        int64_t  ev = event_base + 1 + (int64_t)acc[t];
+        for (uint64_t k = k0; k < k1; ++k) {
+            const unsigned c = count_of(k);
+            for (unsigned j = 0; j < c; ++j, ++i) {
+                uint16_t col, row;
+                uint32_t q;
+                rows_of(i, col, row, q);
+                unsigned char *r = dst + i * 18;
+                const uint16_t frame = 0;
+                memcpy(r, &ev, 8);
+                memcpy(r + 8, &frame, 2);
+                memcpy(r + 10, &col, 2);
+                memcpy(r + 12, &row, 2);
+                memcpy(r + 14, &q, 4);
+            }
+            ev += (accepted[k >> 5] >> (k & 31)) & 1u;
+        }
+    };
+    run_threads(expand_pass);
+    return (int64_t)rows[T];
+}
+
 extern "C" {
 
 int ptb_create(const PtbBeam *beam, const PtbDevice *dev, int32_t n_dev, const PtbOptions *opt, PtbHandle *out)
@@ -1377,6 +1511,7 @@ int ptb_create(const PtbBeam *beam, const PtbDevice *dev, int32_t n_dev, const P
         c.sigma0 = sqrt(c.diff2 + 0.0) * 1e6;
         c.rcp_3p6 = 1.0 / 3.6;
         c.rcp_cden = 1.0 / c.cden;
+        for (int j = 0; j < 64; ++j) c.exp2_tab[j] = (double)exp2l((long double)j / 64.0L);   // rounded once, from 64 bits
     }
     double mean_prev = 0.0;   // mean loss in the previous plane; the reference indexes row -1 (all zero) for plane 0
     for (int d = 0; d < n_dev; ++d) {
@@ -1637,8 +1772,17 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
     const bool         compact = (flags & PTB_COMPACT) != 0;
     if (compact && (!(flags & PTB_DIGITISE) || (flags & PTB_KEEP_CHARGE64)))
         return fail(h, PTB_E_INVALID, "PTB_COMPACT needs PTB_DIGITISE and excludes PTB_KEEP_CHARGE64");
-    if (compact && (!run->compact.hits || !run->compact.counts || !run->compact.accepted))
+    const bool         narrow = (flags & PTB_COMPACT_NARROW) != 0;
+    if (narrow && !compact) return fail(h, PTB_E_INVALID, "PTB_COMPACT_NARROW needs PTB_COMPACT");
+    if (compact && (!run->compact.counts || !run->compact.accepted ||
+                    (narrow ? (!run->compact.charge || !run->compact.pos_lo || !run->compact.pos_hi ||
+                               (run->compact.escape_capacity && !run->compact.escapes))
+                            : !run->compact.hits)))
         return fail(h, PTB_E_INVALID, "compact output pointers missing");
+    if (narrow)
+        for (int d = 0; d < D; ++d)
+            if (c.pl[d].ncol > 4095 || c.pl[d].nrow > 4095)
+                return fail(h, PTB_E_INVALID, "PTB_COMPACT_NARROW holds 12 bits per pixel index: a matrix exceeds 4095 columns or rows");
     if (flags & PTB_DIGITISE) {
         for (int d = 0; d < D; ++d) {
             const PtbHitSlab &s = run->slabs[d];
@@ -1666,6 +1810,10 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
     cudaError_t e;
     e = cudaMemsetAsync(P.ws.alloc, 0, sizeof(unsigned long long) * ALLOC_LINES * 16, st);
     if (e != cudaSuccess) return fail_cuda(h, e, "memset alloc");
+    // the error word and the escape counter collect over the call's kernels: every call starts from zero
+    static_assert(offsetof(PtbTotals, escapes) == offsetof(PtbTotals, error) + 4, "error and escapes are cleared together");
+    e = cudaMemsetAsync(&run->totals->error, 0, 8, st);
+    if (e != cudaSuccess) return fail_cuda(h, e, "memset totals");
 
     const bool keep64 = (flags & PTB_KEEP_CHARGE64) != 0;
     cudaEvent_t *tp = timing_pair(h);
@@ -1803,63 +1951,45 @@ int64_t ptb_expand_hits(const uint64_t *hits, const uint8_t *counts, const uint3
                         int64_t event_base, uint64_t n_rows_expected, void *out, int32_t threads)
 {
     if ((!hits && n_rows_expected) || !counts || !accepted || (!out && n_rows_expected)) return PTB_E_INVALID;
-    int T = threads > 0 ? threads : (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
-    const uint64_t words = (n + 31) / 32;
-    T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)T, (words + 4095) / 4096));   // >= 128k particles per thread
-    const uint64_t          per = (words + T - 1) / T;   // words per thread
-    std::vector<uint64_t>   rows(T + 1, 0), acc(T + 1, 0);
-    auto range = [&](int t, uint64_t &k0, uint64_t &k1) {
-        k0 = std::min<uint64_t>(n, per * 32 * (uint64_t)t);
-        k1 = std::min<uint64_t>(n, k0 + per * 32);
-    };
-    auto count_pass = [&](int t) {
-        uint64_t k0, k1, r = 0, a = 0;
-        range(t, k0, k1);
-        for (uint64_t k = k0; k < k1; ++k) r += counts[k];
-        for (uint64_t w = k0 / 32; w < (k1 + 31) / 32; ++w) {
-            uint32_t m = accepted[w];
-            if ((w + 1) * 32 > n) m &= (uint32_t)((1ull << (n - w * 32)) - 1ull);   // bits beyond the range do not count
-            a += (uint64_t)__builtin_popcount(m);
-        }
-        rows[t + 1] = r;
-        acc[t + 1] = a;
-    };
-    auto run_threads = [&](auto fn) {
-        std::vector<std::thread> pool;
-        for (int t = 1; t < T; ++t) pool.emplace_back(fn, t);
-        fn(0);
-        for (auto &th : pool) th.join();
-    };
-    run_threads(count_pass);
-    for (int t = 0; t < T; ++t) {
-        rows[t + 1] += rows[t];
-        acc[t + 1] += acc[t];
-    }
-    if (rows[T] != n_rows_expected) return PTB_E_INVALID;
-    unsigned char *dst = (unsigned char *)out;
-    auto expand_pass = [&](int t) {
-        uint64_t k0, k1;
-        range(t, k0, k1);
-        uint64_t i = rows[t];
-        int64_t  ev = event_base + 1 + (int64_t)acc[t];
-        for (uint64_t k = k0; k < k1; ++k) {
-            const unsigned c = counts[k];
-            for (unsigned j = 0; j < c; ++j, ++i) {
-                const uint64_t h = hits[i];
-                unsigned char *r = dst + i * 18;
-                const uint16_t frame = 0, col = (uint16_t)h, row = (uint16_t)(h >> 16);
-                const uint32_t q = (uint32_t)(h >> 32);
-                memcpy(r, &ev, 8);
-                memcpy(r + 8, &frame, 2);
-                memcpy(r + 10, &col, 2);
-                memcpy(r + 12, &row, 2);
-                memcpy(r + 14, &q, 4);
-            }
-            ev += (accepted[k >> 5] >> (k & 31)) & 1u;
-        }
-    };
-    run_threads(expand_pass);
-    return (int64_t)rows[T];
+    return expand_rows(
+        [=](uint64_t i, uint16_t &col, uint16_t &row, uint32_t &q) {
+            const uint64_t h = hits[i];
+            col = (uint16_t)h;
+            row = (uint16_t)(h >> 16);
+            q = (uint32_t)(h >> 32);
+        },
+        [=](uint64_t k) -> unsigned { return counts[k]; }, accepted, n, event_base, n_rows_expected, out, threads);
+}
+
+int64_t ptb_expand_hits_narrow(const float *charge, const uint16_t *pos_lo, const uint8_t *pos_hi, const uint8_t *counts4,
+                               const uint64_t *escapes, uint64_t n_escapes, int32_t plane, const uint32_t *accepted,
+                               uint64_t n, int64_t event_base, uint64_t n_rows_expected, void *out, int32_t threads)
+{
+    if (((!charge || !pos_lo || !pos_hi) && n_rows_expected) || !counts4 || !accepted || (!out && n_rows_expected) ||
+        (n_escapes && !escapes))
+        return PTB_E_INVALID;
+    // this plane's escaped counts, sorted by particle: a nibble of 15 is looked up here
+    std::vector<std::pair<uint64_t, unsigned>> esc;
+    for (uint64_t i = 0; i < n_escapes; ++i)
+        if ((int32_t)((escapes[i] >> 40) & 0xffu) == plane)
+            esc.emplace_back(escapes[i] & 0xffffffffffull, (unsigned)(escapes[i] >> 48));
+    std::sort(esc.begin(), esc.end());
+    const auto *eb = esc.data();
+    const size_t ne = esc.size();
+    return expand_rows(
+        [=](uint64_t i, uint16_t &col, uint16_t &row, uint32_t &q) {
+            const uint32_t pos = (uint32_t)pos_lo[i] | ((uint32_t)pos_hi[i] << 16);   // column | row << 12
+            col = (uint16_t)(pos & 0xfffu);
+            row = (uint16_t)(pos >> 12);
+            memcpy(&q, &charge[i], 4);
+        },
+        [=](uint64_t k) -> unsigned {
+            const unsigned c = (counts4[k >> 1] >> ((k & 1) * 4)) & 15u;
+            if (c < 15u) return c;
+            const auto *it = std::lower_bound(eb, eb + ne, std::make_pair(k, 0u));
+            return (it != eb + ne && it->first == k) ? it->second : 0xffffffffu;   // no entry: the sum check fails
+        },
+        accepted, n, event_base, n_rows_expected, out, threads);
 }
 
 double ptb_measure_fp64_peak(void *stream)

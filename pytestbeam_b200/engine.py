@@ -85,17 +85,24 @@ class RunResult:
     event_base: int = 0
 
     def compact_host(self) -> dict:
-        """The PtbCompactOut on the host: per-plane uint64 rows, uint8 counts [D, n], uint32 trigger words."""
-        D, hits, pf = len(self.totals["hits"]), self.totals["hits"], self.compact["plane_first"]
-        return {"hits": [self.compact["hits"][pf[d]:pf[d] + hits[d]].cpu().numpy().view(np.uint64) for d in range(D)],
-                "counts": self.compact["counts"].cpu().numpy().reshape(D, self.n),
-                "accepted": self.compact["accepted"].cpu().numpy().view(np.uint32)}
+        """The PtbCompactOut on the host, plane by plane: uint64 rows + uint8 counts [D, n] (wide form) or the
+        (charge, pos_lo, pos_hi) slices + nibble pairs [D, (n+1)//2] (narrow form); uint32 trigger words."""
+        D, hits, c = len(self.totals["hits"]), self.totals["hits"], self.compact
+        acc = c["accepted"].cpu().numpy().view(np.uint32)
+        if c.get("narrow"):
+            first = np.concatenate([[0], np.cumsum(hits)]).astype(np.int64)      # the planes lie back to back
+            cut = lambda k, dt: [c[k][first[d]:first[d + 1]].cpu().numpy().view(dt) for d in range(D)]  # noqa: E731
+            return {"narrow": True, "charge": cut("charge", np.float32), "pos_lo": cut("pos_lo", np.uint16),
+                    "pos_hi": cut("pos_hi", np.uint8), "counts": c["counts"].cpu().numpy().reshape(D, (self.n + 1) // 2),
+                    "escapes": c["escapes"][:self.totals["escapes"]].cpu().numpy().view(np.uint64), "accepted": acc}
+        pf = c["plane_first"]
+        return {"hits": [c["hits"][pf[d]:pf[d] + hits[d]].cpu().numpy().view(np.uint64) for d in range(D)],
+                "counts": c["counts"].cpu().numpy().reshape(D, self.n), "accepted": acc}
 
     def hits_numpy(self, plane: int) -> np.ndarray:
         """Rows of one plane as the reference's structured array (main/device.py:20-28)."""
         if self.compact is not None:
-            c = self.compact_host()
-            return expand_compact(N.load(), c["hits"][plane], c["counts"][plane], c["accepted"], self.n, self.event_base)
+            return expand_compact(N.load(), plane_of(self.compact_host(), plane), self.n, self.event_base)
         s = self.slabs[plane]
         out = np.zeros(int(s["event"].numel()), dtype=HITS_DTYPE)
         out["event_number"] = s["event"].cpu().numpy()
@@ -164,13 +171,36 @@ class Simulator:
             slabs.append(s)
         return slabs
 
-    def alloc_compact(self, n, capacities):
+    def alloc_compact(self, n, capacities, narrow=False):
         """Device buffers of a PtbCompactOut for n particles and the given rows per plane."""
         first = np.concatenate([[0], np.cumsum([int(c) for c in capacities])]).astype(np.int64)
-        return {"plane_first": [int(v) for v in first],
-                "hits": torch.empty(int(first[-1]), dtype=torch.int64, device=self.device),
-                "counts": torch.empty(self.D * int(n), dtype=torch.uint8, device=self.device),
-                "accepted": torch.empty((int(n) + 31) // 32, dtype=torch.int32, device=self.device)}
+        rows, dev = int(first[-1]), self.device
+        out = {"plane_first": [int(v) for v in first], "narrow": bool(narrow),
+               "accepted": torch.empty((int(n) + 31) // 32, dtype=torch.int32, device=dev)}
+        if narrow:
+            out.update(charge=torch.empty(rows, dtype=torch.float32, device=dev),
+                       pos_lo=torch.empty(rows, dtype=torch.int16, device=dev),
+                       pos_hi=torch.empty(rows, dtype=torch.uint8, device=dev),
+                       counts=torch.empty(self.D * ((int(n) + 1) // 2), dtype=torch.uint8, device=dev),
+                       # counts of 15 and more: one entry per 256 (particle, plane) pairs is far above any telescope's need
+                       escapes=torch.empty(max(1024, self.D * int(n) // 256), dtype=torch.int64, device=dev))
+        else:
+            out.update(hits=torch.empty(rows, dtype=torch.int64, device=dev),
+                       counts=torch.empty(self.D * int(n), dtype=torch.uint8, device=dev))
+        return out
+
+    def narrow_ok(self, seed=12345, pilot=32768) -> bool:
+        """Does the narrow compressed-row form (PTB_COMPACT_NARROW) fit this set-up?  Matrices within 4095 x 4095 pixels
+        and a pilot range whose counts of 15 and more fit the escape list (a later overflow is retried)."""
+        if getattr(self, "_narrow_ok", None) is None:
+            ok = all(int(d["column"]) <= 4095 and int(d["row"]) <= 4095 for d in self.devices)
+            if ok:
+                try:
+                    self.run(0, pilot, seed=seed, capacities=[pilot * 64] * self.D, compact="narrow")
+                except PtbError:
+                    ok = False
+            self._narrow_ok = ok
+        return self._narrow_ok
 
     def alloc_tracks(self, n):
         D = self.D
@@ -232,8 +262,14 @@ class Simulator:
                                             s["charge64"].data_ptr() if "charge64" in s else None,
                                             int(s["event"].numel()))
         if compact is not None:
-            run.compact.hits, run.compact.counts = compact["hits"].data_ptr(), compact["counts"].data_ptr()
-            run.compact.accepted = compact["accepted"].data_ptr()
+            if compact.get("narrow"):
+                run.flags |= N.PTB_COMPACT_NARROW
+                run.compact.charge, run.compact.pos_lo = compact["charge"].data_ptr(), compact["pos_lo"].data_ptr()
+                run.compact.pos_hi, run.compact.escapes = compact["pos_hi"].data_ptr(), compact["escapes"].data_ptr()
+                run.compact.escape_capacity = int(compact["escapes"].numel())
+            else:
+                run.compact.hits = compact["hits"].data_ptr()
+            run.compact.counts, run.compact.accepted = compact["counts"].data_ptr(), compact["accepted"].data_ptr()
             for d, v in enumerate(compact["plane_first"]):
                 run.compact.plane_first[d] = int(v)
         run.bases_in = bases_in.data_ptr() if bases_in is not None else None
@@ -253,7 +289,7 @@ class Simulator:
         a = t.cpu().numpy()
         u = a.view(np.uint64)
         return {"hits": [int(v) for v in u[:D]], "accepted": int(u[32]), "time_sum": int(a[33]), "pairs": int(u[34]),
-                "inside": int(u[35]), "pixels": int(u[36]), "error": int(u[37] & 0xFFFFFFFF),
+                "inside": int(u[35]), "pixels": int(u[36]), "error": int(u[37] & 0xFFFFFFFF), "escapes": int(u[37] >> 32),
                 "reserved": [int(v) for v in u[38:38 + D]]}
 
     def run(self, first, n, *, seed=0, injected=None, digitise=True, write_tracks=False, tracks_in=None,
@@ -281,7 +317,7 @@ class Simulator:
             capacities = [4 * n + 4096] * self.D if digitise else [0] * self.D
         for attempt in range(8):
             slabs = self.alloc_slabs(capacities, keep_charge64) if (digitise and not compact) else None
-            cmp_out = self.alloc_compact(n, capacities) if compact else None
+            cmp_out = self.alloc_compact(n, capacities, narrow=(compact == "narrow")) if compact else None
             if compact and scratch_rows is None:
                 scratch_rows = [N.default_scratch_rows(int(c)) for c in capacities]
             tracks = tracks_in if tracks_in is not None else (self.alloc_tracks(n) if write_tracks else None)
@@ -305,7 +341,8 @@ class Simulator:
                 scratch_rows = [max(int(r), 1) for r in tot["reserved"]]
                 continue
             if err & N.PTB_DEV_COUNT_OVERFLOW:
-                raise PtbError("a particle left more than 255 rows on one plane: run this range without compact=True")
+                raise PtbError("a particle left more than 255 rows on one plane (or the narrow form ran out of escape "
+                               "entries): run this range without compact")
             if digitise and not compact:
                 slabs = [{k: v[:tot["hits"][d]] for k, v in s.items()} for d, s in enumerate(slabs)]
             ev0 = int(bases_in[0].item()) if bases_in is not None else 0
@@ -366,20 +403,40 @@ class Simulator:
         return out
 
 
-def expand_compact(lib, hits: np.ndarray, counts: np.ndarray, accepted: np.ndarray, n: int, event_base: int,
-                   out: np.ndarray | None = None, threads: int = 0) -> np.ndarray:
-    """One plane of a PtbCompactOut (host arrays) -> the reference's 18-byte records (``ptb_expand_hits``).
+def plane_of(c: dict, plane: int) -> dict:
+    """One plane's arrays of a host-side PtbCompactOut (RunResult.compact_host / HostChunk.compact)."""
+    keys = ("charge", "pos_lo", "pos_hi") if c.get("narrow") else ("hits",)
+    out = {k: c[k][plane] for k in keys}
+    out.update(narrow=bool(c.get("narrow")), counts=c["counts"][plane], accepted=c["accepted"], plane=plane,
+               escapes=c.get("escapes"))
+    return out
 
-    hits: the plane's uint64 rows; counts: uint8 [n]; accepted: uint32 [(n+31)//32]; out: optional destination
-    (any writable buffer of len(hits) records, e.g. a slice of a memory-mapped HDF5 dataset)."""
-    rows = int(hits.shape[0])
+
+def expand_compact(lib, c: dict, n: int, event_base: int, out: np.ndarray | None = None, threads: int = 0) -> np.ndarray:
+    """One plane of a PtbCompactOut (host arrays, see plane_of) -> the reference's 18-byte records (``ptb_expand_hits``
+    / ``ptb_expand_hits_narrow``).
+
+    wide: hits uint64 rows, counts uint8 [n]; narrow: charge f32, pos_lo u16, pos_hi u8 rows, counts [(n+1)//2] nibble
+    pairs, escapes uint64 (the call's entries for counts of 15 and more) and the plane's index; accepted: uint32
+    [(n+31)//32]; out: optional destination (any writable buffer of that many records, e.g. a
+    slice of a memory-mapped HDF5 dataset)."""
+    narrow = bool(c.get("narrow"))
+    rows = int((c["charge"] if narrow else c["hits"]).shape[0])
     if out is None:
         out = np.empty(rows, dtype=HITS_DTYPE)
     if out.shape[0] != rows or out.dtype.itemsize != 18 or not out.flags["C_CONTIGUOUS"]:
-        raise ValueError("destination must be a contiguous array of len(hits) 18-byte records")
-    counts = np.ascontiguousarray(counts, dtype=np.uint8)
-    got = lib.ptb_expand_hits(hits.ctypes.data if rows else None, counts.ctypes.data, accepted.ctypes.data, int(n),
-                              int(event_base), rows, out.ctypes.data if rows else None, int(threads))
+        raise ValueError("destination must be a contiguous array of as many 18-byte records as the plane has rows")
+    counts = np.ascontiguousarray(c["counts"], dtype=np.uint8)
+    acc, dst = c["accepted"].ctypes.data, out.ctypes.data if rows else None
+    ptr = lambda a: a.ctypes.data if rows else None  # noqa: E731
+    if narrow:
+        esc = c.get("escapes")
+        esc = np.zeros(0, np.uint64) if esc is None else np.ascontiguousarray(esc, dtype=np.uint64)
+        got = lib.ptb_expand_hits_narrow(ptr(c["charge"]), ptr(c["pos_lo"]), ptr(c["pos_hi"]), counts.ctypes.data,
+                                         esc.ctypes.data if len(esc) else None, len(esc), int(c.get("plane", 0)), acc,
+                                         int(n), int(event_base), rows, dst, int(threads))
+    else:
+        got = lib.ptb_expand_hits(ptr(c["hits"]), counts.ctypes.data, acc, int(n), int(event_base), rows, dst, int(threads))
     if got != rows:
         raise PtbError(f"ptb_expand_hits: counts add up to something else than {rows} rows ({got})")
     return out

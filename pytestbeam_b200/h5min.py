@@ -286,8 +286,12 @@ class TableWriter:
         if a.ndim != 1:
             raise ValueError("rows must be one-dimensional")
         if len(a):
-            self._f.seek(self._row_addr(self.nrows))
-            a.tofile(self._f)
+            # positioned writes on the descriptor (no shared file position, the GIL is released meanwhile): writers of
+            # different files can be fed from different threads
+            buf, off, fd = memoryview(a).cast("B"), self._row_addr(self.nrows), self._f.fileno()
+            while len(buf):
+                done = os.pwrite(fd, buf[:1 << 30], off)
+                buf, off = buf[done:], off + done
             self.nrows += len(a)
 
     def reserve(self, n: int) -> np.ndarray:

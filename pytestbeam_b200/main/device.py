@@ -60,16 +60,24 @@ class MemorySink:
 
 
 class FileSink:
-    """One streamed ``/Hits`` table per device: rows are written in place through the mapped dataset region."""
+    """One streamed ``/Hits`` table per device.  Every plane's rows are expanded into a reusable staging array and
+    written with positioned writes; the planes of a chunk are served by one thread each (the expansion and the write
+    both release the GIL), which is what the page cache takes fastest: 2-3 times the rate of filling freshly mapped
+    file pages in place."""
+
+    parallel = True
 
     def __init__(self, paths: list):
         self.writers = [h5min.TableWriter(p, "Hits", HITS_DTYPE) for p in paths]
+        self.staging = [np.empty(0, dtype=HITS_DTYPE) for _ in paths]
 
     def room(self, plane: int, rows: int) -> np.ndarray:
-        return self.writers[plane].reserve(rows)
+        if len(self.staging[plane]) < rows:
+            self.staging[plane] = np.empty(int(rows * 1.1) + 4096, dtype=HITS_DTYPE)
+        return self.staging[plane][:rows]
 
     def done(self, plane: int, view) -> None:
-        pass            # no msync: the page cache is coherent for every later reader, the kernel writes back on its own
+        self.writers[plane].append(view)
 
     def close(self) -> None:
         for w in self.writers:
@@ -77,11 +85,27 @@ class FileSink:
 
 
 def _consume_into(sink):
+    """consume(chunk) for ChunkPipeline.run_to_host: every plane's rows go to the sink as the reference's records."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    pool = None
+
+    def one(chunk, d, threads):
+        out = sink.room(d, chunk.rows[d])
+        chunk.records(d, out=out, threads=threads)
+        sink.done(d, out)
+
     def consume(chunk):
-        for d in range(chunk.D):
-            out = sink.room(d, chunk.rows[d])
-            chunk.records(d, out=out)
-            sink.done(d, out)
+        nonlocal pool
+        if not getattr(sink, "parallel", False) or chunk.D == 1:
+            for d in range(chunk.D):
+                one(chunk, d, 0)
+            return
+        if pool is None:
+            pool = ThreadPoolExecutor(max_workers=chunk.D)
+        per = max(1, (os.cpu_count() or 1) // chunk.D)       # threads of each plane's expansion
+        for f in [pool.submit(one, chunk, d, per) for d in range(chunk.D)]:
+            f.result()
     return consume
 
 

@@ -17,6 +17,7 @@ PTB_KEEP_CHARGE64 = 8
 PTB_RECYCLE_SLABS = 16
 PTB_ZERO_RADIUS = 32
 PTB_COMPACT = 64
+PTB_COMPACT_NARROW = 128
 
 PTB_DEV_SCRATCH_OVERFLOW = 1
 PTB_DEV_SLAB_OVERFLOW = 2
@@ -64,7 +65,8 @@ class PtbHitSlab(C.Structure):
 
 class PtbCompactOut(C.Structure):
     _fields_ = [("hits", C.c_void_p), ("counts", C.c_void_p), ("accepted", C.c_void_p),
-                ("plane_first", C.c_uint64 * (PTB_MAX_PLANES + 1))]
+                ("plane_first", C.c_uint64 * (PTB_MAX_PLANES + 1)), ("charge", C.c_void_p), ("pos_lo", C.c_void_p),
+                ("pos_hi", C.c_void_p), ("escapes", C.c_void_p), ("escape_capacity", C.c_uint64)]
 
 
 class PtbBases(C.Structure):
@@ -74,7 +76,7 @@ class PtbBases(C.Structure):
 class PtbTotals(C.Structure):
     _fields_ = [("hits", C.c_uint64 * PTB_MAX_PLANES), ("accepted", C.c_uint64), ("time_sum", C.c_int64),
                 ("pairs", C.c_uint64), ("inside", C.c_uint64), ("pixels", C.c_uint64), ("error", C.c_uint32),
-                ("_pad", C.c_uint32), ("reserved", C.c_uint64 * PTB_MAX_PLANES)]
+                ("escapes", C.c_uint32), ("reserved", C.c_uint64 * PTB_MAX_PLANES)]
 
 
 class PtbRun(C.Structure):
@@ -87,7 +89,8 @@ class PtbRun(C.Structure):
 
 EXPORTS = ("ptb_create", "ptb_destroy", "ptb_last_error", "ptb_n_planes", "ptb_workspace_bytes",
            "ptb_prefix", "ptb_simulate", "ptb_pack_hits", "ptb_launch_count", "ptb_measure_fp64_peak",
-           "ptb_timing_enable", "ptb_timing_read", "ptb_timing_read_stages", "ptb_correlate", "ptb_digest", "ptb_expand_hits")
+           "ptb_timing_enable", "ptb_timing_read", "ptb_timing_read_stages", "ptb_correlate", "ptb_digest", "ptb_expand_hits",
+           "ptb_expand_hits_narrow")
 
 _lib = None
 
@@ -139,6 +142,9 @@ def load() -> C.CDLL:
     L.ptb_expand_hits.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64, C.c_uint64, C.c_void_p,
                                   C.c_int32]
     L.ptb_expand_hits.restype = C.c_int64
+    L.ptb_expand_hits_narrow.argtypes = [C.c_void_p] * 5 + [C.c_uint64, C.c_int32, C.c_void_p, C.c_uint64, C.c_int64,
+                                         C.c_uint64, C.c_void_p, C.c_int32]
+    L.ptb_expand_hits_narrow.restype = C.c_int64
     L.ptb_launch_count.argtypes = []
     L.ptb_launch_count.restype = C.c_uint64
     L.ptb_measure_fp64_peak.argtypes = [C.c_void_p]

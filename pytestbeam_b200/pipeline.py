@@ -4,9 +4,11 @@ buffers (1e10 electrons produce 1.3 TB of hits, far more than fits
 ``ChunkPipeline.run`` keeps everything on the device (throughput measurements, digest sink);
 ``ChunkPipeline.run_to_host`` additionally lands every chunk's hit tables in pinned host memory on a second stream,
 double-buffered so that the copy of chunk i overlaps the kernels of chunk i+1.  What travels over PCIe is the
-compressed-row form of the tables (``PtbCompactOut`` in include/ptb.h: 8-byte rows, one count byte per particle and
-plane, the trigger mask -- 66 instead of 118 bytes per electron on the default telescope); ``HostChunk.records``
-expands it to the reference's 18-byte rows (``ptb_expand_hits``), straight into the caller's buffer if it names one.
+compressed-row form of the tables (``PtbCompactOut`` in include/ptb.h).  Its narrow variant -- 7-byte rows in three
+arrays with the planes back to back, 4-bit counts per particle and plane (larger ones on an escape list), the trigger mask: 55 instead of 118 bytes per
+electron on the default telescope -- is used whenever the set-up fits it (``Simulator.narrow_ok``); the wide one (8-byte
+rows, count bytes: 66 bytes per electron) otherwise.  ``HostChunk.records`` expands either to the reference's 18-byte
+rows (``ptb_expand_hits`` / ``ptb_expand_hits_narrow``), straight into the caller's buffer if it names one.
 """
 from __future__ import annotations
 
@@ -14,7 +16,7 @@ import numpy as np
 import torch
 
 from . import native as N
-from .engine import _BASES_WORDS, _TOTALS_WORDS, HITS_DTYPE, PtbError, Simulator, expand_compact
+from .engine import _BASES_WORDS, _TOTALS_WORDS, HITS_DTYPE, PtbError, Simulator, expand_compact, plane_of
 
 _RETRY = N.PTB_DEV_SLAB_OVERFLOW | N.PTB_DEV_SCRATCH_OVERFLOW | N.PTB_DEV_COUNT_OVERFLOW
 
@@ -52,9 +54,8 @@ class HostChunk:
         """The plane's rows as the reference's records (main/device.py:20-28), written to `out` when given."""
         m = self.totals["hits"][plane]
         if self.compact is not None:
-            c = self.compact
-            return expand_compact(self.lib, c["hits"][plane], c["counts"][plane], c["accepted"], self.n,
-                                  self.event_base, out=out, threads=threads)
+            return expand_compact(self.lib, plane_of(self.compact, plane), self.n, self.event_base, out=out,
+                                  threads=threads)
         s = self.slabs[plane]
         if out is None:
             out = np.empty(m, dtype=HITS_DTYPE)
@@ -68,11 +69,13 @@ class HostChunk:
 
 class ChunkPipeline:
     def __init__(self, sim: Simulator, chunk: int, *, n_buffers: int = 2, capacities=None, host: bool = False,
-                 seed: int = 0, scratch_rows=None, compact: bool | None = None):
+                 seed: int = 0, scratch_rows=None, compact: bool | None = None, narrow: bool | None = None):
         self.sim, self.chunk, self.seed = sim, int(chunk), int(seed)
         self.compact = bool(host) if compact is None else bool(compact)
         if self.compact and not host:
             raise PtbError("the compressed-row output exists for the trip to the host: use host=True")
+        # the narrow compressed rows whenever the set-up fits them (12-bit pixel indices, <= 15 rows per particle and plane)
+        self.narrow = self.compact and (sim.narrow_ok() if narrow is None else bool(narrow))
         self.flags = N.PTB_DIGITISE | N.PTB_RECYCLE_SLABS | (N.PTB_COMPACT if self.compact else 0)
         self.caps = list(capacities) if capacities is not None else sim.default_capacities(self.chunk)
         self.rows = list(scratch_rows) if scratch_rows is not None else sim.default_scratch_rows(self.chunk)
@@ -84,9 +87,9 @@ class ChunkPipeline:
                  "totals": torch.zeros(_TOTALS_WORDS, dtype=torch.int64, device=dev),
                  "done": torch.cuda.Event(), "copied": torch.cuda.Event()}
             if self.compact:
-                s["cmp"] = sim.alloc_compact(self.chunk, self.caps)
+                s["cmp"] = sim.alloc_compact(self.chunk, self.caps, narrow=self.narrow)
                 s["h_cmp"] = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in s["cmp"].items()
-                              if k != "plane_first"}
+                              if isinstance(v, torch.Tensor)}
             else:
                 s["slabs"] = sim.alloc_slabs(self.caps)
                 if host:
@@ -98,6 +101,9 @@ class ChunkPipeline:
         self.bases = sim.new_bases()
         self._base0 = (0, 0)
         self.copy_stream = torch.cuda.Stream(device=dev) if host else None
+        # the chunk's totals (its sizes) come back on a stream of their own, so that the host learns them while the
+        # previous chunk's rows are still crossing the link and the next copies queue up behind those without a gap
+        self.meta_stream = torch.cuda.Stream(device=dev) if host else None
         self.retries = 0
 
     def set_bases(self, event: int = 0, time: int = 0):
@@ -175,10 +181,12 @@ class ChunkPipeline:
             nonlocal rows, nbytes, ev_base, t_base
             s = self.sets[i % len(self.sets)]
             n_i, first_i = size_of(i), first + i * self.chunk
+            with torch.cuda.stream(self.meta_stream):
+                self.meta_stream.wait_event(s["done"])
+                s["h_totals"].copy_(s["totals"], non_blocking=True)
+                self.meta_stream.synchronize()
             with torch.cuda.stream(self.copy_stream):
                 self.copy_stream.wait_event(s["done"])
-                s["h_totals"].copy_(s["totals"], non_blocking=True)
-                self.copy_stream.synchronize()
                 tot = Simulator.decode_totals(s["h_totals"], D)
                 nbytes += _TOTALS_WORDS * 8
                 err = tot["error"]
@@ -187,6 +195,30 @@ class ChunkPipeline:
                 chunk = None
                 if err:
                     chunk = self._retry(i, first_i, n_i, ev_base, t_base, tot)
+                elif self.compact and self.narrow:
+                    c, h = s["cmp"], s["h_cmp"]
+                    m, w, half = sum(tot["hits"]), (n_i + 31) // 32, (n_i + 1) // 2
+                    for k in ("charge", "pos_lo", "pos_hi"):     # the planes' rows lie back to back: one copy per array
+                        h[k][:m].copy_(c[k][:m], non_blocking=True)
+                    if n_i == self.chunk:
+                        h["counts"].copy_(c["counts"], non_blocking=True)
+                    else:                                        # a shorter last chunk: [D][(n_i+1)//2] sits at the front
+                        h["counts"][:D * half].copy_(c["counts"][:D * half], non_blocking=True)
+                    h["accepted"][:w].copy_(c["accepted"][:w], non_blocking=True)
+                    n_esc = tot["escapes"]
+                    if n_esc:
+                        h["escapes"][:n_esc].copy_(c["escapes"][:n_esc], non_blocking=True)
+                    nbytes += 7 * m + D * half + 4 * w + 8 * n_esc
+                    s["copied"].record(self.copy_stream)
+                    if consume is not None:
+                        first_row = np.concatenate([[0], np.cumsum(tot["hits"])]).astype(np.int64)
+                        cut = lambda k, dt: [h[k].numpy().view(dt)[first_row[d]:first_row[d + 1]] for d in range(D)]  # noqa: E731
+                        chunk = HostChunk(sim.lib, i, first_i, n_i, D, tot, ev_base, t_base, compact={
+                            "narrow": True, "charge": cut("charge", np.float32), "pos_lo": cut("pos_lo", np.uint16),
+                            "pos_hi": cut("pos_hi", np.uint8),
+                            "counts": h["counts"].numpy()[:D * half].reshape(D, half),
+                            "escapes": h["escapes"].numpy().view(np.uint64)[:n_esc],
+                            "accepted": h["accepted"].numpy().view(np.uint32)[:w]})
                 elif self.compact:
                     c, h = s["cmp"], s["h_cmp"]
                     pf, m = c["plane_first"], sum(tot["hits"])
@@ -239,6 +271,7 @@ class ChunkPipeline:
             finish(pending)
         self.copy_stream.synchronize()
         return rows, nbytes
+
 
 
 def shard_range(n_total: int, rank: int, world: int):

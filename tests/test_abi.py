@@ -30,8 +30,8 @@ def test_struct_sizes_match_header_layout():
     assert ctypes.sizeof(native.PtbHitSlab) == 48
     assert ctypes.sizeof(native.PtbBases) == 16 + 8 * 32
     assert ctypes.sizeof(native.PtbTotals) == 8 * 32 + 8 * 5 + 8 + 8 * 32
-    assert ctypes.sizeof(native.PtbCompactOut) == 24 + 8 * 33
-    assert ctypes.sizeof(native.PtbRun) == 32 + 8 + 72 + 48 * 32 + 8 * 5 + 8 * 32 + 24 + 8 * 33
+    assert ctypes.sizeof(native.PtbCompactOut) == 24 + 8 * 33 + 40
+    assert ctypes.sizeof(native.PtbRun) == 32 + 8 + 72 + 48 * 32 + 8 * 5 + 8 * 32 + 24 + 8 * 33 + 40
 
 
 def test_struct_layout_agrees_with_a_c_compiler(tmp_path):

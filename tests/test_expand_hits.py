@@ -1,5 +1,5 @@
-"""ptb_expand_hits (host code of libptb_b200, no GPU needed): the compressed-row form of a hit table (PtbCompactOut in
-include/ptb.h) back into the reference's 18-byte records (main/device.py:20-28, 156-165)."""
+"""ptb_expand_hits / ptb_expand_hits_narrow (host code of libptb_b200, no GPU needed): both compressed-row forms of a hit
+table (PtbCompactOut in include/ptb.h) back into the reference's 18-byte records (main/device.py:20-28, 156-165)."""
 import numpy as np
 import pytest
 
@@ -24,6 +24,28 @@ def _case(n, seed, max_count=5, p_accept=0.7):
     return counts, acc, words, hits, (col, row, q)
 
 
+def _plane(form, counts, words, hits, cols, plane=3):
+    """The host arrays of one plane in the wide or the narrow form (engine.plane_of)."""
+    if form == "wide":
+        return {"narrow": False, "hits": hits, "counts": counts, "accepted": words}
+    col, row, q = cols
+    pos = (col | (row << np.uint64(12))).astype(np.uint32)
+    c = np.minimum(np.concatenate([counts, np.zeros(len(counts) & 1, np.uint8)]), 15)
+    # counts of 15 and more stand on the escape list, in no particular order, among entries of other planes
+    big = np.flatnonzero(counts >= 15)
+    esc = (counts[big].astype(np.uint64) << np.uint64(48)) | (np.uint64(plane) << np.uint64(40)) | big.astype(np.uint64)
+    other = (np.uint64(77) << np.uint64(48)) | (np.uint64(plane + 1) << np.uint64(40)) | big.astype(np.uint64)
+    esc = np.random.RandomState(0).permutation(np.concatenate([esc, other]))
+    return {"narrow": True, "charge": q, "pos_lo": (pos & 0xFFFF).astype(np.uint16), "pos_hi": (pos >> 16).astype(np.uint8),
+            "counts": (c[0::2] | (c[1::2] << 4)).astype(np.uint8), "accepted": words, "escapes": esc, "plane": plane}
+
+
+def _short(p):
+    """The same plane with its last row cut off (counts then promise one row too many)."""
+    keys = ("charge", "pos_lo", "pos_hi") if p["narrow"] else ("hits",)
+    return dict(p, **{k: p[k][:-1] for k in keys})
+
+
 def _expected(counts, acc, cols, event_base):
     # event number of particle k: 1 + accepted particles before k (main/device.py:159,164-165)
     ev_k = event_base + 1 + np.concatenate([[0], np.cumsum(acc)[:-1]]) if len(acc) else np.zeros(0, np.int64)
@@ -33,32 +55,45 @@ def _expected(counts, acc, cols, event_base):
     return out
 
 
+@pytest.mark.parametrize("form", ["wide", "narrow"])
 @pytest.mark.parametrize("n,threads", [(0, 0), (1, 1), (31, 0), (32, 0), (33, 2), (1000, 0), (600_001, 0), (600_001, 5)])
-def test_expand_matches_the_reference_numbering(n, threads):
+def test_expand_matches_the_reference_numbering(n, threads, form):
     lib = native.load()
-    counts, acc, words, hits, cols = _case(n, seed=n + 1)
-    got = expand_compact(lib, hits, counts, words, n, event_base=12345, threads=threads)
+    counts, acc, words, hits, cols = _case(n, seed=n + 1, max_count=40 if form == "narrow" else 5)
+    got = expand_compact(lib, _plane(form, counts, words, hits, cols), n, event_base=12345, threads=threads)
     want = _expected(counts, acc, cols, 12345)
     assert got.tobytes() == want.tobytes()
 
 
-def test_bits_beyond_the_range_do_not_count_and_mismatch_is_refused():
+@pytest.mark.parametrize("form", ["wide", "narrow"])
+def test_bits_beyond_the_range_do_not_count_and_mismatch_is_refused(form):
     lib = native.load()
     n = 70
     counts, acc, words, hits, cols = _case(n, seed=5)
     words = words.copy()
     words[-1] |= np.uint32(0xFFFFFFFF) << np.uint32(n - 64)      # garbage above particle n-1
-    got = expand_compact(lib, hits, counts, words, n, event_base=0)
+    plane = _plane(form, counts, words, hits, cols)
+    got = expand_compact(lib, plane, n, event_base=0)
     assert got.tobytes() == _expected(counts, acc, cols, 0).tobytes()
     with pytest.raises(PtbError):
-        expand_compact(lib, hits[:-1], counts, words, n, event_base=0)
+        expand_compact(lib, _short(plane), n, event_base=0)
 
 
-def test_expand_into_a_caller_buffer():
+@pytest.mark.parametrize("form", ["wide", "narrow"])
+def test_expand_into_a_caller_buffer(form):
     lib = native.load()
     counts, acc, words, hits, cols = _case(5000, seed=9)
     dest = np.zeros(len(hits) + 10, dtype=HITS_DTYPE)
     view = dest[3:3 + len(hits)]
-    expand_compact(lib, hits, counts, words, 5000, event_base=7, out=view)
+    expand_compact(lib, _plane(form, counts, words, hits, cols), 5000, event_base=7, out=view)
     assert view.tobytes() == _expected(counts, acc, cols, 7).tobytes()
     assert dest[:3].tobytes() == bytes(54) and dest[3 + len(hits):].tobytes() == bytes(7 * 18)
+
+
+def test_narrow_count_of_15_without_an_escape_entry_is_refused():
+    lib = native.load()
+    counts, acc, words, hits, cols = _case(500, seed=3, max_count=40)
+    plane = _plane("narrow", counts, words, hits, cols)
+    assert (counts >= 15).any()
+    with pytest.raises(PtbError):
+        expand_compact(lib, dict(plane, escapes=plane["escapes"][:0]), 500, event_base=0)

@@ -17,17 +17,32 @@ def _sim(setup, **kw):
     return Simulator(beam, devices, materials, **kw)
 
 
+def _count_sums(c):
+    """Rows per plane that the counts of a host-side PtbCompactOut promise (bytes; or nibble pairs + escape entries)."""
+    if not c.get("narrow"):
+        return [int(x.sum(dtype=np.int64)) for x in c["counts"]]
+    out = []
+    for d, x in enumerate(c["counts"]):
+        nib = np.stack([x & 15, x >> 4], axis=1).reshape(-1).astype(np.int64)
+        esc = c["escapes"][((c["escapes"] >> np.uint64(40)) & np.uint64(0xff)) == np.uint64(d)]
+        assert int((nib == 15).sum()) == len(esc)
+        out.append(int(nib[nib < 15].sum() + (esc >> np.uint64(48)).astype(np.int64).sum()))
+    return out
+
+
+@pytest.mark.parametrize("form", [True, "narrow"])
 @pytest.mark.parametrize("name,first,n", [("c1", 0, 50_003), ("c3", 77, 40_000), ("c4", 1_000_000_007, 33_333),
-                                          ("c1", 5, 1), ("c1", 0, 31)])
-def test_compact_tables_equal_the_slab_tables(name, first, n):
-    """Production mode: the same particles through both output forms; the expanded rows must be byte-identical, the
-    count bytes must add up to the rows of every plane, the trigger words to the accepted particles."""
+                                          ("c1", 5, 1), ("c1", 0, 31), ("c1", 64, 32)])
+def test_compact_tables_equal_the_slab_tables(name, first, n, form):
+    """Production mode: the same particles through the slab form and both compressed-row forms; the expanded rows must
+    be byte-identical, the counts must add up to the rows of every plane, the trigger words to the accepted particles."""
     sim = _sim(H.setup(name, n))
     a = sim.run(first, n, seed=2024)
-    b = sim.run(first, n, seed=2024, compact=True)
+    b = sim.run(first, n, seed=2024, compact=form)
     assert a.totals["hits"] == b.totals["hits"] and b.totals["error"] == 0
     c = b.compact_host()
-    assert [int(x.sum()) for x in c["counts"]] == b.totals["hits"]
+    assert bool(c.get("narrow")) == (form == "narrow")
+    assert _count_sums(c) == b.totals["hits"]
     mask = np.unpackbits(c["accepted"].view(np.uint8), bitorder="little")[:n]
     assert int(mask.sum()) == b.totals["accepted"]
     for d in range(sim.D):
@@ -42,13 +57,14 @@ def test_compact_deterministic_vs_oracle_with_event_base():
     sim = _sim(setup)
     lo = 5000
     first = sim.run(0, lo, injected=H.injected_for(sim, run, 0, lo))
-    second = sim.run(lo, n - lo, injected=H.injected_for(sim, run, lo, n - lo), bases_in=first.bases_out, compact=True)
-    assert second.event_base == int(run.variates.accepted[:lo].sum())
-    for d in range(sim.D):
-        want = run.hits[d][len(first.hits_numpy(d)):]
-        got = second.hits_numpy(d)
-        for f in ("event_number", "column", "row", "frame"):
-            assert np.array_equal(got[f], want[f]), (d, f)
+    for form in (True, "narrow"):
+        second = sim.run(lo, n - lo, injected=H.injected_for(sim, run, lo, n - lo), bases_in=first.bases_out, compact=form)
+        assert second.event_base == int(run.variates.accepted[:lo].sum())
+        for d in range(sim.D):
+            want = run.hits[d][len(first.hits_numpy(d)):]
+            got = second.hits_numpy(d)
+            for f in ("event_number", "column", "row", "frame"):
+                assert np.array_equal(got[f], want[f]), (form, d, f)
 
 
 def test_compact_with_pool_rounds_wide_clusters_and_count_overflow():
@@ -76,6 +92,54 @@ def test_compact_with_pool_rounds_wide_clusters_and_count_overflow():
     sim = Simulator(beam, devices, materials)
     with pytest.raises(PtbError, match="255"):
         sim.run(0, 600, seed=5, compact=True)          # (the undersized default buffers are retried first)
+    assert not sim.narrow_ok()                         # 60000 columns do not fit 12 bits: refused by the library
+
+
+def test_narrow_form_with_more_than_15_rows_per_particle():
+    """Pixels well below the cloud width: several rows per particle, some beyond 15.  Their counts travel on the escape
+    list and the expanded tables still equal the slab tables; with an escape list that is too short the device says so
+    and the pipeline retries the chunk; a geometry where such counts are the rule is steered to the wide form."""
+    from pytestbeam_b200 import config as cfg
+    from pytestbeam_b200.engine import Simulator
+    from pytestbeam_b200.pipeline import ChunkPipeline
+    n = 20_000
+    sim = whole = None
+    for pitch in (12.0, 11.0, 10.0, 9.0):                 # the first pitch at which a few hundred particles exceed 15 rows
+        setup = cfg.c1(n)
+        setup["devices"]["mimosa26_p3"].update(column=int(21000 / pitch), row=int(10500 / pitch), column_pitch=pitch,
+                                               row_pitch=pitch, threshold=0)
+        beam, devices, materials, names = cfg.flatten(setup)
+        sim = Simulator(beam, devices, materials)
+        whole = sim.run(0, n, seed=3, capacities=[64 * n] * sim.D)
+        wide = sim.run(0, n, seed=3, capacities=[64 * n] * sim.D, compact=True).compact_host()["counts"]
+        big = int((wide >= 15).sum())                     # (particle, plane) pairs whose count needs an escape entry
+        if 150 <= big <= 900:
+            break
+    else:
+        pytest.skip("no pitch of the list gives a few hundred clusters beyond 15 rows")
+    caps = [64 * n] * sim.D
+    b = sim.run(0, n, seed=3, capacities=caps, compact="narrow")
+    assert b.totals["escapes"] == big and b.totals["error"] == 0
+    assert _count_sums(b.compact_host()) == whole.totals["hits"]
+    for d in range(sim.D):
+        assert b.hits_numpy(d).tobytes() == whole.hits_numpy(d).tobytes(), d
+    assert sim.narrow_ok()
+    pipe = ChunkPipeline(sim, 5000, host=True, seed=3, capacities=[64 * 5000] * sim.D)
+    assert pipe.narrow
+    for s in pipe.sets:                                   # an escape list far too short for these clusters
+        s["cmp"]["escapes"] = s["cmp"]["escapes"][:1]
+    got = [[] for _ in range(sim.D)]
+    pipe.run_to_host(0, 4, consume=lambda c: [got[d].append(c.records(d).copy()) for d in range(sim.D)])
+    assert pipe.retries == 4
+    for d in range(sim.D):
+        assert np.concatenate(got[d]).tobytes() == whole.hits_numpy(d).tobytes(), d
+    # 8 um pixels: a dozen rows per particle; the pilot finds the escape list too small and the pipeline stays wide
+    setup = cfg.c1(n)
+    setup["devices"]["mimosa26_p3"].update(column=2500, row=1250, column_pitch=8.0, row_pitch=8.0, threshold=0)
+    beam, devices, materials, names = cfg.flatten(setup)
+    sim8 = Simulator(beam, devices, materials)
+    if not sim8.narrow_ok():
+        assert not ChunkPipeline(sim8, 5000, host=True, seed=3).narrow
 
 
 @pytest.mark.parametrize("chunk,n_total", [(20_000, 100_000), (30_000, 100_001), (64, 1000)])
@@ -84,8 +148,9 @@ def test_pipeline_to_host_equals_one_call(chunk, n_total):
     sim = _sim(H.setup("c4", n_total))
     first, seed = 12_345, 77
     whole = sim.run(first, n_total, seed=seed)
-    for compact in (True, False):
-        pipe = ChunkPipeline(sim, chunk, host=True, seed=seed, compact=compact)
+    for compact, narrow in ((True, True), (True, False), (False, False)):
+        pipe = ChunkPipeline(sim, chunk, host=True, seed=seed, compact=compact, narrow=narrow)
+        assert pipe.narrow == narrow
         got = [[] for _ in range(sim.D)]
         bases = []
 
@@ -99,7 +164,8 @@ def test_pipeline_to_host_equals_one_call(chunk, n_total):
         assert [b[0] for b in bases] == list(range(first, first + n_total, chunk))
         assert sum(b[1] for b in bases) == n_total
         for d in range(sim.D):
-            assert np.concatenate(got[d]).tobytes() == whole.hits_numpy(d).tobytes(), (compact, d)
+            assert np.concatenate(got[d]).tobytes() == whole.hits_numpy(d).tobytes(), (compact, narrow, d)
+    assert ChunkPipeline(sim, chunk, host=True, seed=seed).narrow        # the default for a telescope that fits
 
 
 def test_pipeline_retries_a_chunk_that_overflows_instead_of_raising():
@@ -109,14 +175,14 @@ def test_pipeline_retries_a_chunk_that_overflows_instead_of_raising():
     n_total, chunk, seed = 60_000, 20_000, 5
     sim = _sim(H.setup("c1", n_total))
     whole = sim.run(0, n_total, seed=seed)
-    for compact in (True, False):
-        pipe = ChunkPipeline(sim, chunk, host=True, seed=seed, compact=compact, capacities=[500] * sim.D,
+    for compact, narrow in ((True, True), (True, False), (False, False)):
+        pipe = ChunkPipeline(sim, chunk, host=True, seed=seed, compact=compact, narrow=narrow, capacities=[500] * sim.D,
                              scratch_rows=[700] * sim.D)
         got = [[] for _ in range(sim.D)]
         pipe.run_to_host(0, 3, consume=lambda c: [got[d].append(c.records(d).copy()) for d in range(sim.D)])
         assert pipe.retries == 3
         for d in range(sim.D):
-            assert np.concatenate(got[d]).tobytes() == whole.hits_numpy(d).tobytes(), (compact, d)
+            assert np.concatenate(got[d]).tobytes() == whole.hits_numpy(d).tobytes(), (compact, narrow, d)
     dev_pipe = ChunkPipeline(sim, chunk, seed=seed, capacities=[500] * sim.D, scratch_rows=[700] * sim.D)
     dev_pipe.run(0, 3)
     from pytestbeam_b200 import native as N
