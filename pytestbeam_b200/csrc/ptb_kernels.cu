@@ -1095,8 +1095,9 @@ __global__ void __launch_bounds__(256, 8) k_gather(const __grid_constant__ Gathe
         const unsigned nz = __ballot_sync(FULL, n_l != 0);
         const int      R = __popc(nz);
         const int      from = lane < R ? (int)__fns(nz, 0, lane + 1) : 0;
-        const int      endR = lane < R ? __shfl_sync(FULL, cum, from) : 0x7fffffff;
-        const int      firstR = endR - (int)__shfl_sync(FULL, (unsigned)n_l, from);
+        const int      end_from = __shfl_sync(FULL, cum, from);           // (every lane takes part in the shuffles)
+        const int      endR = lane < R ? end_from : 0x7fffffff;
+        const int      firstR = end_from - (int)__shfl_sync(FULL, (unsigned)n_l, from);
         const unsigned long long dstAll = dst_l + (narrow ? dense_l : (compact && lane < D) ? G.cmp.plane_first[lane] : 0ull);
         const unsigned long long srcR = __shfl_sync(FULL, src_l, from) - (unsigned long long)firstR;
         const unsigned long long dstR = __shfl_sync(FULL, dstAll, from) - (unsigned long long)firstR;
