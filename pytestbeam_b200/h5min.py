@@ -294,6 +294,29 @@ class TableWriter:
                 buf, off = buf[done:], off + done
             self.nrows += len(a)
 
+    def append_from_file(self, src_fd: int, extents: list) -> None:
+        """Append rows that already lie in another file as raw records: extents = [(offset, bytes)] in row order
+        (TableReader.extents).  The bytes move inside the kernel (copy_file_range) where the platform allows it --
+        nothing passes through this process -- and through a bounce buffer otherwise."""
+        isz, fd = self.dtype.itemsize, self._f.fileno()
+        self._f.flush()
+        for off, nbytes in extents:
+            if nbytes % isz:
+                raise ValueError("extent is not a whole number of records")
+            dst, left = self._row_addr(self.nrows), nbytes
+            while left:
+                try:
+                    done = os.copy_file_range(src_fd, fd, min(left, 1 << 30), off, dst)
+                except (OSError, AttributeError):
+                    done = 0
+                if done <= 0:                                  # other file system, old kernel: read + positioned write
+                    buf = os.pread(src_fd, min(left, 1 << 24), off)
+                    if not buf:
+                        raise ValueError("source file ends inside an extent")
+                    done = os.pwrite(fd, buf, dst)
+                off, dst, left = off + done, dst + done, left - done
+            self.nrows += nbytes // isz
+
     def reserve(self, n: int) -> np.ndarray:
         """A writable view of rows [nrows, nrows+n) of the file (numpy memmap); the rows count as appended."""
         n = int(n)
@@ -353,13 +376,19 @@ def write_table(path: str, name: str, table: np.ndarray, chunk_rows: int | None 
 
 
 def concatenate_tables(dest: str, name: str, parts: list, dtype, chunk_rows: int = 65536, title: str = "") -> int:
-    """Append the table `name` of every file in `parts`, in order, to a new file `dest`, piece by piece (no part is
-    ever held in memory as a whole).  Returns the number of rows."""
+    """Append the table `name` of every file in `parts`, in order, to a new file `dest`: the parts' raw records are
+    copied extent by extent, file to file (no part is read into this process, let alone held as a whole).  Returns the
+    number of rows."""
     with TableWriter(dest, name, dtype, chunk_rows, title) as w:
         for p in parts:
             with TableReader(p) as r:
-                for piece in r.iter_rows(name, 1 << 20):
-                    w.append(piece)
+                if r.dtype_of(name) != w.dtype:
+                    raise ValueError(f"{p}: table {name!r} has another record type")
+                fd = os.open(p, os.O_RDONLY)
+                try:
+                    w.append_from_file(fd, r.extents(name))
+                finally:
+                    os.close(fd)
         return w.nrows
 
 
@@ -616,6 +645,38 @@ class TableReader:
 
     def nrows(self, name: str) -> int:
         return int(self._describe(name)["dims"][0])
+
+    def dtype_of(self, name: str) -> np.dtype:
+        return self._describe(name)["dtype"]
+
+    def extents(self, name: str) -> list:
+        """[(file offset, bytes)] of the raw records of a rank-1 dataset in row order, neighbouring chunks merged."""
+        info = self._describe(name)
+        if len(info["dims"]) != 1:
+            raise ValueError("extents is for rank-1 datasets")
+        n, isz = info["dims"][0], info["dtype"].itemsize
+        if n == 0:
+            return []
+        if info["kind"] == "contiguous":
+            return [(self._b.base + info["addr"], n * isz)]
+        crow, out = info["chunk"][0], []
+        if info["chunk"][-1] != isz:
+            raise ValueError("chunk element size does not match the datatype")
+        expect = 0
+        for row, addr, nbytes in self._chunks(info):
+            if nbytes != crow * isz or row != expect:
+                raise ValueError("the chunks do not tile the dataspace")
+            m = min(crow, n - row) * isz
+            if m <= 0:
+                break
+            if out and out[-1][0] + out[-1][1] == addr:
+                out[-1] = (out[-1][0], out[-1][1] + m)
+            else:
+                out.append((addr, m))
+            expect = row + crow
+        if expect < n:
+            raise ValueError("the chunks do not cover the dataspace")
+        return out
 
     def iter_rows(self, name: str, max_rows: int = 1 << 20):
         """The rows of a rank-1 dataset in pieces of at most max_rows (views of the mapped file, or small copies)."""

@@ -113,7 +113,8 @@ def stream_fused(sim: Simulator, first: int, n: int, seed: int, sink, event_base
                  chunk: int = CHUNK) -> dict:
     """Particles [first, first+n) through the fused GPU path into `sink`.  Returns the summed counters."""
     chunk = max(32, min(int(chunk), n))
-    pipe = ChunkPipeline(sim, chunk, host=True, seed=seed)
+    # a range that fits one chunk needs one buffer set (pinning host memory is the largest fixed cost of a small run)
+    pipe = ChunkPipeline(sim, chunk, host=True, seed=seed, n_buffers=1 if n <= chunk else 2)
     pipe.set_bases(event_base, time_base)
     tot = {"hits": [0] * sim.D, "accepted": 0, "time_sum": 0}
     inner = _consume_into(sink)
