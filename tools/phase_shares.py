@@ -17,9 +17,14 @@ def find(txt):
 # (code inlined from describe() / profile_entry() is attributed to its call site in the kernel)
 marks = [('prolog', find('__device__ __forceinline__ void digitise_group')), ('fetch', find('cp_async_wait_all();   //')),
          ('descriptors', find('// ---- cluster descriptors')), ('census+reserve', find('{   // census, one packed word')),
+         ('work list', find('// ---- the work list')), ('stage 1', find('// ---- stage 1')),
+         ('stage 2', find('// ---- stage 2')), ('emit', find('// kept pixels of my particle up to my slot')),
+         ('plane end', find('if (!more) break;')), ('epilog', find('// ---- per-group counters for k_scan')),
+         ('ticket loop', find('k_digitise(const __grid_constant__')),
+         # (markers of the pooled version, before the two-stage pixel walk)
          ('rounds setup', find('// inclusive prefixes of the profile entries')), ('phase A', find('// ---- phase A')),
-         ('phase B', find('// ---- phase B')), ('emit', find('// kept pixels of my particle in this step')),
-         ('plane end', find('if (o_end >= 32) break;')), ('epilog', find('// ---- per-group counters for k_scan')), ('ticket loop', find('k_digitise(const __grid_constant__'))]
+         ('phase B', find('// ---- phase B')), ('emit (pooled)', find('// kept pixels of my particle in this step'))]
+marks = [m for m in marks if m[1]]
 marks.sort(key=lambda m: m[1])
 lines = open(src_csv).read().split('\n')
 starts = [i for i, l in enumerate(lines) if l.startswith('"Kernel Name"')] + [len(lines)]
