@@ -169,10 +169,16 @@ def _is_hit_tuple(hit_data) -> bool:
         return False
 
 
+LAST_RUN: dict = {}     # counters of the most recent calculate_device_hit / device_hits (the front end's run record)
+
+
 def _run(beam: dict, devices: list, hit_data, sink) -> None:
     n, D = int(beam["nmb_particles"]), len(devices)
+    chunk = int(beam.get("chunk") or CHUNK)          # optional key of the beam block; the default suits any size
+    LAST_RUN.clear()
     if isinstance(hit_data, HitTables) and not hit_data.materialised:
-        stream_fused(hit_data.sim, 0, n, hit_data.seed, sink)
+        tot = stream_fused(hit_data.sim, 0, n, hit_data.seed, sink, chunk=chunk)
+        LAST_RUN.update(route="fused", seed=hit_data.seed, electrons=n, chunk=min(chunk, n), **tot)
         return
     if not _is_hit_tuple(hit_data):
         raise TypeError("hit_data must be the 8-tuple of hit.tracks: (energy, anglex, angley, x, y, z, time_stamp, "
@@ -184,7 +190,8 @@ def _run(beam: dict, devices: list, hit_data, sink) -> None:
     else:
         # a foreign tuple: the digitisation needs the device geometry only, the material entries stay unused
         sim, seed = Simulator(beam, devices, [dict(SILICON) for _ in devices]), _seed_of(beam)
-    stream_from_arrays(sim, hit_data[3], hit_data[4], hit_data[7], seed, sink)
+    stream_from_arrays(sim, hit_data[3], hit_data[4], hit_data[7], seed, sink, chunk=chunk)
+    LAST_RUN.update(route="calc_position", seed=seed, electrons=n, chunk=min(chunk, n))
 
 
 def device_hits(beam: dict, devices: list, hit_data, log=None) -> list:

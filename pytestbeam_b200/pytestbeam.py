@@ -36,6 +36,11 @@ def load_job(workdir: str = ".") -> Job:
             return yaml.full_load(fh)
 
     setup, catalogue = read("setup.yml"), read("material.yml")
+    # optional keys beyond the reference's schema; their defaults are the only values there are
+    if str(setup.get("backend", "cuda")).lower() != "cuda":
+        raise ValueError("backend: this package runs on CUDA (sm_100a) only; there is no CPU path")
+    if str(setup.get("precision", "f64")).lower() not in ("f64", "float64", "double"):
+        raise ValueError("precision: the physics arithmetic is fp64 (the reference's); no other precision is built")
     names = list(setup["devices"])
     devices = [setup["devices"][n] for n in names]
     prefix = setup.get("data_output") or "output_data/"
@@ -45,14 +50,36 @@ def load_job(workdir: str = ".") -> Job:
                bool(setup.get("saving_tracks")), bool(setup.get("plotting")))
 
 
+def write_run_record(job: Job, seconds: float, log) -> str:
+    """``<folder>run_record.json``: what was simulated and how fast (no counterpart in the reference, which logs
+    milestones only)."""
+    import json
+    last = dict(device.LAST_RUN)
+    hits = last.get("hits") or []
+    n = int(job.beam["nmb_particles"])
+    rec = {"electrons": n, "seconds": seconds, "electrons_per_s": n / seconds if seconds > 0 else None,
+           "hits_per_s": sum(hits) / seconds if hits and seconds > 0 else None, "seed": last.get("seed"),
+           "route": last.get("route"), "chunk": last.get("chunk"), "retried_chunks": last.get("retries"),
+           "device_to_host_bytes": last.get("d2h_bytes"), "rows": dict(zip(job.names, hits)),
+           "files": [f"{name}_dut.h5" for name in job.names] + (["particle_tracks.h5"] if job.saving_tracks else [])}
+    path = job.folder + "run_record.json"
+    with open(path, "w") as fh:
+        json.dump(rec, fh, indent=1)
+    log.info("%d electrons in %.2f s (%.3g electrons/s); record in %s" % (n, seconds, n / max(seconds, 1e-9), path))
+    return path
+
+
 def run_job(job: Job, log) -> None:
+    import time
     if job.folder.endswith("/"):
         os.makedirs(job.folder, exist_ok=True)
+    t0 = time.perf_counter()
     tables = hit.tracks(job.beam, job.devices, job.materials, log)
     if job.saving_tracks:
         log.info("Saving tracks")
         hit.create_output_tracks(tables, job.folder)
     device.calculate_device_hit(job.beam, job.devices, tables, job.names, job.folder, log)
+    write_run_record(job, time.perf_counter() - t0, log)
     if job.plotting:
         log.info("plots are not produced here: hand the *_dut.h5 files and the hit_tables tuple to the reference's "
                  "main.plotting.plot_default")

@@ -22,11 +22,17 @@ def test_entry_point_writes_the_reference_files(tmp_path):
     setup["plotting"] = False
     (tmp_path / "setup.yml").write_text(yaml.safe_dump(setup, sort_keys=False))
     (tmp_path / "material.yml").write_text(yaml.safe_dump(cfg.default_material()))
+    setup["beam"]["chunk"] = 7_000                      # optional key: five chunks, the last one short
+    (tmp_path / "setup.yml").write_text(yaml.safe_dump(setup, sort_keys=False))
     pytestbeam.main(str(tmp_path))
     beam, devices, materials, names = cfg.flatten(setup)
     sim = Simulator(beam, devices, materials)
     ref = sim.run(0, 30_000, seed=777, write_tracks=True)
     out = tmp_path / "output_data"
+    import json
+    rec = json.loads((out / "run_record.json").read_text())
+    assert rec["electrons"] == 30_000 and rec["seed"] == 777 and rec["chunk"] == 7_000 and rec["route"] == "fused"
+    assert [rec["rows"][nm] for nm in names] == ref.totals["hits"] and rec["electrons_per_s"] > 0
     for d, name in enumerate(names):
         got = h5min.read_table(str(out / f"{name}_dut.h5"), "Hits")
         assert got.tobytes() == ref.hits_numpy(d).tobytes(), name
@@ -70,3 +76,14 @@ def test_foreign_arrays_with_explicit_mask():
         assert abs(len(parts[d]) - len(run.hits[d])) < 0.1 * len(run.hits[d]) + 50
         if len(parts[d]):
             assert parts[d]["event_number"].max() <= int(run.variates.accepted.sum()) + 1
+
+
+def test_optional_keys_refuse_what_is_not_built(tmp_path):
+    from pytestbeam_b200 import pytestbeam
+    for key, value in (("backend", "cpu"), ("precision", "f32")):
+        setup = cfg.c1(100)
+        setup[key] = value
+        (tmp_path / "setup.yml").write_text(yaml.safe_dump(setup, sort_keys=False))
+        (tmp_path / "material.yml").write_text(yaml.safe_dump(cfg.default_material()))
+        with pytest.raises(ValueError, match=key):
+            pytestbeam.load_job(str(tmp_path))
