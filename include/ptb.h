@@ -52,6 +52,7 @@ extern "C" {
 #define PTB_E_INVALID (-1)   /* bad argument / unsupported geometry (see ptb_last_error) */
 #define PTB_E_CUDA (-2)      /* a CUDA runtime call failed */
 #define PTB_E_NOMEM (-3)
+#define PTB_E_IO (-4)        /* a write to the caller's file descriptor failed (ptb_expand_hits*_fd) */
 
 /* bits of PtbTotals.error (device-detected) */
 #define PTB_DEV_SCRATCH_OVERFLOW 1u /* the workspace's scratch rows of a plane ran out; PtbTotals.reserved is exact */
@@ -245,6 +246,16 @@ int64_t ptb_expand_hits(const uint64_t *hits, const uint8_t *counts, const uint3
 int64_t ptb_expand_hits_narrow(const float *charge, const uint16_t *pos_lo, const uint8_t *pos_hi, const uint8_t *counts4,
                                const uint64_t *escapes, uint64_t n_escapes, int32_t plane, const uint32_t *accepted,
                                uint64_t n, int64_t event_base, uint64_t n_rows_expected, void *out, int32_t threads);
+
+/* Both expansions with a file instead of a buffer as destination: the plane's records go to file descriptor fd from
+ * byte file_offset on, written block by block (positioned writes of 256 KiB that never leave the writing core's cache)
+ * -- the dataset region of a *_dut.h5 file is filled without staging the table in memory.  PTB_E_IO when a write fails. */
+int64_t ptb_expand_hits_fd(const uint64_t *hits, const uint8_t *counts, const uint32_t *accepted, uint64_t n,
+                           int64_t event_base, uint64_t n_rows_expected, int32_t fd, uint64_t file_offset, int32_t threads);
+int64_t ptb_expand_hits_narrow_fd(const float *charge, const uint16_t *pos_lo, const uint8_t *pos_hi,
+                                  const uint8_t *counts4, const uint64_t *escapes, uint64_t n_escapes, int32_t plane,
+                                  const uint32_t *accepted, uint64_t n, int64_t event_base, uint64_t n_rows_expected,
+                                  int32_t fd, uint64_t file_offset, int32_t threads);
 
 /*
  * Checksums of rows [0, n) of a hit table, added (modulo 2^64) to out_dev[0..6]:

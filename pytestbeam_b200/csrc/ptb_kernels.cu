@@ -28,6 +28,7 @@
 #include <cstring>
 #include <new>
 #include <thread>
+#include <unistd.h>
 #include <vector>
 
 #include "ptb_device.cuh"
@@ -1385,16 +1386,68 @@ static double moyal_density(double delta, double loc, double scale)
 // F(lambda) = P(Lambda <= lambda) for the Moyal law = erfc(exp(-lambda/2)/sqrt 2)
 static double moyal_cdf(double lam) { return erfc(exp(-lam / 2) / sqrt(2.0)); }
 
-// Rows: how a compressed row is read (hit i of the plane -> column, row, charge bits); Counts: rows of particle k.
-template <class Rows, class Counts>
+// Where the expanded 18-byte records of one thread go: straight to memory, or block by block into a file.  A thread
+// writes its rows strictly in order, so the file writer only ever holds one partly filled block.
+struct RowsToMemory {
+    unsigned char *dst;
+    unsigned char *at(uint64_t i) { return dst + i * 18; }
+    bool           finish() { return true; }
+};
+
+#ifndef PTB_FILE_BLOCK_ROWS
+#define PTB_FILE_BLOCK_ROWS 233016   /* 4 MiB of records: measured best on a disk-backed page cache (256 KiB .. 16 MiB tried) */
+#endif
+struct RowsToFile {
+    static constexpr size_t BLOCK_ROWS = PTB_FILE_BLOCK_ROWS;   // stays in the core's cache until pwrite copies it out
+    int                     fd;
+    uint64_t                offset;                // file position of row 0 of the plane
+    std::vector<unsigned char> buf;
+    uint64_t                first = 0;
+    size_t                  used = 0;
+    bool                    ok = true;
+    RowsToFile(int fd_, uint64_t offset_) : fd(fd_), offset(offset_), buf(BLOCK_ROWS * 18) {}
+    void flush()
+    {
+        const unsigned char *p = buf.data();
+        size_t               left = used * 18;
+        uint64_t             at = offset + first * 18;
+        while (left && ok) {
+            const ssize_t done = pwrite(fd, p, left, (off_t)at);
+            if (done <= 0) {
+                ok = false;
+                break;
+            }
+            p += done;
+            at += (uint64_t)done;
+            left -= (size_t)done;
+        }
+        used = 0;
+    }
+    unsigned char *at(uint64_t i)
+    {
+        if (used == BLOCK_ROWS) flush();
+        if (used == 0) first = i;
+        return buf.data() + 18 * used++;
+    }
+    bool finish()
+    {
+        if (used) flush();
+        return ok;
+    }
+};
+
+// Rows: how a compressed row is read (hit i of the plane -> column, row, charge bits); Counts: rows of particle k;
+// make_out(): the per-thread destination (RowsToMemory / RowsToFile).
+template <class Rows, class Counts, class MakeOut>
 static int64_t expand_rows(const Rows &rows_of, const Counts &count_of, const uint32_t *accepted, uint64_t n,
-                           int64_t event_base, uint64_t n_rows_expected, void *out, int32_t threads)
+                           int64_t event_base, uint64_t n_rows_expected, const MakeOut &make_out, int32_t threads)
 {
     int T = threads > 0 ? threads : (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
     const uint64_t words = (n + 31) / 32;
     T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)T, (words + 4095) / 4096));   // >= 128k particles per thread
     const uint64_t          per = (words + T - 1) / T;   // words per thread
     std::vector<uint64_t>   rows(T + 1, 0), acc(T + 1, 0);
+    std::vector<int>        failed(T, 0);
     auto range = [&](int t, uint64_t &k0, uint64_t &k1) {
         k0 = std::min<uint64_t>(n, per * 32 * (uint64_t)t);
         k1 = std::min<uint64_t>(n, k0 + per * 32);
@@ -1423,31 +1476,75 @@ static int64_t expand_rows(const Rows &rows_of, const Counts &count_of, const ui
         acc[t + 1] += acc[t];
     }
     if (rows[T] != n_rows_expected) return PTB_E_INVALID;
-    unsigned char *dst = (unsigned char *)out;
     auto expand_pass = [&](int t) {
         uint64_t k0, k1;
         range(t, k0, k1);
         uint64_t i = rows[t];
         int64_t  ev = event_base + 1 + (int64_t)acc[t];
+        auto     out = make_out();
         for (uint64_t k = k0; k < k1; ++k) {
             const unsigned c = count_of(k);
             for (unsigned j = 0; j < c; ++j, ++i) {
                 uint16_t col, row;
                 uint32_t q;
                 rows_of(i, col, row, q);
-                unsigned char *r = dst + i * 18;
-                const uint16_t frame = 0;
+                // event_number <i8 | frame <u2 = 0 | column <u2 | row <u2 | charge <f4 (main/device.py:20-28) as 8 + 8 + 2 bytes
+                unsigned char *r = out.at(i);
+                const uint64_t mid = ((uint64_t)col << 16) | ((uint64_t)row << 32) | ((uint64_t)(q & 0xffffu) << 48);
+                const uint16_t top = (uint16_t)(q >> 16);
                 memcpy(r, &ev, 8);
-                memcpy(r + 8, &frame, 2);
-                memcpy(r + 10, &col, 2);
-                memcpy(r + 12, &row, 2);
-                memcpy(r + 14, &q, 4);
+                memcpy(r + 8, &mid, 8);
+                memcpy(r + 16, &top, 2);
             }
             ev += (accepted[k >> 5] >> (k & 31)) & 1u;
         }
+        failed[t] = out.finish() ? 0 : 1;
     };
     run_threads(expand_pass);
+    for (int t = 0; t < T; ++t)
+        if (failed[t]) return PTB_E_IO;
     return (int64_t)rows[T];
+}
+
+// one plane of the wide / narrow compressed form as (rows_of, count_of) pairs handed to `go`
+template <class Go>
+static int64_t with_wide_plane(const uint64_t *hits, const uint8_t *counts, const Go &go)
+{
+    return go(
+        [=](uint64_t i, uint16_t &col, uint16_t &row, uint32_t &q) {
+            const uint64_t h = hits[i];
+            col = (uint16_t)h;
+            row = (uint16_t)(h >> 16);
+            q = (uint32_t)(h >> 32);
+        },
+        [=](uint64_t k) -> unsigned { return counts[k]; });
+}
+
+template <class Go>
+static int64_t with_narrow_plane(const float *charge, const uint16_t *pos_lo, const uint8_t *pos_hi, const uint8_t *counts4,
+                                 const uint64_t *escapes, uint64_t n_escapes, int32_t plane, const Go &go)
+{
+    // this plane's escaped counts, sorted by particle: a nibble of 15 is looked up here
+    std::vector<std::pair<uint64_t, unsigned>> esc;
+    for (uint64_t i = 0; i < n_escapes; ++i)
+        if ((int32_t)((escapes[i] >> 40) & 0xffu) == plane)
+            esc.emplace_back(escapes[i] & 0xffffffffffull, (unsigned)(escapes[i] >> 48));
+    std::sort(esc.begin(), esc.end());
+    const auto  *eb = esc.data();
+    const size_t ne = esc.size();
+    return go(
+        [=](uint64_t i, uint16_t &col, uint16_t &row, uint32_t &q) {
+            const uint32_t pos = (uint32_t)pos_lo[i] | ((uint32_t)pos_hi[i] << 16);   // column | row << 12
+            col = (uint16_t)(pos & 0xfffu);
+            row = (uint16_t)(pos >> 12);
+            memcpy(&q, &charge[i], 4);
+        },
+        [=](uint64_t k) -> unsigned {
+            const unsigned c = (counts4[k >> 1] >> ((k & 1) * 4)) & 15u;
+            if (c < 15u) return c;
+            const auto *it = std::lower_bound(eb, eb + ne, std::make_pair(k, 0u));
+            return (it != eb + ne && it->first == k) ? it->second : 0xffffffffu;   // no entry: the sum check fails
+        });
 }
 
 extern "C" {
@@ -1952,14 +2049,10 @@ int64_t ptb_expand_hits(const uint64_t *hits, const uint8_t *counts, const uint3
                         int64_t event_base, uint64_t n_rows_expected, void *out, int32_t threads)
 {
     if ((!hits && n_rows_expected) || !counts || !accepted || (!out && n_rows_expected)) return PTB_E_INVALID;
-    return expand_rows(
-        [=](uint64_t i, uint16_t &col, uint16_t &row, uint32_t &q) {
-            const uint64_t h = hits[i];
-            col = (uint16_t)h;
-            row = (uint16_t)(h >> 16);
-            q = (uint32_t)(h >> 32);
-        },
-        [=](uint64_t k) -> unsigned { return counts[k]; }, accepted, n, event_base, n_rows_expected, out, threads);
+    return with_wide_plane(hits, counts, [&](const auto &rows_of, const auto &count_of) {
+        return expand_rows(rows_of, count_of, accepted, n, event_base, n_rows_expected,
+                           [=] { return RowsToMemory{(unsigned char *)out}; }, threads);
+    });
 }
 
 int64_t ptb_expand_hits_narrow(const float *charge, const uint16_t *pos_lo, const uint8_t *pos_hi, const uint8_t *counts4,
@@ -1969,28 +2062,35 @@ int64_t ptb_expand_hits_narrow(const float *charge, const uint16_t *pos_lo, cons
     if (((!charge || !pos_lo || !pos_hi) && n_rows_expected) || !counts4 || !accepted || (!out && n_rows_expected) ||
         (n_escapes && !escapes))
         return PTB_E_INVALID;
-    // this plane's escaped counts, sorted by particle: a nibble of 15 is looked up here
-    std::vector<std::pair<uint64_t, unsigned>> esc;
-    for (uint64_t i = 0; i < n_escapes; ++i)
-        if ((int32_t)((escapes[i] >> 40) & 0xffu) == plane)
-            esc.emplace_back(escapes[i] & 0xffffffffffull, (unsigned)(escapes[i] >> 48));
-    std::sort(esc.begin(), esc.end());
-    const auto *eb = esc.data();
-    const size_t ne = esc.size();
-    return expand_rows(
-        [=](uint64_t i, uint16_t &col, uint16_t &row, uint32_t &q) {
-            const uint32_t pos = (uint32_t)pos_lo[i] | ((uint32_t)pos_hi[i] << 16);   // column | row << 12
-            col = (uint16_t)(pos & 0xfffu);
-            row = (uint16_t)(pos >> 12);
-            memcpy(&q, &charge[i], 4);
-        },
-        [=](uint64_t k) -> unsigned {
-            const unsigned c = (counts4[k >> 1] >> ((k & 1) * 4)) & 15u;
-            if (c < 15u) return c;
-            const auto *it = std::lower_bound(eb, eb + ne, std::make_pair(k, 0u));
-            return (it != eb + ne && it->first == k) ? it->second : 0xffffffffu;   // no entry: the sum check fails
-        },
-        accepted, n, event_base, n_rows_expected, out, threads);
+    return with_narrow_plane(charge, pos_lo, pos_hi, counts4, escapes, n_escapes, plane,
+                             [&](const auto &rows_of, const auto &count_of) {
+                                 return expand_rows(rows_of, count_of, accepted, n, event_base, n_rows_expected,
+                                                    [=] { return RowsToMemory{(unsigned char *)out}; }, threads);
+                             });
+}
+
+int64_t ptb_expand_hits_fd(const uint64_t *hits, const uint8_t *counts, const uint32_t *accepted, uint64_t n,
+                           int64_t event_base, uint64_t n_rows_expected, int32_t fd, uint64_t file_offset, int32_t threads)
+{
+    if ((!hits && n_rows_expected) || !counts || !accepted || fd < 0) return PTB_E_INVALID;
+    return with_wide_plane(hits, counts, [&](const auto &rows_of, const auto &count_of) {
+        return expand_rows(rows_of, count_of, accepted, n, event_base, n_rows_expected,
+                           [=] { return RowsToFile(fd, file_offset); }, threads);
+    });
+}
+
+int64_t ptb_expand_hits_narrow_fd(const float *charge, const uint16_t *pos_lo, const uint8_t *pos_hi,
+                                  const uint8_t *counts4, const uint64_t *escapes, uint64_t n_escapes, int32_t plane,
+                                  const uint32_t *accepted, uint64_t n, int64_t event_base, uint64_t n_rows_expected,
+                                  int32_t fd, uint64_t file_offset, int32_t threads)
+{
+    if (((!charge || !pos_lo || !pos_hi) && n_rows_expected) || !counts4 || !accepted || fd < 0 || (n_escapes && !escapes))
+        return PTB_E_INVALID;
+    return with_narrow_plane(charge, pos_lo, pos_hi, counts4, escapes, n_escapes, plane,
+                             [&](const auto &rows_of, const auto &count_of) {
+                                 return expand_rows(rows_of, count_of, accepted, n, event_base, n_rows_expected,
+                                                    [=] { return RowsToFile(fd, file_offset); }, threads);
+                             });
 }
 
 double ptb_measure_fp64_peak(void *stream)

@@ -440,3 +440,25 @@ def expand_compact(lib, c: dict, n: int, event_base: int, out: np.ndarray | None
     if got != rows:
         raise PtbError(f"ptb_expand_hits: counts add up to something else than {rows} rows ({got})")
     return out
+
+
+def expand_compact_to_fd(lib, c: dict, n: int, event_base: int, fd: int, file_offset: int, threads: int = 0) -> int:
+    """expand_compact with a file as destination (``ptb_expand_hits_fd`` / ``ptb_expand_hits_narrow_fd``): the plane's
+    records are written to descriptor `fd` from byte `file_offset` on, block by block.  Returns the number of rows."""
+    narrow = bool(c.get("narrow"))
+    rows = int((c["charge"] if narrow else c["hits"]).shape[0])
+    counts = np.ascontiguousarray(c["counts"], dtype=np.uint8)
+    acc = c["accepted"].ctypes.data
+    ptr = lambda a: a.ctypes.data if rows else None  # noqa: E731
+    if narrow:
+        esc = c.get("escapes")
+        esc = np.zeros(0, np.uint64) if esc is None else np.ascontiguousarray(esc, dtype=np.uint64)
+        got = lib.ptb_expand_hits_narrow_fd(ptr(c["charge"]), ptr(c["pos_lo"]), ptr(c["pos_hi"]), counts.ctypes.data,
+                                            esc.ctypes.data if len(esc) else None, len(esc), int(c.get("plane", 0)), acc,
+                                            int(n), int(event_base), rows, int(fd), int(file_offset), int(threads))
+    else:
+        got = lib.ptb_expand_hits_fd(ptr(c["hits"]), counts.ctypes.data, acc, int(n), int(event_base), rows, int(fd),
+                                     int(file_offset), int(threads))
+    if got != rows:
+        raise PtbError(f"ptb_expand_hits_fd: {'a write failed' if got == -4 else 'counts and rows disagree'} ({got}, {rows} rows)")
+    return rows

@@ -294,6 +294,16 @@ class TableWriter:
                 buf, off = buf[done:], off + done
             self.nrows += len(a)
 
+    def append_with(self, n: int, fill) -> None:
+        """Append n rows that `fill(fd, byte offset)` writes into the file itself (positioned writes; it returns the
+        number of rows it wrote, which must be n)."""
+        n = int(n)
+        if n:
+            self._f.flush()
+            if fill(self._f.fileno(), self._row_addr(self.nrows)) != n:
+                raise ValueError("the rows written do not match the rows announced")
+            self.nrows += n
+
     def append_from_file(self, src_fd: int, extents: list) -> None:
         """Append rows that already lie in another file as raw records: extents = [(offset, bytes)] in row order
         (TableReader.extents).  The bytes move inside the kernel (copy_file_range) where the platform allows it --

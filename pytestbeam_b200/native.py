@@ -90,7 +90,7 @@ class PtbRun(C.Structure):
 EXPORTS = ("ptb_create", "ptb_destroy", "ptb_last_error", "ptb_n_planes", "ptb_workspace_bytes",
            "ptb_prefix", "ptb_simulate", "ptb_pack_hits", "ptb_launch_count", "ptb_measure_fp64_peak",
            "ptb_timing_enable", "ptb_timing_read", "ptb_timing_read_stages", "ptb_correlate", "ptb_digest", "ptb_expand_hits",
-           "ptb_expand_hits_narrow")
+           "ptb_expand_hits_narrow", "ptb_expand_hits_fd", "ptb_expand_hits_narrow_fd")
 
 _lib = None
 
@@ -145,6 +145,12 @@ def load() -> C.CDLL:
     L.ptb_expand_hits_narrow.argtypes = [C.c_void_p] * 5 + [C.c_uint64, C.c_int32, C.c_void_p, C.c_uint64, C.c_int64,
                                          C.c_uint64, C.c_void_p, C.c_int32]
     L.ptb_expand_hits_narrow.restype = C.c_int64
+    L.ptb_expand_hits_fd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64, C.c_uint64, C.c_int32,
+                                     C.c_uint64, C.c_int32]
+    L.ptb_expand_hits_fd.restype = C.c_int64
+    L.ptb_expand_hits_narrow_fd.argtypes = [C.c_void_p] * 5 + [C.c_uint64, C.c_int32, C.c_void_p, C.c_uint64, C.c_int64,
+                                            C.c_uint64, C.c_int32, C.c_uint64, C.c_int32]
+    L.ptb_expand_hits_narrow_fd.restype = C.c_int64
     L.ptb_launch_count.argtypes = []
     L.ptb_launch_count.restype = C.c_uint64
     L.ptb_measure_fp64_peak.argtypes = [C.c_void_p]

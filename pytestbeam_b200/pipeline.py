@@ -16,7 +16,8 @@ import numpy as np
 import torch
 
 from . import native as N
-from .engine import _BASES_WORDS, _TOTALS_WORDS, HITS_DTYPE, PtbError, Simulator, expand_compact, plane_of
+from .engine import (_BASES_WORDS, _TOTALS_WORDS, HITS_DTYPE, PtbError, Simulator, expand_compact,
+                     expand_compact_to_fd, plane_of)
 
 _RETRY = N.PTB_DEV_SLAB_OVERFLOW | N.PTB_DEV_SCRATCH_OVERFLOW | N.PTB_DEV_COUNT_OVERFLOW
 
@@ -65,6 +66,20 @@ class HostChunk:
         out["row"] = s["row"].numpy().view(np.uint16)
         out["charge"] = s["charge"].numpy()
         return out
+
+
+    def records_to_fd(self, plane: int, fd: int, file_offset: int, threads: int = 0) -> int:
+        """The plane's records written to file descriptor `fd` from byte `file_offset` on; returns the rows written."""
+        if self.compact is not None:
+            return expand_compact_to_fd(self.lib, plane_of(self.compact, plane), self.n, self.event_base, fd, file_offset,
+                                        threads=threads)
+        import os
+        buf, off = memoryview(self.records(plane)).cast("B"), int(file_offset)   # a repeated chunk: slab rows
+        rows = len(buf) // 18
+        while len(buf):
+            done = os.pwrite(fd, buf[:1 << 30], off)
+            buf, off = buf[done:], off + done
+        return rows
 
 
 class ChunkPipeline:

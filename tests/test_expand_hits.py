@@ -97,3 +97,28 @@ def test_narrow_count_of_15_without_an_escape_entry_is_refused():
     assert (counts >= 15).any()
     with pytest.raises(PtbError):
         expand_compact(lib, dict(plane, escapes=plane["escapes"][:0]), 500, event_base=0)
+
+
+@pytest.mark.parametrize("form", ["wide", "narrow"])
+@pytest.mark.parametrize("n,threads", [(0, 0), (33, 2), (70_000, 0), (600_001, 5)])
+def test_expand_into_a_file_equals_expand_into_memory(tmp_path, form, n, threads):
+    """ptb_expand_hits*_fd: the records written block by block at a byte offset of a file are the records of the
+    in-memory expansion; bytes before the offset stay untouched; a bad descriptor is an error, not a crash."""
+    import os
+    from pytestbeam_b200.engine import expand_compact_to_fd
+    lib = native.load()
+    counts, acc, words, hits, cols = _case(n, seed=n + 11, max_count=40 if form == "narrow" else 5)
+    plane = _plane(form, counts, words, hits, cols)
+    want = expand_compact(lib, plane, n, event_base=99)
+    path = tmp_path / "rows.bin"
+    path.write_bytes(b"\xaa" * 1000)
+    fd = os.open(str(path), os.O_RDWR)
+    try:
+        assert expand_compact_to_fd(lib, plane, n, 99, fd, 1000, threads=threads) == len(want)
+    finally:
+        os.close(fd)
+    data = path.read_bytes()
+    assert data[:1000] == b"\xaa" * 1000 and data[1000:] == want.tobytes()
+    if len(want):
+        with pytest.raises(PtbError):
+            expand_compact_to_fd(lib, plane, n, 99, 10_000, 0)      # no such descriptor

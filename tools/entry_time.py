@@ -24,7 +24,7 @@ try:
         print(f"run {rep}: {dt:.2f} s -> {n / dt:.4g} electrons/s", flush=True)
     out = os.path.join(d, "output_data")
     rows = size = 0
-    for f in os.listdir(out):
+    for f in (f for f in os.listdir(out) if f.endswith(".h5")):
         with h5min.TableReader(os.path.join(out, f)) as r:
             rows += r.nrows("Hits")
         size += os.path.getsize(os.path.join(out, f))
