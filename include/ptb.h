@@ -248,7 +248,7 @@ int64_t ptb_expand_hits_narrow(const float *charge, const uint16_t *pos_lo, cons
                                uint64_t n, int64_t event_base, uint64_t n_rows_expected, void *out, int32_t threads);
 
 /* Both expansions with a file instead of a buffer as destination: the plane's records go to file descriptor fd from
- * byte file_offset on, written block by block (positioned writes of 256 KiB that never leave the writing core's cache)
+ * byte file_offset on, written block by block (positioned writes of 4 MiB per worker thread)
  * -- the dataset region of a *_dut.h5 file is filled without staging the table in memory.  PTB_E_IO when a write fails. */
 int64_t ptb_expand_hits_fd(const uint64_t *hits, const uint8_t *counts, const uint32_t *accepted, uint64_t n,
                            int64_t event_base, uint64_t n_rows_expected, int32_t fd, uint64_t file_offset, int32_t threads);

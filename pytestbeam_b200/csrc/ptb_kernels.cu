@@ -1398,7 +1398,7 @@ struct RowsToMemory {
 #define PTB_FILE_BLOCK_ROWS 233016   /* 4 MiB of records: measured best on a disk-backed page cache (256 KiB .. 16 MiB tried) */
 #endif
 struct RowsToFile {
-    static constexpr size_t BLOCK_ROWS = PTB_FILE_BLOCK_ROWS;   // stays in the core's cache until pwrite copies it out
+    static constexpr size_t BLOCK_ROWS = PTB_FILE_BLOCK_ROWS;
     int                     fd;
     uint64_t                offset;                // file position of row 0 of the plane
     std::vector<unsigned char> buf;

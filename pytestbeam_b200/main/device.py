@@ -61,7 +61,7 @@ class MemorySink:
 
 class FileSink:
     """One streamed ``/Hits`` table per device.  Every plane's rows are expanded by the library straight into its file
-    (``ptb_expand_hits*_fd``: cache-sized blocks, positioned writes) -- no staging copy of the table, no page faults on
+    (``ptb_expand_hits*_fd``: 4 MiB blocks, positioned writes) -- no staging copy of the table, no page faults on
     freshly mapped file pages; the planes of a chunk are served by one thread each (the call releases the GIL)."""
 
     parallel = True
