@@ -84,11 +84,22 @@ class FileSink:
             w.close()
 
 
+_PLANE_POOL = None      # worker threads shared by every run of the process: one per plane of the widest telescope seen
+
+
+def _plane_pool(planes: int):
+    global _PLANE_POOL
+    from concurrent.futures import ThreadPoolExecutor
+    if _PLANE_POOL is None or _PLANE_POOL._max_workers < planes:
+        if _PLANE_POOL is not None:
+            _PLANE_POOL.shutdown(wait=True)
+        _PLANE_POOL = ThreadPoolExecutor(max_workers=planes, thread_name_prefix="ptb-plane")
+    return _PLANE_POOL
+
+
 def _consume_into(sink):
     """consume(chunk) for ChunkPipeline.run_to_host: every plane's rows go to the sink as the reference's records."""
     import os
-    from concurrent.futures import ThreadPoolExecutor
-    pool = None
 
     def one(chunk, d, threads):
         if hasattr(sink, "write"):                   # the sink takes the rows itself (files)
@@ -99,15 +110,12 @@ def _consume_into(sink):
         sink.done(d, out)
 
     def consume(chunk):
-        nonlocal pool
         if not getattr(sink, "parallel", False) or chunk.D == 1:
             for d in range(chunk.D):
                 one(chunk, d, 0)
             return
-        if pool is None:
-            pool = ThreadPoolExecutor(max_workers=chunk.D)
         per = max(1, (os.cpu_count() or 1) // chunk.D)       # threads of each plane's expansion
-        for f in [pool.submit(one, chunk, d, per) for d in range(chunk.D)]:
+        for f in [_plane_pool(chunk.D).submit(one, chunk, d, per) for d in range(chunk.D)]:
             f.result()
     return consume
 
