@@ -100,3 +100,35 @@ def test_prefix_exchange_and_merge_world_size_2(tmp_path):
     assert list(merged["column"]) == [1, 1, 1, 2, 2, 2, 2]                 # rank order = particle order
     assert list(merged["event_number"]) == [1, 2, 3, 101, 102, 103, 104]
     assert not os.path.exists(folder + "plane_dut.part000.h5")
+
+
+def test_bench_combines_piecewise_digests_like_one_table():
+    """bench.py's shard_check puts rank-local digests end to end (combine_digests): with the order-sensitive word S2 taken
+    relative to every piece's first row, the combination must equal the digest of the whole table, modulo 2^64."""
+    import importlib.util
+    import numpy as np
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    M = (1 << 64) - 1
+    rs = np.random.RandomState(3)
+
+    def digest(cols, mix):
+        """[rows, sum of four columns, S1 = sum m_i, S2 = sum (i+1) m_i] of one piece, S2 relative to its first row."""
+        w = [len(mix)] + [int(sum(int(v) for v in c)) & M for c in cols]
+        w.append(sum(int(m) for m in mix) & M)
+        w.append(sum((i + 1) * int(m) for i, m in enumerate(mix)) & M)
+        return w
+
+    planes, cuts = 3, [0, 5, 5, 40, 64]                        # an empty piece included
+    whole, pieces = [], [[] for _ in range(len(cuts) - 1)]
+    for d in range(planes):
+        n = cuts[-1]
+        cols = [rs.randint(0, 1 << 62, n, dtype=np.int64).astype(np.uint64) for _ in range(4)]
+        mix = rs.randint(0, 1 << 62, n, dtype=np.int64).astype(np.uint64) * np.uint64(4) + np.uint64(3)
+        whole.append(digest(cols, mix))
+        for p in range(len(cuts) - 1):
+            lo, hi = cuts[p], cuts[p + 1]
+            pieces[p].append(digest([c[lo:hi] for c in cols], mix[lo:hi]))
+    assert bench.combine_digests(pieces) == whole
