@@ -23,8 +23,11 @@
  *   ptb_pack_hits   the structured-array rows handed to create_hit_file (main/device.py:317-327)
  *   PtbCompactOut   the same hit tables in compressed-row form for the trip to the host: per (plane, particle) the
  *                   number of rows calc_position appended for it (main/device.py:156-163) instead of a repeated event
- *                   number, the trigger mask (main/device.py:56) and 8-byte (column, row, charge) rows
- *   ptb_expand_hits that form back into the 18-byte rows of main/device.py:20-28 (host code, multi-threaded)
+ *                   number, the trigger mask (main/device.py:56) and 8-byte (column, row, charge) rows -- or, with
+ *                   PTB_COMPACT_NARROW, 7-byte rows in three arrays and 4-bit counts
+ *   ptb_expand_hits, ptb_expand_hits_narrow   that form back into the 18-byte rows of main/device.py:20-28 (host code,
+ *                   multi-threaded); ptb_expand_hits_fd, ptb_expand_hits_narrow_fd write them into a file at a byte
+ *                   offset instead: the /Hits dataset that create_hit_file fills (main/device.py:306-340)
  *   ptb_digest      no counterpart: order-sensitive checksums of a hit table, for comparing sharded runs
  *   PTB_ZERO_RADIUS the calc_cluster_hits call of the threshold scan (main/threshold_scan.py:55-69)
  *   ptb_correlate   _eventloop_fast of the correlation plot (main/plotting.py:730-764)
