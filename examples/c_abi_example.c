@@ -4,8 +4,13 @@
  * first rows of the last plane.
  *
  *   nvcc -x c -I include -o c_abi_example examples/c_abi_example.c -L pytestbeam_b200/_lib -lptb_b200 -lcudart
- *   LD_LIBRARY_PATH=pytestbeam_b200/_lib ./c_abi_example [n_electrons] [seed]
+ *   LD_LIBRARY_PATH=pytestbeam_b200/_lib ./c_abi_example [n_electrons] [seed] [file for the last plane's records]
+ *
+ * With a file name the same particles run once more in the narrow compressed-row form (what a caller ships over PCIe),
+ * and the library expands the last plane's rows straight into that file (ptb_expand_hits_narrow_fd).
  */
+#include <fcntl.h>
+#include <unistd.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -111,6 +116,59 @@ int main(int argc, char **argv)
             printf("itkpix row %llu: event %lld frame %u column %u row %u charge %.6f\n", (unsigned long long)i,
                    (long long)ev, f, c, r, q);
         }
+    }
+    if (argc > 3) {
+        /* the same range as compressed rows: 7 bytes per hit + 4 bits per (particle, plane) + 1 bit per particle */
+        uint64_t rows_cap = 0;
+        memset(&run.compact, 0, sizeof(run.compact));
+        for (int d = 0; d < 7; ++d) {
+            run.compact.plane_first[d] = rows_cap;
+            rows_cap += cap[d];
+        }
+        run.compact.plane_first[7] = rows_cap;
+        const uint64_t half = (n + 1) / 2, words = (n + 31) / 32;
+        run.compact.escape_capacity = 4096;
+        CK(cudaMalloc((void **)&run.compact.charge, rows_cap * sizeof(float)));
+        CK(cudaMalloc((void **)&run.compact.pos_lo, rows_cap * sizeof(uint16_t)));
+        CK(cudaMalloc((void **)&run.compact.pos_hi, rows_cap));
+        CK(cudaMalloc((void **)&run.compact.counts, 7 * half));
+        CK(cudaMalloc((void **)&run.compact.accepted, words * sizeof(uint32_t)));
+        CK(cudaMalloc((void **)&run.compact.escapes, run.compact.escape_capacity * sizeof(uint64_t)));
+        run.flags = PTB_DIGITISE | PTB_RECYCLE_SLABS | PTB_COMPACT | PTB_COMPACT_NARROW;
+        rc = ptb_simulate(h, &run, NULL);
+        if (rc != PTB_OK) {
+            fprintf(stderr, "ptb_simulate (compressed rows): %d %s\n", rc, ptb_last_error(h));
+            return 1;
+        }
+        CK(cudaMemcpy(&tot, run.totals, sizeof(tot), cudaMemcpyDeviceToHost));
+        if (tot.error) {
+            fprintf(stderr, "device error bits %#x (compressed rows)\n", tot.error);
+            return 1;
+        }
+        uint64_t first6 = 0; /* the planes' rows lie back to back */
+        for (int d = 0; d < 6; ++d) first6 += tot.hits[d];
+        const uint64_t m = tot.hits[6];
+        float         *q = malloc((m ? m : 1) * sizeof(float));
+        uint16_t      *lo = malloc((m ? m : 1) * sizeof(uint16_t));
+        uint8_t       *hi = malloc(m ? m : 1), *cnt = malloc(half);
+        uint32_t      *acc = malloc(words * sizeof(uint32_t));
+        uint64_t      *esc = malloc((tot.escapes ? tot.escapes : 1) * sizeof(uint64_t));
+        CK(cudaMemcpy(q, run.compact.charge + first6, m * sizeof(float), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(lo, run.compact.pos_lo + first6, m * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(hi, run.compact.pos_hi + first6, m, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(cnt, run.compact.counts + 6 * half, half, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(acc, run.compact.accepted, words * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(esc, run.compact.escapes, tot.escapes * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        const int fd = open(argv[3], O_CREAT | O_TRUNC | O_WRONLY, 0644);
+        if (fd < 0) {
+            perror(argv[3]);
+            return 1;
+        }
+        const int64_t wrote = ptb_expand_hits_narrow_fd(q, lo, hi, cnt, esc, tot.escapes, 6, acc, n, 0, m, fd, 0, 0);
+        close(fd);
+        printf("file rows %lld of %llu (%llu bytes of compressed rows for all planes)\n", (long long)wrote,
+               (unsigned long long)m, (unsigned long long)(7 * (first6 + m) + 7 * half + 4 * words + 8 * tot.escapes));
+        if (wrote != (int64_t)m) return 1;
     }
     ptb_destroy(h);
     return 0;

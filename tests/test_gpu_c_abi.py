@@ -25,7 +25,8 @@ def test_plain_c_caller_matches_the_python_host(tmp_path):
                            os.path.join(ROOT, "examples", "c_abi_example.c"), "-L", lib_dir, "-lptb_b200", "-lcudart"])
     n, seed = 200_000, 7
     env = dict(os.environ, LD_LIBRARY_PATH=lib_dir + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
-    out = subprocess.run([exe, str(n), str(seed)], env=env, capture_output=True, text=True, timeout=300)
+    rows_file = str(tmp_path / "itkpix_rows.bin")
+    out = subprocess.run([exe, str(n), str(seed), rows_file], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
     rows = [int(m) for m in re.findall(r"plane \d+ rows (\d+)", out.stdout)]
     beam, devices, materials, names = cfg.flatten(cfg.default_setup(n))
@@ -39,3 +40,6 @@ def test_plain_c_caller_matches_the_python_host(tmp_path):
     for g, w in zip(got, want):
         assert (int(g[0]), int(g[1]), int(g[2]), int(g[3])) == (w["event_number"], w["frame"], w["column"], w["row"])
         assert abs(float(g[4]) - float(w["charge"])) < 1e-5
+    # the narrow compressed rows, expanded by the library straight into a file: the last plane's records, byte for byte
+    assert int(re.search(r"file rows (\d+)", out.stdout).group(1)) == res.totals["hits"][-1]
+    assert open(rows_file, "rb").read() == res.hits_numpy(len(devices) - 1).tobytes()
