@@ -492,6 +492,16 @@ def run_gpu(args):
             ncu["note"] = "from the committed ncu capture (profiles/), not measured in this run"
         except Exception:
             pass
+        issue = None
+        if ncu and "warp_instructions_per_launch" in ncu and clocks and clocks.get("sm_mhz"):
+            # the roof that actually binds: warp instructions issued per second against 4 schedulers x SMs x clock
+            props = torch.cuda.get_device_properties(sim.device)
+            inst = ncu["warp_instructions_per_launch"] * (chunk / tj["chunk"])
+            peak = 4.0 * props.multi_processor_count * clocks["sm_mhz"] * 1e6
+            issue = {"achieved": inst / (launch_ms * 1e-3), "peak": peak, "unit": "warp instructions/s",
+                     "frac": inst / (launch_ms * 1e-3) / peak,
+                     "note": "instruction count of the committed ncu capture (profiles/traffic.json) over the live k_digitise "
+                             "duration; peak = 4 issue slots per SM and clock"}
         ach_tf = F * chunk / (launch_ms * 1e-3) / 1e12
         ach_gb = alg_bytes / (launch_ms * 1e-3) / 1e9
         roof = {"bound": "fp64", "kernel": "k_digitise<PhiloxSource>", "achieved": ach_tf, "peak": fp64_peak / 1e12,
@@ -503,7 +513,7 @@ def run_gpu(args):
                                       "k_digitise_big+scans": stages[2] / max(sim_launches, 1),
                                       "k_gather": stages[3] / max(sim_launches, 1)},
                 "share_of_step": launch_ms / (ms / K), "traffic": traffic, "traffic_over_algorithmic":
-                    traffic / alg_bytes if traffic else None, "ncu": ncu,
+                    traffic / alg_bytes if traffic else None, "ncu": ncu, "issue": issue,
                 "binding": "instruction issue (see ncu.issue_active_pct; FP64 pipe about a quarter busy): profiles/README.md",
                 "hbm": {"achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
                         "bytes_per_electron": alg_bytes / chunk, "peak_source": hbm_src}}
