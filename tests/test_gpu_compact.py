@@ -358,3 +358,46 @@ def test_entry_point_streams_files_equal_to_one_call(tmp_path):
     assert np.array_equal(trk["time_stamp"], one.tracks["time_stamp"].cpu().numpy().astype(np.uint16))
     head = tables.head(1000)
     assert np.array_equal(head[3], one.tracks["x"].cpu().numpy()[:1000 * sim.D]) and head[7].shape == (sim.D, 1000)
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_compressed_rows_on_random_telescopes(seed):
+    """Telescopes drawn at random inside the setup.yml schema (tests/test_gpu_parity.py:_random_setup: 2..9 planes,
+    single-pixel absorbers that never fire, matrices up to 3000 x 3000, 3 um .. 12 cm pitches, either trigger mode):
+    both compressed-row forms and the host pipeline in whichever form it picks must expand to the slab tables byte for
+    byte, and file-to-file expansion must write the same records."""
+    import os
+    import tempfile
+    from pytestbeam_b200.engine import PtbError, Simulator, expand_compact_to_fd, plane_of
+    from pytestbeam_b200.pipeline import ChunkPipeline
+    from tests.test_gpu_parity import _random_setup
+    rng = np.random.default_rng(5000 + seed)
+    n = 6000
+    beam, devices, materials, names = _random_setup(rng, n)
+    sim = Simulator(beam, devices, materials)
+    first = int(rng.integers(0, 1 << 40))
+    slab = sim.run(first, n, seed=seed)
+    if max(slab.totals["hits"]) > 200 * n:
+        pytest.skip("a geometry with hundreds of rows per particle: covered by the fine-pitch tests")
+    forms = [True] + (["narrow"] if all(d["column"] <= 4095 and d["row"] <= 4095 for d in devices) else [])
+    for form in forms:
+        try:
+            c = sim.run(first, n, seed=seed, compact=form)
+        except PtbError as exc:                     # more than 255 rows of one particle on a plane: the documented refusal
+            assert "255" in str(exc)
+            continue
+        assert c.totals["hits"] == slab.totals["hits"]
+        host = c.compact_host()
+        for d in range(sim.D):
+            want = slab.hits_numpy(d)
+            assert c.hits_numpy(d).tobytes() == want.tobytes(), (form, names[d])
+            with tempfile.TemporaryFile() as fh:
+                rows = expand_compact_to_fd(sim.lib, plane_of(host, d), n, c.event_base, fh.fileno(), 64)
+                assert rows == len(want)
+                fh.seek(64)
+                assert fh.read() == want.tobytes(), (form, names[d], "file")
+    pipe = ChunkPipeline(sim, 2048, host=True, seed=seed)
+    got = [[] for _ in range(sim.D)]
+    pipe.run_to_host(first, 0, consume=lambda ch: [got[d].append(ch.records(d).copy()) for d in range(sim.D)], n_total=n)
+    for d in range(sim.D):
+        assert np.concatenate(got[d]).tobytes() == slab.hits_numpy(d).tobytes(), (pipe.narrow, names[d])
