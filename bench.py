@@ -532,11 +532,12 @@ def run_gpu(args):
                 "e2e": {"value": job.total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": d2h / K, "rows_per_step": rows / K,
                         "bytes_per_electron": d2h / K / chunk,
-                        "form": "PTB_COMPACT_NARROW" if host_pipe.narrow else "PTB_COMPACT",
+                        "form": {"packed": "PTB_COMPACT_PACKED", "narrow": "PTB_COMPACT_NARROW"}.get(host_pipe.form, "PTB_COMPACT"),
                         "note": "ChunkPipeline.run_to_host: every chunk's hit tables copied to pinned host memory on a "
-                                "second stream in compressed-row form (PtbCompactOut, include/ptb.h: narrow = 7-byte rows "
-                                "in three arrays + 4-bit counts per particle and plane + trigger mask; wide = 8-byte rows "
-                                "+ count bytes); ptb_expand_hits[_narrow] turns it into the reference's 18-byte rows; "
+                                "second stream in compressed-row form (PtbCompactOut, include/ptb.h: packed = 6-byte rows "
+                                "in three arrays + 4-bit counts per particle and plane + trigger mask; narrow = 7-byte "
+                                "rows; wide = 8-byte rows + count bytes); ptb_expand_hits* turns it into the reference's "
+                                "18-byte rows; "
                                 "production mode has no per-step input arrays"},
                 "gpu_launches": int(launches),
                 "roofline": roof}

@@ -61,6 +61,8 @@ extern "C" {
 #define PTB_DEV_SCRATCH_OVERFLOW 1u /* the workspace's scratch rows of a plane ran out; PtbTotals.reserved is exact */
 #define PTB_DEV_SLAB_OVERFLOW 2u  /* a hit slab's capacity was exceeded; totals still hold the exact counts */
 #define PTB_DEV_BOX_TOO_LARGE 4u  /* a cluster bounding box exceeded 2^20 pixels */
+#define PTB_DEV_PACK_OVERFLOW 16u /* PTB_COMPACT_PACKED: a negative charge or one below the plane's threshold reached the
+                                     row packer (an internal inconsistency: a row exists because it reached the threshold) */
 #define PTB_DEV_COUNT_OVERFLOW 8u /* PTB_COMPACT: one particle left more than 255 rows on a plane (the count saturated),
                                      or PTB_COMPACT_NARROW ran out of escape entries; rerun the range without
                                      PTB_COMPACT */
@@ -75,6 +77,8 @@ extern "C" {
 #define PTB_RECYCLE_SLABS 16u    /* rows start at 0 of each slab: ignore bases_in->hits and write bases_out->hits = 0 */
 #define PTB_COMPACT 64u          /* with PTB_DIGITISE: write PtbRun.compact instead of PtbRun.slabs (always recycled) */
 #define PTB_COMPACT_NARROW 128u  /* with PTB_COMPACT: 7-byte rows in three arrays and 4-bit counts (PtbCompactOut) */
+#define PTB_COMPACT_PACKED 256u  /* with PTB_COMPACT: 6-byte rows in three arrays and 4-bit counts (PtbCompactOut); for
+                                    set-ups ptb_packed_layout() accepts */
 
 /* beam block of setup.yml; lengths um, angles rad, energy MeV, rate Hz */
 typedef struct PtbBeam {
@@ -147,7 +151,17 @@ typedef struct PtbHitSlab {
  * per (plane, particle): the count of particle k on plane d is nibble (k & 1) of counts[d * ((n + 1) / 2) + k / 2].
  * A nibble of 15 means "15 or more": the exact count (up to 255) then stands in one of the totals.escapes entries of
  * the escapes array, in no particular order, as  count << 48 | plane << 40 | (k - first).
- * 55 bytes per electron on the default telescope: this is what travels over PCIe.
+ * 55 bytes per electron on the default telescope.
+ *
+ * PTB_COMPACT_PACKED (set-ups ptb_packed_layout accepts: every plane's column and row indices fit 21 bits together and
+ * its threshold is positive): counts, escapes, trigger mask and row order as in the narrow form; a row is 48 bits,
+ * word0[i] | word1[i] << 16 | word2[i] << 32:
+ *     bits 0-22   mantissa of the f32 charge (its sign is +: a row exists because the charge reached the threshold)
+ *     bits 23-26  biased exponent of the charge minus exp_min[plane] (the exponent of the threshold as f32); a charge
+ *                 beyond these 16 binades (the far tail of the deposit law) keeps 15 here and stands on the escape list
+ *                 as  1 << 63 | row index (counted over all planes, < 2^31) << 32 | f32 bits of the charge
+ *     bits 27 ..  column (col_bits[plane] bits), then row
+ * 48 bytes per electron on the default telescope: this is what travels over PCIe.
  */
 typedef struct PtbCompactOut {
     uint64_t *hits;     /* column | row << 16 | (f32 charge bits) << 32; unused with PTB_COMPACT_NARROW */
@@ -157,9 +171,16 @@ typedef struct PtbCompactOut {
     float    *charge;   /* PTB_COMPACT_NARROW: the three row arrays, plane_first[D] rows each */
     uint16_t *pos_lo;
     uint8_t  *pos_hi;
-    uint64_t *escapes;  /* PTB_COMPACT_NARROW: counts of 15 and more (see above), escape_capacity entries */
+    uint64_t *escapes;  /* PTB_COMPACT_NARROW / _PACKED: counts of 15 and more (see above), escape_capacity entries */
     uint64_t  escape_capacity;
+    uint16_t *word0, *word1, *word2; /* PTB_COMPACT_PACKED: the three row arrays, plane_first[D] rows each */
 } PtbCompactOut;
+
+/* bit layout of the PTB_COMPACT_PACKED rows of every plane (see above) */
+typedef struct PtbPackedLayout {
+    uint8_t exp_min[PTB_MAX_PLANES];  /* biased f32 exponent of the plane's threshold in ke */
+    uint8_t col_bits[PTB_MAX_PLANES]; /* bits of the column index; the row index takes the bits above it */
+} PtbPackedLayout;
 
 /* running prefixes carried from one particle range to the next (device memory) */
 typedef struct PtbBases {
@@ -210,6 +231,10 @@ void        ptb_destroy(PtbHandle h);
 const char *ptb_last_error(PtbHandle h);
 int32_t     ptb_n_planes(PtbHandle h);
 
+/* the row layout PTB_COMPACT_PACKED uses for this handle's planes; PTB_E_INVALID (and *out untouched) when a plane does
+ * not fit it: more than 21 bits of column + row index, or a threshold that is not positive */
+int ptb_packed_layout(PtbHandle h, PtbPackedLayout *out);
+
 /* bytes of workspace ptb_simulate needs for n particles, the given slab capacities and scratch rows (NULL = default) */
 size_t ptb_workspace_bytes(PtbHandle h, uint64_t n, const uint64_t *capacity /*[n_planes]*/,
                            const uint64_t *scratch_rows /*[n_planes] or NULL*/, uint32_t flags);
@@ -250,6 +275,13 @@ int64_t ptb_expand_hits_narrow(const float *charge, const uint16_t *pos_lo, cons
                                const uint64_t *escapes, uint64_t n_escapes, int32_t plane, const uint32_t *accepted,
                                uint64_t n, int64_t event_base, uint64_t n_rows_expected, void *out, int32_t threads);
 
+/* the same for plane `plane` of the PTB_COMPACT_PACKED form (layout: ptb_packed_layout of the handle that produced it;
+ * row_base: the plane's first row counted over all planes = totals.hits[0] + ... + totals.hits[plane-1]) */
+int64_t ptb_expand_hits_packed(const uint16_t *word0, const uint16_t *word1, const uint16_t *word2, const uint8_t *counts4,
+                               const uint64_t *escapes, uint64_t n_escapes, int32_t plane, const PtbPackedLayout *layout,
+                               uint64_t row_base, const uint32_t *accepted, uint64_t n, int64_t event_base,
+                               uint64_t n_rows_expected, void *out, int32_t threads);
+
 /* Both expansions with a file instead of a buffer as destination: the plane's records go to file descriptor fd from
  * byte file_offset on, written block by block (positioned writes of 4 MiB per worker thread)
  * -- the dataset region of a *_dut.h5 file is filled without staging the table in memory.  PTB_E_IO when a write fails. */
@@ -259,6 +291,12 @@ int64_t ptb_expand_hits_narrow_fd(const float *charge, const uint16_t *pos_lo, c
                                   const uint8_t *counts4, const uint64_t *escapes, uint64_t n_escapes, int32_t plane,
                                   const uint32_t *accepted, uint64_t n, int64_t event_base, uint64_t n_rows_expected,
                                   int32_t fd, uint64_t file_offset, int32_t threads);
+
+int64_t ptb_expand_hits_packed_fd(const uint16_t *word0, const uint16_t *word1, const uint16_t *word2,
+                                  const uint8_t *counts4, const uint64_t *escapes, uint64_t n_escapes, int32_t plane,
+                                  const PtbPackedLayout *layout, uint64_t row_base, const uint32_t *accepted, uint64_t n,
+                                  int64_t event_base, uint64_t n_rows_expected, int32_t fd, uint64_t file_offset,
+                                  int32_t threads);
 
 /*
  * Checksums of rows [0, n) of a hit table, added (modulo 2^64) to out_dev[0..6]:

@@ -686,7 +686,7 @@ __device__ __forceinline__ void digitise_group(const ConfigK &cfg, const KParams
         }
         __syncwarp();
         if (compact) {
-            if (P.flags & PTB_COMPACT_NARROW) {   // 4 bits per particle: the even lane stores the pair's byte
+            if (P.flags & (PTB_COMPACT_NARROW | PTB_COMPACT_PACKED)) {   // 4 bits per particle: the even lane stores the pair's byte
                 const unsigned full = W.cnt[lane], c = min(full, 15u);
                 if (full >= 15u) escape_count(P, d, kl, full);   // (invalid lanes count 0)
                 const unsigned pair = c | (__shfl_down_sync(FULL, c, 1) << 4);
@@ -861,7 +861,7 @@ __global__ void __launch_bounds__(32 * BIG_WARPS) k_digitise_big(const __grid_co
                 kept = 1;
             }
             if (compact && lane == 0) {
-                if (P.flags & PTB_COMPACT_NARROW) {   // the particle's nibble of the byte k_digitise left (zero) for the pair
+                if (P.flags & (PTB_COMPACT_NARROW | PTB_COMPACT_PACKED)) {   // the particle's nibble of the byte k_digitise left (zero) for the pair
                     uint8_t  *byte = &P.cmp.counts[(unsigned long long)d * ((P.n + 1) / 2) + (group * 32 + b) / 2];
                     const int sh = (b & 1) * 4;
                     *byte = (uint8_t)((*byte & ~(15u << sh)) | ((unsigned)min(kept, 15) << sh));
@@ -1017,6 +1017,7 @@ struct GatherParams {
     Workspace          ws;
     PtbHitSlab         slabs[PTB_MAX_PLANES];
     PtbCompactOut      cmp;
+    PtbPackedLayout    packed;   // PTB_COMPACT_PACKED
     int64_t           *time_stamp;
     PtbTotals         *totals;
 };
@@ -1047,7 +1048,8 @@ __global__ void __launch_bounds__(256, 8) k_gather(const __grid_constant__ Gathe
     if (G.flags & PTB_DIGITISE) {
         // PTB_COMPACT_NARROW: the planes' rows lie back to back, plane d starts where the rows of planes 0..d-1 end
         // (k_scan has written this call's totals)
-        const bool         narrow = (G.flags & PTB_COMPACT_NARROW) != 0;
+        const bool         packed = (G.flags & PTB_COMPACT_PACKED) != 0;
+        const bool         narrow = (G.flags & PTB_COMPACT_NARROW) != 0 || packed;   // dense rows, planes back to back
         unsigned long long dense_l = 0;
         if (narrow) {
             const unsigned long long mine = lane < D ? G.totals->hits[lane] : 0ull;
@@ -1113,7 +1115,28 @@ __global__ void __launch_bounds__(256, 8) k_gather(const __grid_constant__ Gathe
             const unsigned long long o = __shfl_sync(FULL, dstR, rank) + (unsigned long long)w;
             if (w >= total) continue;
             const uint2 hit = s_hit[d][si];
-            if (narrow) {
+            if (packed) {
+                // 48 bits: f32 mantissa | exponent above the plane's threshold << 23 | column << 27 | row << (27 + col_bits)
+                const unsigned ex = (hit.y >> 23) & 0xffu, ex_min = G.packed.exp_min[d];
+                unsigned       off = ex - ex_min;
+                if (ex < ex_min || (hit.y >> 31)) atomicOr(&G.totals->error, PTB_DEV_PACK_OVERFLOW);   // (cannot happen)
+                if (off > 15u) {
+                    // a charge beyond the 16 binades of the row format (the far tail of the deposit law): the row
+                    // keeps exponent 15 and the charge travels on the escape list under the row's index
+                    const unsigned slot = atomicAdd(&G.totals->escapes, 1u);
+                    if (slot < G.cmp.escape_capacity)
+                        G.cmp.escapes[slot] = (1ull << 63) | ((o & 0x7fffffffull) << 32) | (unsigned long long)hit.y;
+                    else
+                        atomicOr(&G.totals->error, PTB_DEV_COUNT_OVERFLOW);
+                    off = 15u;
+                }
+                const unsigned long long word = (unsigned long long)(hit.y & 0x7fffffu) | ((unsigned long long)(off & 15u) << 23) |
+                                                ((unsigned long long)(hit.x & 0xffffu) << 27) |
+                                                ((unsigned long long)(hit.x >> 16) << (27 + G.packed.col_bits[d]));
+                G.cmp.word0[o] = (uint16_t)word;
+                G.cmp.word1[o] = (uint16_t)(word >> 16);
+                G.cmp.word2[o] = (uint16_t)(word >> 32);
+            } else if (narrow) {
                 const unsigned pos = (hit.x & 0xfffu) | ((hit.x >> 16) << 12);   // column | row << 12
                 G.cmp.charge[o] = __uint_as_float(hit.y);
                 G.cmp.pos_lo[o] = (uint16_t)pos;
@@ -1547,6 +1570,58 @@ static int64_t with_wide_plane(const uint64_t *hits, const uint8_t *counts, cons
         [=](uint64_t k) -> unsigned { return counts[k]; });
 }
 
+// the 4-bit counts of the narrow and the packed form: a nibble of 15 is looked up among the plane's escape entries
+struct NibbleCounts {
+    const uint8_t                             *counts4;
+    std::vector<std::pair<uint64_t, unsigned>> esc;   // this plane's escaped counts, sorted by particle
+    NibbleCounts(const uint8_t *c4, const uint64_t *escapes, uint64_t n_escapes, int32_t plane) : counts4(c4)
+    {
+        for (uint64_t i = 0; i < n_escapes; ++i)
+            if (!(escapes[i] >> 63) && (int32_t)((escapes[i] >> 40) & 0xffu) == plane)   // (bit 63: a charge, not a count)
+                esc.emplace_back(escapes[i] & 0xffffffffffull, (unsigned)(escapes[i] >> 48));
+        std::sort(esc.begin(), esc.end());
+    }
+};
+
+template <class Go>
+static int64_t with_packed_plane(const uint16_t *w0, const uint16_t *w1, const uint16_t *w2, const uint8_t *counts4,
+                                 const uint64_t *escapes, uint64_t n_escapes, int32_t plane, const PtbPackedLayout &L,
+                                 uint64_t row_base, uint64_t n_rows, const Go &go)
+{
+    const NibbleCounts nc(counts4, escapes, n_escapes, plane);
+    const auto        *eb = nc.esc.data();
+    const size_t       ne = nc.esc.size();
+    // charges beyond the row format's 16 binades, by row of this plane
+    std::vector<std::pair<uint64_t, uint32_t>> big;
+    for (uint64_t i = 0; i < n_escapes; ++i)
+        if (escapes[i] >> 63) {
+            const uint64_t at = (escapes[i] >> 32) & 0x7fffffffull;
+            if (at >= row_base && at - row_base < n_rows) big.emplace_back(at - row_base, (uint32_t)escapes[i]);
+        }
+    std::sort(big.begin(), big.end());
+    const auto    *bb = big.data();
+    const size_t   nb = big.size();
+    const unsigned ex = L.exp_min[plane], cb = L.col_bits[plane];
+    return go(
+        [=](uint64_t i, uint16_t &col, uint16_t &row, uint32_t &q) {
+            const uint64_t w = (uint64_t)w0[i] | ((uint64_t)w1[i] << 16) | ((uint64_t)w2[i] << 32);
+            const uint32_t off = (uint32_t)((w >> 23) & 15u);
+            q = (uint32_t)(w & 0x7fffffu) | ((ex + off) << 23);
+            if (off == 15u && nb) {   // the top binade, or beyond it: then the charge stands on the escape list
+                const auto *it = std::lower_bound(bb, bb + nb, std::make_pair(i, (uint32_t)0));
+                if (it != bb + nb && it->first == i) q = it->second;
+            }
+            col = (uint16_t)((w >> 27) & ((1u << cb) - 1u));
+            row = (uint16_t)(w >> (27 + cb));
+        },
+        [=](uint64_t k) -> unsigned {
+            const unsigned c = (counts4[k >> 1] >> ((k & 1) * 4)) & 15u;
+            if (c < 15u) return c;
+            const auto *it = std::lower_bound(eb, eb + ne, std::make_pair(k, 0u));
+            return (it != eb + ne && it->first == k) ? it->second : 0xffffffffu;   // no entry: the sum check fails
+        });
+}
+
 template <class Go>
 static int64_t with_narrow_plane(const float *charge, const uint16_t *pos_lo, const uint8_t *pos_hi, const uint8_t *counts4,
                                  const uint64_t *escapes, uint64_t n_escapes, int32_t plane, const Go &go)
@@ -1902,8 +1977,20 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
     if (compact && (!run->compact.counts || !run->compact.accepted ||
                     (narrow ? (!run->compact.charge || !run->compact.pos_lo || !run->compact.pos_hi ||
                                (run->compact.escape_capacity && !run->compact.escapes))
-                            : !run->compact.hits)))
+                            : (!(flags & PTB_COMPACT_PACKED) && !run->compact.hits))))
         return fail(h, PTB_E_INVALID, "compact output pointers missing");
+    const bool packed = (flags & PTB_COMPACT_PACKED) != 0;
+    PtbPackedLayout layout;
+    memset(&layout, 0, sizeof(layout));
+    if (packed) {
+        if (!compact || narrow) return fail(h, PTB_E_INVALID, "PTB_COMPACT_PACKED needs PTB_COMPACT and excludes PTB_COMPACT_NARROW");
+        if (!run->compact.word0 || !run->compact.word1 || !run->compact.word2 ||
+            (run->compact.escape_capacity && !run->compact.escapes))
+            return fail(h, PTB_E_INVALID, "compact output pointers missing");
+        if (ptb_packed_layout(h, &layout) != PTB_OK) return PTB_E_INVALID;   // (the message is set there)
+        if (run->compact.plane_first[D] > 0x7fffffffull)
+            return fail(h, PTB_E_INVALID, "PTB_COMPACT_PACKED: at most 2^31 - 1 rows per call");
+    }
     if (narrow)
         for (int d = 0; d < D; ++d)
             if (c.pl[d].ncol > 4095 || c.pl[d].nrow > 4095)
@@ -2017,6 +2104,7 @@ int ptb_simulate(PtbHandle h, const PtbRun *run, void *stream)
         G.ws = P.ws;
         for (int d = 0; d < D; ++d) G.slabs[d] = run->slabs[d];
         G.cmp = run->compact;
+        G.packed = layout;
         G.time_stamp = run->tracks.time_stamp;
         G.totals = run->totals;
         k_gather<<<(unsigned)((P.n_groups + 7) / 8), 256, 0, st>>>(G);
@@ -2072,6 +2160,35 @@ int ptb_digest(const PtbHitSlab *slab, uint64_t n, uint64_t row_base, uint64_t *
 // Host side of PtbCompactOut: counts + trigger mask -> event numbers, 8-byte rows -> the reference's 18-byte records.
 // The particle range is cut into blocks of whole 32-particle words; a first pass sums every block's rows and accepted
 // particles, the second pass lets each thread expand its blocks from those prefixes.
+int ptb_packed_layout(PtbHandle h, PtbPackedLayout *out)
+{
+    if (!h || !out) return PTB_E_INVALID;
+    PtbPackedLayout L;
+    memset(&L, 0, sizeof(L));
+    auto bits_for = [](int32_t n) {
+        int b = 0;
+        while ((1ll << b) <= (long long)n) ++b;   // indices run from 1 to n
+        return b;
+    };
+    for (int d = 0; d < h->cfg.n_planes; ++d) {
+        const PlaneK &pl = h->cfg.pl[d];
+        const int     cb = bits_for(pl.ncol), rb = bits_for(pl.nrow);
+        const float   thr = (float)pl.thr_ke;
+        uint32_t      tb;
+        memcpy(&tb, &thr, 4);
+        const unsigned ex = (tb >> 23) & 0xffu;
+        // a row exists because its charge reached the threshold (as doubles; rounding to f32 keeps the order): with a
+        // positive, normal threshold every charge is positive and its exponent is at least the threshold's
+        if (cb + rb > 21 || !(pl.thr_ke > 0.0) || ex == 0 || ex > 239)
+            return fail(h, PTB_E_INVALID, "PTB_COMPACT_PACKED: a plane needs more than 21 bits of column + row index, or its "
+                                          "threshold is not a positive number");
+        L.exp_min[d] = (uint8_t)ex;
+        L.col_bits[d] = (uint8_t)cb;
+    }
+    *out = L;
+    return PTB_OK;
+}
+
 int64_t ptb_expand_hits(const uint64_t *hits, const uint8_t *counts, const uint32_t *accepted, uint64_t n,
                         int64_t event_base, uint64_t n_rows_expected, void *out, int32_t threads)
 {
@@ -2093,6 +2210,37 @@ int64_t ptb_expand_hits_narrow(const float *charge, const uint16_t *pos_lo, cons
                              [&](const auto &rows_of, const auto &count_of) {
                                  return expand_rows(rows_of, count_of, accepted, n, event_base, n_rows_expected,
                                                     [=] { return RowsToMemory{(unsigned char *)out}; }, threads);
+                             });
+}
+
+int64_t ptb_expand_hits_packed(const uint16_t *word0, const uint16_t *word1, const uint16_t *word2, const uint8_t *counts4,
+                               const uint64_t *escapes, uint64_t n_escapes, int32_t plane, const PtbPackedLayout *layout,
+                               uint64_t row_base, const uint32_t *accepted, uint64_t n, int64_t event_base,
+                               uint64_t n_rows_expected, void *out, int32_t threads)
+{
+    if (((!word0 || !word1 || !word2) && n_rows_expected) || !counts4 || !accepted || (!out && n_rows_expected) ||
+        (n_escapes && !escapes) || !layout || plane < 0 || plane >= PTB_MAX_PLANES)
+        return PTB_E_INVALID;
+    return with_packed_plane(word0, word1, word2, counts4, escapes, n_escapes, plane, *layout, row_base, n_rows_expected,
+                             [&](const auto &rows_of, const auto &count_of) {
+                                 return expand_rows(rows_of, count_of, accepted, n, event_base, n_rows_expected,
+                                                    [=] { return RowsToMemory{(unsigned char *)out}; }, threads);
+                             });
+}
+
+int64_t ptb_expand_hits_packed_fd(const uint16_t *word0, const uint16_t *word1, const uint16_t *word2,
+                                  const uint8_t *counts4, const uint64_t *escapes, uint64_t n_escapes, int32_t plane,
+                                  const PtbPackedLayout *layout, uint64_t row_base, const uint32_t *accepted, uint64_t n,
+                                  int64_t event_base, uint64_t n_rows_expected, int32_t fd, uint64_t file_offset,
+                                  int32_t threads)
+{
+    if (((!word0 || !word1 || !word2) && n_rows_expected) || !counts4 || !accepted || fd < 0 || (n_escapes && !escapes) ||
+        !layout || plane < 0 || plane >= PTB_MAX_PLANES)
+        return PTB_E_INVALID;
+    return with_packed_plane(word0, word1, word2, counts4, escapes, n_escapes, plane, *layout, row_base, n_rows_expected,
+                             [&](const auto &rows_of, const auto &count_of) {
+                                 return expand_rows(rows_of, count_of, accepted, n, event_base, n_rows_expected,
+                                                    [=] { return RowsToFile(fd, file_offset); }, threads);
                              });
 }
 

@@ -85,18 +85,25 @@ class RunResult:
     event_base: int = 0
 
     def compact_host(self) -> dict:
-        """The PtbCompactOut on the host, plane by plane: uint64 rows + uint8 counts [D, n] (wide form) or the
-        (charge, pos_lo, pos_hi) slices + nibble pairs [D, (n+1)//2] (narrow form); uint32 trigger words."""
+        """The PtbCompactOut on the host, plane by plane: uint64 rows + uint8 counts [D, n] (wide form); the (charge,
+        pos_lo, pos_hi) slices (narrow) or the (word0, word1, word2) slices + row layout (packed) with nibble pairs
+        [D, (n+1)//2] and escape entries; uint32 trigger words."""
         D, hits, c = len(self.totals["hits"]), self.totals["hits"], self.compact
         acc = c["accepted"].cpu().numpy().view(np.uint32)
-        if c.get("narrow"):
+        form = c.get("form", "wide")
+        if form in ("narrow", "packed"):
             first = np.concatenate([[0], np.cumsum(hits)]).astype(np.int64)      # the planes lie back to back
             cut = lambda k, dt: [c[k][first[d]:first[d + 1]].cpu().numpy().view(dt) for d in range(D)]  # noqa: E731
-            return {"narrow": True, "charge": cut("charge", np.float32), "pos_lo": cut("pos_lo", np.uint16),
-                    "pos_hi": cut("pos_hi", np.uint8), "counts": c["counts"].cpu().numpy().reshape(D, (self.n + 1) // 2),
-                    "escapes": c["escapes"][:self.totals["escapes"]].cpu().numpy().view(np.uint64), "accepted": acc}
+            out = {"form": form, "narrow": True, "counts": c["counts"].cpu().numpy().reshape(D, (self.n + 1) // 2),
+                   "escapes": c["escapes"][:self.totals["escapes"]].cpu().numpy().view(np.uint64), "accepted": acc}
+            if form == "narrow":
+                out.update(charge=cut("charge", np.float32), pos_lo=cut("pos_lo", np.uint16), pos_hi=cut("pos_hi", np.uint8))
+            else:
+                out.update(word0=cut("word0", np.uint16), word1=cut("word1", np.uint16), word2=cut("word2", np.uint16),
+                           layout=c["layout"], row_base=[int(v) for v in first[:D]])
+            return out
         pf = c["plane_first"]
-        return {"hits": [c["hits"][pf[d]:pf[d] + hits[d]].cpu().numpy().view(np.uint64) for d in range(D)],
+        return {"form": "wide", "hits": [c["hits"][pf[d]:pf[d] + hits[d]].cpu().numpy().view(np.uint64) for d in range(D)],
                 "counts": c["counts"].cpu().numpy().reshape(D, self.n), "accepted": acc}
 
     def hits_numpy(self, plane: int) -> np.ndarray:
@@ -171,36 +178,62 @@ class Simulator:
             slabs.append(s)
         return slabs
 
-    def alloc_compact(self, n, capacities, narrow=False):
-        """Device buffers of a PtbCompactOut for n particles and the given rows per plane."""
+    def alloc_compact(self, n, capacities, narrow=False, form: str | None = None):
+        """Device buffers of a PtbCompactOut for n particles and the given rows per plane; form = "wide", "narrow" or
+        "packed" (include/ptb.h)."""
+        form = form or ("narrow" if narrow else "wide")
         first = np.concatenate([[0], np.cumsum([int(c) for c in capacities])]).astype(np.int64)
         rows, dev = int(first[-1]), self.device
-        out = {"plane_first": [int(v) for v in first], "narrow": bool(narrow),
+        out = {"plane_first": [int(v) for v in first], "form": form, "narrow": form != "wide",
                "accepted": torch.empty((int(n) + 31) // 32, dtype=torch.int32, device=dev)}
-        if narrow:
-            out.update(charge=torch.empty(rows, dtype=torch.float32, device=dev),
-                       pos_lo=torch.empty(rows, dtype=torch.int16, device=dev),
-                       pos_hi=torch.empty(rows, dtype=torch.uint8, device=dev),
-                       counts=torch.empty(self.D * ((int(n) + 1) // 2), dtype=torch.uint8, device=dev),
-                       # counts of 15 and more: one entry per 256 (particle, plane) pairs is far above any telescope's need
-                       escapes=torch.empty(max(1024, self.D * int(n) // 256), dtype=torch.int64, device=dev))
-        else:
+        if form == "wide":
             out.update(hits=torch.empty(rows, dtype=torch.int64, device=dev),
                        counts=torch.empty(self.D * int(n), dtype=torch.uint8, device=dev))
+            return out
+        # counts of 15 and more: one entry per 256 (particle, plane) pairs is far above any telescope's need
+        out.update(counts=torch.empty(self.D * ((int(n) + 1) // 2), dtype=torch.uint8, device=dev),
+                   escapes=torch.empty(max(1024, self.D * int(n) // 256), dtype=torch.int64, device=dev))
+        if form == "narrow":
+            out.update(charge=torch.empty(rows, dtype=torch.float32, device=dev),
+                       pos_lo=torch.empty(rows, dtype=torch.int16, device=dev),
+                       pos_hi=torch.empty(rows, dtype=torch.uint8, device=dev))
+        elif form == "packed":
+            layout = self.packed_layout()
+            if layout is None:
+                raise PtbError("the packed compressed rows do not fit this set-up (ptb_packed_layout)")
+            out.update(layout=layout, **{k: torch.empty(rows, dtype=torch.int16, device=dev) for k in ("word0", "word1", "word2")})
+        else:
+            raise ValueError(f"unknown compressed-row form {form!r}")
         return out
 
-    def narrow_ok(self, seed=12345, pilot=32768) -> bool:
-        """Does the narrow compressed-row form (PTB_COMPACT_NARROW) fit this set-up?  Matrices within 4095 x 4095 pixels
-        and a pilot range whose counts of 15 and more fit the escape list (a later overflow is retried)."""
-        if getattr(self, "_narrow_ok", None) is None:
-            ok = all(int(d["column"]) <= 4095 and int(d["row"]) <= 4095 for d in self.devices)
-            if ok:
+    def packed_layout(self):
+        """The PtbPackedLayout of this set-up, or None when PTB_COMPACT_PACKED does not fit it."""
+        if getattr(self, "_packed_layout", 0) == 0:
+            L = N.PtbPackedLayout()
+            self._packed_layout = L if self.lib.ptb_packed_layout(self._h, C.byref(L)) == 0 else None
+        return self._packed_layout
+
+    def compact_form(self, seed=12345, pilot=32768) -> str:
+        """The most compressed row form this set-up supports: "packed" (6-byte rows), "narrow" (7-byte rows) or "wide".
+        The candidates are tried on a pilot range: a form whose escape list or exponent window overflows there is
+        passed over (a later overflow of a chunk is retried by the pipeline)."""
+        if getattr(self, "_compact_form", None) is None:
+            forms = (["packed"] if self.packed_layout() is not None else []) + \
+                    (["narrow"] if all(int(d["column"]) <= 4095 and int(d["row"]) <= 4095 for d in self.devices) else [])
+            chosen = "wide"
+            for form in forms:
                 try:
-                    self.run(0, pilot, seed=seed, capacities=[pilot * 64] * self.D, compact="narrow")
+                    self.run(0, pilot, seed=seed, capacities=[pilot * 64] * self.D, compact=form)
+                    chosen = form
+                    break
                 except PtbError:
-                    ok = False
-            self._narrow_ok = ok
-        return self._narrow_ok
+                    continue
+            self._compact_form = chosen
+        return self._compact_form
+
+    def narrow_ok(self, seed=12345, pilot=32768) -> bool:
+        """Does a form with 4-bit counts and back-to-back rows (narrow or packed) fit this set-up?"""
+        return self.compact_form(seed, pilot) != "wide"
 
     def alloc_tracks(self, n):
         D = self.D
@@ -262,13 +295,20 @@ class Simulator:
                                             s["charge64"].data_ptr() if "charge64" in s else None,
                                             int(s["event"].numel()))
         if compact is not None:
-            if compact.get("narrow"):
-                run.flags |= N.PTB_COMPACT_NARROW
-                run.compact.charge, run.compact.pos_lo = compact["charge"].data_ptr(), compact["pos_lo"].data_ptr()
-                run.compact.pos_hi, run.compact.escapes = compact["pos_hi"].data_ptr(), compact["escapes"].data_ptr()
-                run.compact.escape_capacity = int(compact["escapes"].numel())
-            else:
+            form = compact.get("form", "narrow" if compact.get("narrow") else "wide")
+            if form == "wide":
                 run.compact.hits = compact["hits"].data_ptr()
+            else:
+                run.compact.escapes = compact["escapes"].data_ptr()
+                run.compact.escape_capacity = int(compact["escapes"].numel())
+                if form == "narrow":
+                    run.flags |= N.PTB_COMPACT_NARROW
+                    run.compact.charge, run.compact.pos_lo = compact["charge"].data_ptr(), compact["pos_lo"].data_ptr()
+                    run.compact.pos_hi = compact["pos_hi"].data_ptr()
+                else:
+                    run.flags |= N.PTB_COMPACT_PACKED
+                    run.compact.word0, run.compact.word1 = compact["word0"].data_ptr(), compact["word1"].data_ptr()
+                    run.compact.word2 = compact["word2"].data_ptr()
             run.compact.counts, run.compact.accepted = compact["counts"].data_ptr(), compact["accepted"].data_ptr()
             for d, v in enumerate(compact["plane_first"]):
                 run.compact.plane_first[d] = int(v)
@@ -317,7 +357,7 @@ class Simulator:
             capacities = [4 * n + 4096] * self.D if digitise else [0] * self.D
         for attempt in range(8):
             slabs = self.alloc_slabs(capacities, keep_charge64) if (digitise and not compact) else None
-            cmp_out = self.alloc_compact(n, capacities, narrow=(compact == "narrow")) if compact else None
+            cmp_out = self.alloc_compact(n, capacities, form=compact if isinstance(compact, str) else "wide") if compact else None
             if compact and scratch_rows is None:
                 scratch_rows = [N.default_scratch_rows(int(c)) for c in capacities]
             tracks = tracks_in if tracks_in is not None else (self.alloc_tracks(n) if write_tracks else None)
@@ -332,7 +372,7 @@ class Simulator:
             tot = self.decode_totals(totals, self.D)
             err = tot["error"]
             if err & ~(N.PTB_DEV_BOX_TOO_LARGE | N.PTB_DEV_SLAB_OVERFLOW | N.PTB_DEV_SCRATCH_OVERFLOW |
-                       N.PTB_DEV_COUNT_OVERFLOW):
+                       N.PTB_DEV_COUNT_OVERFLOW | N.PTB_DEV_PACK_OVERFLOW):
                 raise PtbError(f"device reported an internal consistency failure (error bits {err:#x})")
             if err & N.PTB_DEV_BOX_TOO_LARGE:
                 raise PtbError("a cluster bounding box exceeded 2^20 pixels (check pitch / geometry)")
@@ -340,6 +380,8 @@ class Simulator:
                 capacities = [max(int(h), 1) for h in tot["hits"]]
                 scratch_rows = [max(int(r), 1) for r in tot["reserved"]]
                 continue
+            if err & N.PTB_DEV_PACK_OVERFLOW:
+                raise PtbError("the row packer met a charge below its plane's threshold (internal inconsistency)")
             if err & N.PTB_DEV_COUNT_OVERFLOW:
                 raise PtbError("a particle left more than 255 rows on one plane (or the narrow form ran out of escape "
                                "entries): run this range without compact")
@@ -403,62 +445,69 @@ class Simulator:
         return out
 
 
+_ROW_KEYS = {"wide": ("hits",), "narrow": ("charge", "pos_lo", "pos_hi"), "packed": ("word0", "word1", "word2")}
+
+
+def _form_of(c: dict) -> str:
+    return c.get("form") or ("narrow" if c.get("narrow") else "wide")
+
+
 def plane_of(c: dict, plane: int) -> dict:
     """One plane's arrays of a host-side PtbCompactOut (RunResult.compact_host / HostChunk.compact)."""
-    keys = ("charge", "pos_lo", "pos_hi") if c.get("narrow") else ("hits",)
-    out = {k: c[k][plane] for k in keys}
-    out.update(narrow=bool(c.get("narrow")), counts=c["counts"][plane], accepted=c["accepted"], plane=plane,
-               escapes=c.get("escapes"))
+    form = _form_of(c)
+    out = {k: c[k][plane] for k in _ROW_KEYS[form]}
+    out.update(form=form, narrow=form != "wide", counts=c["counts"][plane], accepted=c["accepted"], plane=plane,
+               escapes=c.get("escapes"), layout=c.get("layout"),
+               row_base=int(c["row_base"][plane]) if c.get("row_base") is not None else 0)
     return out
+
+
+def _expand_args(c: dict):
+    """(form, rows, leading pointer arguments of the plane's expansion call) for one plane of a host-side PtbCompactOut."""
+    form = _form_of(c)
+    keys = _ROW_KEYS[form]
+    rows = int(c[keys[0]].shape[0])
+    counts = np.ascontiguousarray(c["counts"], dtype=np.uint8)
+    args = [c[k].ctypes.data if rows else None for k in keys] + [counts.ctypes.data]
+    keep = [counts]                                      # arrays that must outlive the call
+    if form != "wide":
+        esc = c.get("escapes")
+        esc = np.zeros(0, np.uint64) if esc is None else np.ascontiguousarray(esc, dtype=np.uint64)
+        keep.append(esc)
+        args += [esc.ctypes.data if len(esc) else None, len(esc), int(c.get("plane", 0))]
+        if form == "packed":
+            args += [C.byref(c["layout"]), int(c.get("row_base", 0))]
+    args.append(c["accepted"].ctypes.data)
+    return form, rows, args, keep
+
+
+_EXPAND = {"wide": "ptb_expand_hits", "narrow": "ptb_expand_hits_narrow", "packed": "ptb_expand_hits_packed"}
 
 
 def expand_compact(lib, c: dict, n: int, event_base: int, out: np.ndarray | None = None, threads: int = 0) -> np.ndarray:
     """One plane of a PtbCompactOut (host arrays, see plane_of) -> the reference's 18-byte records (``ptb_expand_hits``
-    / ``ptb_expand_hits_narrow``).
+    / ``ptb_expand_hits_narrow`` / ``ptb_expand_hits_packed``).
 
-    wide: hits uint64 rows, counts uint8 [n]; narrow: charge f32, pos_lo u16, pos_hi u8 rows, counts [(n+1)//2] nibble
-    pairs, escapes uint64 (the call's entries for counts of 15 and more) and the plane's index; accepted: uint32
-    [(n+31)//32]; out: optional destination (any writable buffer of that many records, e.g. a
-    slice of a memory-mapped HDF5 dataset)."""
-    narrow = bool(c.get("narrow"))
-    rows = int((c["charge"] if narrow else c["hits"]).shape[0])
+    wide: hits uint64 rows, counts uint8 [n]; narrow: charge f32, pos_lo u16, pos_hi u8 rows; packed: word0..2 u16 rows
+    and the row layout; narrow and packed: counts [(n+1)//2] nibble pairs, escapes uint64 (the call's entries for counts
+    of 15 and more) and the plane's index; accepted: uint32 [(n+31)//32]; out: optional destination (any writable buffer
+    of that many records, e.g. a slice of a memory-mapped HDF5 dataset)."""
+    form, rows, args, _keep = _expand_args(c)
     if out is None:
         out = np.empty(rows, dtype=HITS_DTYPE)
     if out.shape[0] != rows or out.dtype.itemsize != 18 or not out.flags["C_CONTIGUOUS"]:
         raise ValueError("destination must be a contiguous array of as many 18-byte records as the plane has rows")
-    counts = np.ascontiguousarray(c["counts"], dtype=np.uint8)
-    acc, dst = c["accepted"].ctypes.data, out.ctypes.data if rows else None
-    ptr = lambda a: a.ctypes.data if rows else None  # noqa: E731
-    if narrow:
-        esc = c.get("escapes")
-        esc = np.zeros(0, np.uint64) if esc is None else np.ascontiguousarray(esc, dtype=np.uint64)
-        got = lib.ptb_expand_hits_narrow(ptr(c["charge"]), ptr(c["pos_lo"]), ptr(c["pos_hi"]), counts.ctypes.data,
-                                         esc.ctypes.data if len(esc) else None, len(esc), int(c.get("plane", 0)), acc,
-                                         int(n), int(event_base), rows, dst, int(threads))
-    else:
-        got = lib.ptb_expand_hits(ptr(c["hits"]), counts.ctypes.data, acc, int(n), int(event_base), rows, dst, int(threads))
+    got = getattr(lib, _EXPAND[form])(*args, int(n), int(event_base), rows, out.ctypes.data if rows else None, int(threads))
     if got != rows:
         raise PtbError(f"ptb_expand_hits: counts add up to something else than {rows} rows ({got})")
     return out
 
 
 def expand_compact_to_fd(lib, c: dict, n: int, event_base: int, fd: int, file_offset: int, threads: int = 0) -> int:
-    """expand_compact with a file as destination (``ptb_expand_hits_fd`` / ``ptb_expand_hits_narrow_fd``): the plane's
-    records are written to descriptor `fd` from byte `file_offset` on, block by block.  Returns the number of rows."""
-    narrow = bool(c.get("narrow"))
-    rows = int((c["charge"] if narrow else c["hits"]).shape[0])
-    counts = np.ascontiguousarray(c["counts"], dtype=np.uint8)
-    acc = c["accepted"].ctypes.data
-    ptr = lambda a: a.ctypes.data if rows else None  # noqa: E731
-    if narrow:
-        esc = c.get("escapes")
-        esc = np.zeros(0, np.uint64) if esc is None else np.ascontiguousarray(esc, dtype=np.uint64)
-        got = lib.ptb_expand_hits_narrow_fd(ptr(c["charge"]), ptr(c["pos_lo"]), ptr(c["pos_hi"]), counts.ctypes.data,
-                                            esc.ctypes.data if len(esc) else None, len(esc), int(c.get("plane", 0)), acc,
-                                            int(n), int(event_base), rows, int(fd), int(file_offset), int(threads))
-    else:
-        got = lib.ptb_expand_hits_fd(ptr(c["hits"]), counts.ctypes.data, acc, int(n), int(event_base), rows, int(fd),
-                                     int(file_offset), int(threads))
+    """expand_compact with a file as destination (``ptb_expand_hits*_fd``): the plane's records are written to descriptor
+    `fd` from byte `file_offset` on, block by block.  Returns the number of rows."""
+    form, rows, args, _keep = _expand_args(c)
+    got = getattr(lib, _EXPAND[form] + "_fd")(*args, int(n), int(event_base), rows, int(fd), int(file_offset), int(threads))
     if got != rows:
         raise PtbError(f"ptb_expand_hits_fd: {'a write failed' if got == -4 else 'counts and rows disagree'} ({got}, {rows} rows)")
     return rows

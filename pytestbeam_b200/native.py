@@ -18,11 +18,13 @@ PTB_RECYCLE_SLABS = 16
 PTB_ZERO_RADIUS = 32
 PTB_COMPACT = 64
 PTB_COMPACT_NARROW = 128
+PTB_COMPACT_PACKED = 256
 
 PTB_DEV_SCRATCH_OVERFLOW = 1
 PTB_DEV_SLAB_OVERFLOW = 2
 PTB_DEV_BOX_TOO_LARGE = 4
 PTB_DEV_COUNT_OVERFLOW = 8
+PTB_DEV_PACK_OVERFLOW = 16
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PTB_LIB_PATH") or os.path.join(_HERE, "_lib", "libptb_b200.so")   # env: developer builds
@@ -66,7 +68,12 @@ class PtbHitSlab(C.Structure):
 class PtbCompactOut(C.Structure):
     _fields_ = [("hits", C.c_void_p), ("counts", C.c_void_p), ("accepted", C.c_void_p),
                 ("plane_first", C.c_uint64 * (PTB_MAX_PLANES + 1)), ("charge", C.c_void_p), ("pos_lo", C.c_void_p),
-                ("pos_hi", C.c_void_p), ("escapes", C.c_void_p), ("escape_capacity", C.c_uint64)]
+                ("pos_hi", C.c_void_p), ("escapes", C.c_void_p), ("escape_capacity", C.c_uint64),
+                ("word0", C.c_void_p), ("word1", C.c_void_p), ("word2", C.c_void_p)]
+
+
+class PtbPackedLayout(C.Structure):
+    _fields_ = [("exp_min", C.c_uint8 * PTB_MAX_PLANES), ("col_bits", C.c_uint8 * PTB_MAX_PLANES)]
 
 
 class PtbBases(C.Structure):
@@ -90,7 +97,8 @@ class PtbRun(C.Structure):
 EXPORTS = ("ptb_create", "ptb_destroy", "ptb_last_error", "ptb_n_planes", "ptb_workspace_bytes",
            "ptb_prefix", "ptb_simulate", "ptb_pack_hits", "ptb_launch_count", "ptb_measure_fp64_peak",
            "ptb_timing_enable", "ptb_timing_read", "ptb_timing_read_stages", "ptb_correlate", "ptb_digest", "ptb_expand_hits",
-           "ptb_expand_hits_narrow", "ptb_expand_hits_fd", "ptb_expand_hits_narrow_fd")
+           "ptb_expand_hits_narrow", "ptb_expand_hits_fd", "ptb_expand_hits_narrow_fd", "ptb_packed_layout",
+           "ptb_expand_hits_packed", "ptb_expand_hits_packed_fd")
 
 _lib = None
 
@@ -151,6 +159,15 @@ def load() -> C.CDLL:
     L.ptb_expand_hits_narrow_fd.argtypes = [C.c_void_p] * 5 + [C.c_uint64, C.c_int32, C.c_void_p, C.c_uint64, C.c_int64,
                                             C.c_uint64, C.c_int32, C.c_uint64, C.c_int32]
     L.ptb_expand_hits_narrow_fd.restype = C.c_int64
+    L.ptb_packed_layout.argtypes = [C.c_void_p, C.POINTER(PtbPackedLayout)]
+    L.ptb_packed_layout.restype = C.c_int
+    L.ptb_expand_hits_packed.argtypes = [C.c_void_p] * 5 + [C.c_uint64, C.c_int32, C.POINTER(PtbPackedLayout), C.c_uint64,
+                                         C.c_void_p, C.c_uint64, C.c_int64, C.c_uint64, C.c_void_p, C.c_int32]
+    L.ptb_expand_hits_packed.restype = C.c_int64
+    L.ptb_expand_hits_packed_fd.argtypes = [C.c_void_p] * 5 + [C.c_uint64, C.c_int32, C.POINTER(PtbPackedLayout),
+                                            C.c_uint64, C.c_void_p, C.c_uint64, C.c_int64, C.c_uint64, C.c_int32,
+                                            C.c_uint64, C.c_int32]
+    L.ptb_expand_hits_packed_fd.restype = C.c_int64
     L.ptb_launch_count.argtypes = []
     L.ptb_launch_count.restype = C.c_uint64
     L.ptb_measure_fp64_peak.argtypes = [C.c_void_p]

@@ -4,11 +4,12 @@ buffers (1e10 electrons produce 1.3 TB of hits, far more than fits
 ``ChunkPipeline.run`` keeps everything on the device (throughput measurements, digest sink);
 ``ChunkPipeline.run_to_host`` additionally lands every chunk's hit tables in pinned host memory on a second stream,
 double-buffered so that the copy of chunk i overlaps the kernels of chunk i+1.  What travels over PCIe is the
-compressed-row form of the tables (``PtbCompactOut`` in include/ptb.h).  Its narrow variant -- 7-byte rows in three
-arrays with the planes back to back, 4-bit counts per particle and plane (larger ones on an escape list), the trigger mask: 55 instead of 118 bytes per
-electron on the default telescope -- is used whenever the set-up fits it (``Simulator.narrow_ok``); the wide one (8-byte
-rows, count bytes: 66 bytes per electron) otherwise.  ``HostChunk.records`` expands either to the reference's 18-byte
-rows (``ptb_expand_hits`` / ``ptb_expand_hits_narrow``), straight into the caller's buffer if it names one.
+compressed-row form of the tables (``PtbCompactOut`` in include/ptb.h): per hit the column, row and charge, per (particle,
+plane) a row count, per particle its trigger bit.  Of its three variants the pipeline takes the most compressed one the
+set-up fits (``Simulator.compact_form``): packed (6-byte rows in three u16 arrays, planes back to back, 4-bit counts with
+larger ones on an escape list: 48 bytes per electron on the default telescope against 118 for the slabs), narrow (7-byte
+rows: 55) or wide (8-byte rows, count bytes: 66).  ``HostChunk.records`` expands any of them to the reference's 18-byte
+rows (``ptb_expand_hits*``), straight into the caller's buffer if it names one; ``records_to_fd`` into a file.
 """
 from __future__ import annotations
 
@@ -19,7 +20,7 @@ from . import native as N
 from .engine import (_BASES_WORDS, _TOTALS_WORDS, HITS_DTYPE, PtbError, Simulator, expand_compact,
                      expand_compact_to_fd, plane_of)
 
-_RETRY = N.PTB_DEV_SLAB_OVERFLOW | N.PTB_DEV_SCRATCH_OVERFLOW | N.PTB_DEV_COUNT_OVERFLOW
+_RETRY = N.PTB_DEV_SLAB_OVERFLOW | N.PTB_DEV_SCRATCH_OVERFLOW | N.PTB_DEV_COUNT_OVERFLOW | N.PTB_DEV_PACK_OVERFLOW
 
 
 def bind_host_to_gpu(index: int) -> bool:
@@ -84,13 +85,23 @@ class HostChunk:
 
 class ChunkPipeline:
     def __init__(self, sim: Simulator, chunk: int, *, n_buffers: int = 2, capacities=None, host: bool = False,
-                 seed: int = 0, scratch_rows=None, compact: bool | None = None, narrow: bool | None = None):
+                 seed: int = 0, scratch_rows=None, compact: bool | None = None, narrow: bool | None = None,
+                 form: str | None = None):
         self.sim, self.chunk, self.seed = sim, int(chunk), int(seed)
         self.compact = bool(host) if compact is None else bool(compact)
         if self.compact and not host:
             raise PtbError("the compressed-row output exists for the trip to the host: use host=True")
-        # the narrow compressed rows whenever the set-up fits them (12-bit pixel indices, <= 15 rows per particle and plane)
-        self.narrow = self.compact and (sim.narrow_ok() if narrow is None else bool(narrow))
+        # the most compressed row form the set-up fits (Simulator.compact_form), unless the caller names one
+        # (form = "wide" | "narrow" | "packed"; narrow = True / False is the older spelling of "narrow" / "wide")
+        if not self.compact:
+            self.form = None
+        elif form is not None:
+            self.form = form
+        elif narrow is not None:
+            self.form = "narrow" if narrow else "wide"
+        else:
+            self.form = sim.compact_form()
+        self.narrow = self.form in ("narrow", "packed")     # 4-bit counts, rows of all planes back to back
         self.flags = N.PTB_DIGITISE | N.PTB_RECYCLE_SLABS | (N.PTB_COMPACT if self.compact else 0)
         self.caps = list(capacities) if capacities is not None else sim.default_capacities(self.chunk)
         self.rows = list(scratch_rows) if scratch_rows is not None else sim.default_scratch_rows(self.chunk)
@@ -102,7 +113,7 @@ class ChunkPipeline:
                  "totals": torch.zeros(_TOTALS_WORDS, dtype=torch.int64, device=dev),
                  "done": torch.cuda.Event(), "copied": torch.cuda.Event()}
             if self.compact:
-                s["cmp"] = sim.alloc_compact(self.chunk, self.caps, narrow=self.narrow)
+                s["cmp"] = sim.alloc_compact(self.chunk, self.caps, form=self.form)
                 s["h_cmp"] = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in s["cmp"].items()
                               if isinstance(v, torch.Tensor)}
             else:
@@ -213,7 +224,8 @@ class ChunkPipeline:
                 elif self.compact and self.narrow:
                     c, h = s["cmp"], s["h_cmp"]
                     m, w, half = sum(tot["hits"]), (n_i + 31) // 32, (n_i + 1) // 2
-                    for k in ("charge", "pos_lo", "pos_hi"):     # the planes' rows lie back to back: one copy per array
+                    row_keys = ("charge", "pos_lo", "pos_hi") if self.form == "narrow" else ("word0", "word1", "word2")
+                    for k in row_keys:                           # the planes' rows lie back to back: one copy per array
                         h[k][:m].copy_(c[k][:m], non_blocking=True)
                     if n_i == self.chunk:
                         h["counts"].copy_(c["counts"], non_blocking=True)
@@ -223,17 +235,23 @@ class ChunkPipeline:
                     n_esc = tot["escapes"]
                     if n_esc:
                         h["escapes"][:n_esc].copy_(c["escapes"][:n_esc], non_blocking=True)
-                    nbytes += 7 * m + D * half + 4 * w + 8 * n_esc
+                    nbytes += sum(h[k].element_size() for k in row_keys) * m + D * half + 4 * w + 8 * n_esc
                     s["copied"].record(self.copy_stream)
                     if consume is not None:
                         first_row = np.concatenate([[0], np.cumsum(tot["hits"])]).astype(np.int64)
                         cut = lambda k, dt: [h[k].numpy().view(dt)[first_row[d]:first_row[d + 1]] for d in range(D)]  # noqa: E731
-                        chunk = HostChunk(sim.lib, i, first_i, n_i, D, tot, ev_base, t_base, compact={
-                            "narrow": True, "charge": cut("charge", np.float32), "pos_lo": cut("pos_lo", np.uint16),
-                            "pos_hi": cut("pos_hi", np.uint8),
-                            "counts": h["counts"].numpy()[:D * half].reshape(D, half),
-                            "escapes": h["escapes"].numpy().view(np.uint64)[:n_esc],
-                            "accepted": h["accepted"].numpy().view(np.uint32)[:w]})
+                        host = {"form": self.form, "narrow": True,
+                                "counts": h["counts"].numpy()[:D * half].reshape(D, half),
+                                "escapes": h["escapes"].numpy().view(np.uint64)[:n_esc],
+                                "accepted": h["accepted"].numpy().view(np.uint32)[:w]}
+                        if self.form == "narrow":
+                            host.update(charge=cut("charge", np.float32), pos_lo=cut("pos_lo", np.uint16),
+                                        pos_hi=cut("pos_hi", np.uint8))
+                        else:
+                            host.update(word0=cut("word0", np.uint16), word1=cut("word1", np.uint16),
+                                        word2=cut("word2", np.uint16), layout=c["layout"],
+                                        row_base=[int(v) for v in first_row[:D]])
+                        chunk = HostChunk(sim.lib, i, first_i, n_i, D, tot, ev_base, t_base, compact=host)
                 elif self.compact:
                     c, h = s["cmp"], s["h_cmp"]
                     pf, m = c["plane_first"], sum(tot["hits"])

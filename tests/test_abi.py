@@ -30,8 +30,8 @@ def test_struct_sizes_match_header_layout():
     assert ctypes.sizeof(native.PtbHitSlab) == 48
     assert ctypes.sizeof(native.PtbBases) == 16 + 8 * 32
     assert ctypes.sizeof(native.PtbTotals) == 8 * 32 + 8 * 5 + 8 + 8 * 32
-    assert ctypes.sizeof(native.PtbCompactOut) == 24 + 8 * 33 + 40
-    assert ctypes.sizeof(native.PtbRun) == 32 + 8 + 72 + 48 * 32 + 8 * 5 + 8 * 32 + 24 + 8 * 33 + 40
+    assert ctypes.sizeof(native.PtbCompactOut) == 24 + 8 * 33 + 40 + 24
+    assert ctypes.sizeof(native.PtbRun) == 32 + 8 + 72 + 48 * 32 + 8 * 5 + 8 * 32 + 24 + 8 * 33 + 40 + 24
 
 
 def test_struct_layout_agrees_with_a_c_compiler(tmp_path):
@@ -39,7 +39,7 @@ def test_struct_layout_agrees_with_a_c_compiler(tmp_path):
     import subprocess
     structs = {"PtbBeam": native.PtbBeam, "PtbDevice": native.PtbDevice, "PtbOptions": native.PtbOptions,
                "PtbInjected": native.PtbInjected, "PtbTrackTable": native.PtbTrackTable,
-               "PtbHitSlab": native.PtbHitSlab, "PtbCompactOut": native.PtbCompactOut, "PtbBases": native.PtbBases, "PtbTotals": native.PtbTotals,
+               "PtbHitSlab": native.PtbHitSlab, "PtbCompactOut": native.PtbCompactOut, "PtbPackedLayout": native.PtbPackedLayout, "PtbBases": native.PtbBases, "PtbTotals": native.PtbTotals,
                "PtbRun": native.PtbRun}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "ptb.h"', 'int main(void) {']
     for name, st in structs.items():

@@ -40,9 +40,32 @@ def _plane(form, counts, words, hits, cols, plane=3):
             "counts": (c[0::2] | (c[1::2] << 4)).astype(np.uint8), "accepted": words, "escapes": esc, "plane": plane}
 
 
+def _packed_plane(counts, words, cols, plane=2, exp_min=123, col_bits=11, row_base=777):
+    """The host arrays of one plane in the packed form: 48-bit rows (f32 mantissa | exponent - exp_min << 23 | column << 27
+    | row << (27 + col_bits)) as three u16 arrays, nibble counts, the row layout; on the escape list the counts of 15
+    and more and the charges beyond the format's 16 binades (the rows then keep exponent 15), among entries that belong
+    to other planes."""
+    base = _plane("narrow", counts, words, None, cols, plane=plane)
+    col, row, q = cols
+    bits = q.view(np.uint32).astype(np.uint64)
+    off = (bits >> np.uint64(23)) - np.uint64(exp_min)
+    big = np.flatnonzero(off > 15)
+    esc = (np.uint64(1) << np.uint64(63)) | ((big.astype(np.uint64) + np.uint64(row_base)) << np.uint64(32)) | bits[big]
+    other = (np.uint64(1) << np.uint64(63)) | ((big.astype(np.uint64) + np.uint64(row_base + len(q))) << np.uint64(32)) | np.uint64(5)
+    off = np.minimum(off, 15)
+    w = (bits & np.uint64(0x7FFFFF)) | (off << np.uint64(23)) | (col << np.uint64(27)) | (row << np.uint64(27 + col_bits))
+    layout = native.PtbPackedLayout()
+    layout.exp_min[plane], layout.col_bits[plane] = exp_min, col_bits
+    return {"form": "packed", "narrow": True, "word0": (w & np.uint64(0xFFFF)).astype(np.uint16),
+            "word1": ((w >> np.uint64(16)) & np.uint64(0xFFFF)).astype(np.uint16), "word2": (w >> np.uint64(32)).astype(np.uint16),
+            "counts": base["counts"], "accepted": words, "plane": plane, "layout": layout, "row_base": row_base,
+            "escapes": np.random.RandomState(1).permutation(np.concatenate([base["escapes"], esc, other]))}
+
+
 def _short(p):
     """The same plane with its last row cut off (counts then promise one row too many)."""
-    keys = ("charge", "pos_lo", "pos_hi") if p["narrow"] else ("hits",)
+    keys = {"packed": ("word0", "word1", "word2"), "narrow": ("charge", "pos_lo", "pos_hi")}.get(p.get("form"), None)
+    keys = keys or (("charge", "pos_lo", "pos_hi") if p["narrow"] else ("hits",))
     return dict(p, **{k: p[k][:-1] for k in keys})
 
 
@@ -122,3 +145,29 @@ def test_expand_into_a_file_equals_expand_into_memory(tmp_path, form, n, threads
     if len(want):
         with pytest.raises(PtbError):
             expand_compact_to_fd(lib, plane, n, 99, 10_000, 0)      # no such descriptor
+
+
+@pytest.mark.parametrize("n,threads", [(0, 0), (1, 1), (33, 2), (1000, 0), (600_001, 5)])
+def test_packed_rows_expand_to_the_same_records(tmp_path, n, threads):
+    """ptb_expand_hits_packed / _packed_fd: the 48-bit rows (charges between 2^-4 and 2^5 ke above a threshold of 2^-4,
+    11 column bits) give the records of the wide form, in memory and in a file; a short row array is refused."""
+    import os
+    from pytestbeam_b200.engine import expand_compact_to_fd
+    lib = native.load()
+    counts, acc, words, hits, cols = _case(n, seed=n + 21, max_count=40)
+    col, row, q = cols
+    q[::97] *= np.float32(3000.0)                      # some charges far beyond the 16 binades above 2^-4
+    q[5::1013] = np.float32(2048.0 * 1.5)              # and some in the top binade itself (exponent 15, no escape entry)
+    plane = _packed_plane(counts, words, cols)
+    want = _expected(counts, acc, cols, 4242)
+    assert expand_compact(lib, plane, n, event_base=4242, threads=threads).tobytes() == want.tobytes()
+    path = tmp_path / "rows.bin"
+    fd = os.open(str(path), os.O_RDWR | os.O_CREAT)
+    try:
+        assert expand_compact_to_fd(lib, plane, n, 4242, fd, 0, threads=threads) == len(want)
+    finally:
+        os.close(fd)
+    assert path.read_bytes() == want.tobytes()
+    if len(want):
+        with pytest.raises(PtbError):
+            expand_compact(lib, _short(plane), n, event_base=0)

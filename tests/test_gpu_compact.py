@@ -30,7 +30,7 @@ def _count_sums(c):
     return out
 
 
-@pytest.mark.parametrize("form", [True, "narrow"])
+@pytest.mark.parametrize("form", [True, "narrow", "packed"])
 @pytest.mark.parametrize("name,first,n", [("c1", 0, 50_003), ("c3", 77, 40_000), ("c4", 1_000_000_007, 33_333),
                                           ("c1", 5, 1), ("c1", 0, 31), ("c1", 64, 32)])
 def test_compact_tables_equal_the_slab_tables(name, first, n, form):
@@ -41,7 +41,7 @@ def test_compact_tables_equal_the_slab_tables(name, first, n, form):
     b = sim.run(first, n, seed=2024, compact=form)
     assert a.totals["hits"] == b.totals["hits"] and b.totals["error"] == 0
     c = b.compact_host()
-    assert bool(c.get("narrow")) == (form == "narrow")
+    assert c["form"] == (form if isinstance(form, str) else "wide")
     assert _count_sums(c) == b.totals["hits"]
     mask = np.unpackbits(c["accepted"].view(np.uint8), bitorder="little")[:n]
     assert int(mask.sum()) == b.totals["accepted"]
@@ -57,7 +57,7 @@ def test_compact_deterministic_vs_oracle_with_event_base():
     sim = _sim(setup)
     lo = 5000
     first = sim.run(0, lo, injected=H.injected_for(sim, run, 0, lo))
-    for form in (True, "narrow"):
+    for form in (True, "narrow", "packed"):
         second = sim.run(lo, n - lo, injected=H.injected_for(sim, run, lo, n - lo), bases_in=first.bases_out, compact=form)
         assert second.event_base == int(run.variates.accepted[:lo].sum())
         for d in range(sim.D):
@@ -148,9 +148,9 @@ def test_pipeline_to_host_equals_one_call(chunk, n_total):
     sim = _sim(H.setup("c4", n_total))
     first, seed = 12_345, 77
     whole = sim.run(first, n_total, seed=seed)
-    for compact, narrow in ((True, True), (True, False), (False, False)):
-        pipe = ChunkPipeline(sim, chunk, host=True, seed=seed, compact=compact, narrow=narrow)
-        assert pipe.narrow == narrow
+    for compact, narrow, form in ((True, True, "packed"), (True, True, "narrow"), (True, False, "wide"), (False, False, None)):
+        pipe = ChunkPipeline(sim, chunk, host=True, seed=seed, compact=compact, form=form)
+        assert pipe.narrow == narrow and pipe.form == form
         got = [[] for _ in range(sim.D)]
         bases = []
 
@@ -165,7 +165,7 @@ def test_pipeline_to_host_equals_one_call(chunk, n_total):
         assert sum(b[1] for b in bases) == n_total
         for d in range(sim.D):
             assert np.concatenate(got[d]).tobytes() == whole.hits_numpy(d).tobytes(), (compact, narrow, d)
-    assert ChunkPipeline(sim, chunk, host=True, seed=seed).narrow        # the default for a telescope that fits
+    assert ChunkPipeline(sim, chunk, host=True, seed=seed).form == "packed"      # the default for a telescope that fits
 
 
 def test_pipeline_retries_a_chunk_that_overflows_instead_of_raising():
@@ -175,8 +175,8 @@ def test_pipeline_retries_a_chunk_that_overflows_instead_of_raising():
     n_total, chunk, seed = 60_000, 20_000, 5
     sim = _sim(H.setup("c1", n_total))
     whole = sim.run(0, n_total, seed=seed)
-    for compact, narrow in ((True, True), (True, False), (False, False)):
-        pipe = ChunkPipeline(sim, chunk, host=True, seed=seed, compact=compact, narrow=narrow, capacities=[500] * sim.D,
+    for compact, narrow, form in ((True, True, "packed"), (True, True, "narrow"), (True, False, "wide"), (False, False, None)):
+        pipe = ChunkPipeline(sim, chunk, host=True, seed=seed, compact=compact, form=form, capacities=[500] * sim.D,
                              scratch_rows=[700] * sim.D)
         got = [[] for _ in range(sim.D)]
         pipe.run_to_host(0, 3, consume=lambda c: [got[d].append(c.records(d).copy()) for d in range(sim.D)])
@@ -379,12 +379,13 @@ def test_compressed_rows_on_random_telescopes(seed):
     slab = sim.run(first, n, seed=seed)
     if max(slab.totals["hits"]) > 200 * n:
         pytest.skip("a geometry with hundreds of rows per particle: covered by the fine-pitch tests")
-    forms = [True] + (["narrow"] if all(d["column"] <= 4095 and d["row"] <= 4095 for d in devices) else [])
+    forms = [True] + (["narrow"] if all(d["column"] <= 4095 and d["row"] <= 4095 for d in devices) else []) + \
+            (["packed"] if sim.packed_layout() is not None else [])
     for form in forms:
         try:
             c = sim.run(first, n, seed=seed, compact=form)
-        except PtbError as exc:                     # more than 255 rows of one particle on a plane: the documented refusal
-            assert "255" in str(exc)
+        except PtbError as exc:     # the documented refusals: more than 255 rows of one particle on a plane, or (packed
+            assert "255" in str(exc) or "binades" in str(exc)     # rows) a charge 16 binades above a tiny threshold
             continue
         assert c.totals["hits"] == slab.totals["hits"]
         host = c.compact_host()
@@ -401,3 +402,56 @@ def test_compressed_rows_on_random_telescopes(seed):
     pipe.run_to_host(first, 0, consume=lambda ch: [got[d].append(ch.records(d).copy()) for d in range(sim.D)], n_total=n)
     for d in range(sim.D):
         assert np.concatenate(got[d]).tobytes() == slab.hits_numpy(d).tobytes(), (pipe.narrow, names[d])
+
+
+def test_packed_layout_follows_the_geometry():
+    """ptb_packed_layout: 21 bits of column + row index and a positive threshold, else the form is refused -- by the
+    layout call, by ptb_simulate and therefore by the pipeline's choice of form."""
+    from pytestbeam_b200 import config as cfg
+    from pytestbeam_b200.engine import PtbError, Simulator
+    beam, devices, materials, names = H.setup("c1", 1000)
+    L = Simulator(beam, devices, materials).packed_layout()
+    assert [L.col_bits[d] for d in range(7)] == [11] * 6 + [9]
+    assert [L.exp_min[d] for d in range(7)] == [123] * 6 + [127]          # 0.1 ke = 1.6 x 2^-4, 1 ke = 2^0 (bias 127)
+    for change in ({"threshold": 0}, {"column": 4000, "row": 1500}):
+        setup = cfg.c1(1000)
+        setup["devices"]["mimosa26_p4"].update(change)
+        sim = Simulator(*cfg.flatten(setup)[:3])
+        assert sim.packed_layout() is None and sim.compact_form() == "narrow"
+        with pytest.raises(PtbError):
+            sim.run(0, 1000, seed=1, compact="packed")
+
+
+def test_packed_rows_with_charges_beyond_their_sixteen_binades():
+    """A low threshold narrows the window of the packed rows (16 binades from the threshold up): the charges beyond it
+    travel on the escape list and the expanded tables still equal the slab tables, for one call and through the host
+    pipeline."""
+    from pytestbeam_b200 import config as cfg
+    from pytestbeam_b200.engine import Simulator
+    from pytestbeam_b200.pipeline import ChunkPipeline
+    n = 60_000
+    for thr in (1, 0.5, 0.25, 2):
+        setup = cfg.c1(n)
+        setup["devices"]["mimosa26_p2"]["threshold"] = thr
+        beam, devices, materials, names = cfg.flatten(setup)
+        sim = Simulator(beam, devices, materials)
+        slab = sim.run(0, n, seed=17)
+        L = sim.packed_layout()
+        top = np.float32(2.0) ** np.float32(int(L.exp_min[1]) - 127 + 16)
+        beyond = int((slab.hits_numpy(1)["charge"] >= top).sum())
+        if 30 <= beyond <= 1200:
+            break
+    else:
+        pytest.skip("no threshold of the list leaves a few hundred charges beyond the window")
+    c = sim.run(0, n, seed=17, compact="packed")
+    assert c.totals["error"] == 0
+    esc = c.compact_host()["escapes"]
+    assert int((esc >> np.uint64(63)).sum()) >= beyond          # (other planes may add a few of their own)
+    for d in range(sim.D):
+        assert c.hits_numpy(d).tobytes() == slab.hits_numpy(d).tobytes(), names[d]
+    pipe = ChunkPipeline(sim, 16_384, host=True, seed=17, form="packed")
+    got = [[] for _ in range(sim.D)]
+    pipe.run_to_host(0, 0, consume=lambda ch: [got[d].append(ch.records(d).copy()) for d in range(sim.D)], n_total=n)
+    assert pipe.retries == 0
+    for d in range(sim.D):
+        assert np.concatenate(got[d]).tobytes() == slab.hits_numpy(d).tobytes(), names[d]
