@@ -223,8 +223,11 @@ class Simulator:
             chosen = "wide"
             for form in forms:
                 try:
-                    self.run(0, pilot, seed=seed, capacities=[pilot * 64] * self.D, compact=form)
+                    r = self.run(0, pilot, seed=seed, capacities=[pilot * 64] * self.D, compact=form)
                     chosen = form
+                    if self._hits_per_particle is None:      # the same pilot sizes the buffers (hits_per_particle)
+                        self._hits_per_particle = np.array(r.totals["hits"], dtype=np.float64) / pilot
+                        self._rows_per_particle = np.array(r.totals["reserved"], dtype=np.float64) / pilot
                     break
                 except PtbError:
                     continue
