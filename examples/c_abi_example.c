@@ -4,10 +4,11 @@
  * first rows of the last plane.
  *
  *   nvcc -x c -I include -o c_abi_example examples/c_abi_example.c -L pytestbeam_b200/_lib -lptb_b200 -lcudart
- *   LD_LIBRARY_PATH=pytestbeam_b200/_lib ./c_abi_example [n_electrons] [seed] [file for the last plane's records]
+ *   LD_LIBRARY_PATH=pytestbeam_b200/_lib ./c_abi_example [n_electrons] [seed] [file for the last plane's records] [narrow|packed]
  *
- * With a file name the same particles run once more in the narrow compressed-row form (what a caller ships over PCIe),
- * and the library expands the last plane's rows straight into that file (ptb_expand_hits_narrow_fd).
+ * With a file name the same particles run once more in a compressed-row form (what a caller ships over PCIe: 7-byte
+ * "narrow" rows by default, 6-byte "packed" rows on request), and the library expands the last plane's rows straight
+ * into that file (ptb_expand_hits_narrow_fd / ptb_expand_hits_packed_fd).
  */
 #include <fcntl.h>
 #include <unistd.h>
@@ -118,7 +119,7 @@ int main(int argc, char **argv)
         }
     }
     if (argc > 3) {
-        /* the same range as compressed rows: 7 bytes per hit + 4 bits per (particle, plane) + 1 bit per particle */
+        /* the same range as compressed rows: 7 (narrow) or 6 (packed) bytes per hit + 4 bits per (particle, plane) + 1 bit per particle */
         uint64_t rows_cap = 0;
         memset(&run.compact, 0, sizeof(run.compact));
         for (int d = 0; d < 7; ++d) {
@@ -127,14 +128,26 @@ int main(int argc, char **argv)
         }
         run.compact.plane_first[7] = rows_cap;
         const uint64_t half = (n + 1) / 2, words = (n + 31) / 32;
+        const int       packed = argc > 4 && strcmp(argv[4], "packed") == 0;
+        PtbPackedLayout layout;
+        if (packed && ptb_packed_layout(h, &layout) != PTB_OK) {
+            fprintf(stderr, "ptb_packed_layout: %s\n", ptb_last_error(h));
+            return 1;
+        }
         run.compact.escape_capacity = 4096;
-        CK(cudaMalloc((void **)&run.compact.charge, rows_cap * sizeof(float)));
-        CK(cudaMalloc((void **)&run.compact.pos_lo, rows_cap * sizeof(uint16_t)));
-        CK(cudaMalloc((void **)&run.compact.pos_hi, rows_cap));
+        if (packed) {
+            CK(cudaMalloc((void **)&run.compact.word0, rows_cap * sizeof(uint16_t)));
+            CK(cudaMalloc((void **)&run.compact.word1, rows_cap * sizeof(uint16_t)));
+            CK(cudaMalloc((void **)&run.compact.word2, rows_cap * sizeof(uint16_t)));
+        } else {
+            CK(cudaMalloc((void **)&run.compact.charge, rows_cap * sizeof(float)));
+            CK(cudaMalloc((void **)&run.compact.pos_lo, rows_cap * sizeof(uint16_t)));
+            CK(cudaMalloc((void **)&run.compact.pos_hi, rows_cap));
+        }
         CK(cudaMalloc((void **)&run.compact.counts, 7 * half));
         CK(cudaMalloc((void **)&run.compact.accepted, words * sizeof(uint32_t)));
         CK(cudaMalloc((void **)&run.compact.escapes, run.compact.escape_capacity * sizeof(uint64_t)));
-        run.flags = PTB_DIGITISE | PTB_RECYCLE_SLABS | PTB_COMPACT | PTB_COMPACT_NARROW;
+        run.flags = PTB_DIGITISE | PTB_RECYCLE_SLABS | PTB_COMPACT | (packed ? PTB_COMPACT_PACKED : PTB_COMPACT_NARROW);
         rc = ptb_simulate(h, &run, NULL);
         if (rc != PTB_OK) {
             fprintf(stderr, "ptb_simulate (compressed rows): %d %s\n", rc, ptb_last_error(h));
@@ -147,15 +160,10 @@ int main(int argc, char **argv)
         }
         uint64_t first6 = 0; /* the planes' rows lie back to back */
         for (int d = 0; d < 6; ++d) first6 += tot.hits[d];
-        const uint64_t m = tot.hits[6];
-        float         *q = malloc((m ? m : 1) * sizeof(float));
-        uint16_t      *lo = malloc((m ? m : 1) * sizeof(uint16_t));
-        uint8_t       *hi = malloc(m ? m : 1), *cnt = malloc(half);
+        const uint64_t m = tot.hits[6], mm = m ? m : 1;
+        uint8_t       *cnt = malloc(half);
         uint32_t      *acc = malloc(words * sizeof(uint32_t));
         uint64_t      *esc = malloc((tot.escapes ? tot.escapes : 1) * sizeof(uint64_t));
-        CK(cudaMemcpy(q, run.compact.charge + first6, m * sizeof(float), cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(lo, run.compact.pos_lo + first6, m * sizeof(uint16_t), cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(hi, run.compact.pos_hi + first6, m, cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(cnt, run.compact.counts + 6 * half, half, cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(acc, run.compact.accepted, words * sizeof(uint32_t), cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(esc, run.compact.escapes, tot.escapes * sizeof(uint64_t), cudaMemcpyDeviceToHost));
@@ -164,10 +172,26 @@ int main(int argc, char **argv)
             perror(argv[3]);
             return 1;
         }
-        const int64_t wrote = ptb_expand_hits_narrow_fd(q, lo, hi, cnt, esc, tot.escapes, 6, acc, n, 0, m, fd, 0, 0);
+        int64_t wrote;
+        if (packed) {
+            uint16_t *w0 = malloc(mm * 2), *w1 = malloc(mm * 2), *w2 = malloc(mm * 2);
+            CK(cudaMemcpy(w0, run.compact.word0 + first6, m * 2, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(w1, run.compact.word1 + first6, m * 2, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(w2, run.compact.word2 + first6, m * 2, cudaMemcpyDeviceToHost));
+            wrote = ptb_expand_hits_packed_fd(w0, w1, w2, cnt, esc, tot.escapes, 6, &layout, first6, acc, n, 0, m, fd, 0, 0);
+        } else {
+            float    *q = malloc(mm * sizeof(float));
+            uint16_t *lo = malloc(mm * sizeof(uint16_t));
+            uint8_t  *hi = malloc(mm);
+            CK(cudaMemcpy(q, run.compact.charge + first6, m * sizeof(float), cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(lo, run.compact.pos_lo + first6, m * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(hi, run.compact.pos_hi + first6, m, cudaMemcpyDeviceToHost));
+            wrote = ptb_expand_hits_narrow_fd(q, lo, hi, cnt, esc, tot.escapes, 6, acc, n, 0, m, fd, 0, 0);
+        }
         close(fd);
-        printf("file rows %lld of %llu (%llu bytes of compressed rows for all planes)\n", (long long)wrote,
-               (unsigned long long)m, (unsigned long long)(7 * (first6 + m) + 7 * half + 4 * words + 8 * tot.escapes));
+        printf("file rows %lld of %llu (%s rows: %llu bytes of compressed rows for all planes)\n", (long long)wrote,
+               (unsigned long long)m, packed ? "packed" : "narrow",
+               (unsigned long long)((packed ? 6 : 7) * (first6 + m) + 7 * half + 4 * words + 8 * tot.escapes));
         if (wrote != (int64_t)m) return 1;
     }
     ptb_destroy(h);

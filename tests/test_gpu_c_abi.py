@@ -43,3 +43,9 @@ def test_plain_c_caller_matches_the_python_host(tmp_path):
     # the narrow compressed rows, expanded by the library straight into a file: the last plane's records, byte for byte
     assert int(re.search(r"file rows (\d+)", out.stdout).group(1)) == res.totals["hits"][-1]
     assert open(rows_file, "rb").read() == res.hits_numpy(len(devices) - 1).tobytes()
+    # and the packed ones (ptb_packed_layout, ptb_expand_hits_packed_fd)
+    os.remove(rows_file)
+    out = subprocess.run([exe, str(n), str(seed), rows_file, "packed"], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert "packed rows" in out.stdout
+    assert open(rows_file, "rb").read() == res.hits_numpy(len(devices) - 1).tobytes()
