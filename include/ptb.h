@@ -164,14 +164,15 @@ typedef struct PtbHitSlab {
  * 48 bytes per electron on the default telescope: this is what travels over PCIe.
  */
 typedef struct PtbCompactOut {
-    uint64_t *hits;     /* column | row << 16 | (f32 charge bits) << 32; unused with PTB_COMPACT_NARROW */
-    uint8_t  *counts;   /* [D][n] rows of particle k on plane d; [D][(n+1)/2] nibble pairs with PTB_COMPACT_NARROW */
+    uint64_t *hits;     /* column | row << 16 | (f32 charge bits) << 32; unused with PTB_COMPACT_NARROW / _PACKED */
+    uint8_t  *counts;   /* [D][n] rows of particle k on plane d; [D][(n+1)/2] nibble pairs with PTB_COMPACT_NARROW / _PACKED */
     uint32_t *accepted; /* [(n+31)/32] trigger mask, bit j of word g = particle first + 32 g + j */
     uint64_t  plane_first[PTB_MAX_PLANES + 1]; /* first row of every plane's region in hits; [D] = rows of hits in all */
     float    *charge;   /* PTB_COMPACT_NARROW: the three row arrays, plane_first[D] rows each */
     uint16_t *pos_lo;
     uint8_t  *pos_hi;
-    uint64_t *escapes;  /* PTB_COMPACT_NARROW / _PACKED: counts of 15 and more (see above), escape_capacity entries */
+    uint64_t *escapes;  /* PTB_COMPACT_NARROW / _PACKED: counts of 15 and more, out-of-window charges (see above);
+                           escape_capacity entries */
     uint64_t  escape_capacity;
     uint16_t *word0, *word1, *word2; /* PTB_COMPACT_PACKED: the three row arrays, plane_first[D] rows each */
 } PtbCompactOut;
