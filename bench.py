@@ -368,6 +368,41 @@ def shard_check(job, args):
     return result
 
 
+def link_probe(job, nbytes: int = 1 << 29, reps: int = 4):
+    """What bounds the end-to-end rate on this box: every rank copies `nbytes` from its GPU into pinned host memory --
+    alone (rank 0 only: the PCIe link) and all ranks at once (what the host takes in).  GB/s; None on ranks != 0."""
+    torch = job.torch
+    src = torch.empty(nbytes, dtype=torch.uint8, device=job.sim.device).fill_(1)
+    dst = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+
+    def rate():
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        for _ in range(reps):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        return reps * nbytes / (time.perf_counter() - t) / 1e9
+
+    dst.copy_(src)
+    job.sync_all()
+    alone = rate() if job.rank == 0 else 0.0
+    job.sync_all()
+    together = rate()
+    job.sync_all()
+    t = torch.tensor([together], dtype=torch.float64, device=job.sim.device)
+    parts = [torch.zeros_like(t) for _ in range(job.world)]
+    if job.world > 1:
+        job.dist.all_gather(parts, t)
+    else:
+        parts = [t]
+    if job.rank != 0:
+        return None
+    per_rank = [round(float(p[0]), 1) for p in parts]
+    return {"link_alone_GBps": round(alone, 1), "all_ranks_at_once_GBps": per_rank, "sum_GBps": round(sum(per_rank), 1),
+            "what": "device-to-host copies of 512 MiB into pinned memory: rank 0 alone (its PCIe link), then every rank at "
+                    "the same time (what the host takes in); the end-to-end rate x bytes_per_electron cannot exceed the sum"}
+
+
 def entry_point_rate(n: int, seed: int):
     """The reference-shaped entry: hit.tracks + device.calculate_device_hit of the drop-in modules, files included
     (seven *_dut.h5 tables streamed to a scratch directory)."""
@@ -469,6 +504,7 @@ def run_gpu(args):
     hits_per_particle = sum(tot["hits"]) / chunk
 
     check = shard_check(job, args) if not args.no_check else None
+    links = link_probe(job) if world > 1 else None
 
     if rank == 0:
         peaks = {}
@@ -533,6 +569,7 @@ def run_gpu(args):
                         "d2h_bytes_per_step": d2h / K, "rows_per_step": rows / K,
                         "bytes_per_electron": d2h / K / chunk,
                         "form": {"packed": "PTB_COMPACT_PACKED", "narrow": "PTB_COMPACT_NARROW"}.get(host_pipe.form, "PTB_COMPACT"),
+                        "host_ingest": links,
                         "note": "ChunkPipeline.run_to_host: every chunk's hit tables copied to pinned host memory on a "
                                 "second stream in compressed-row form (PtbCompactOut, include/ptb.h: packed = 6-byte rows "
                                 "in three arrays + 4-bit counts per particle and plane + trigger mask; narrow = 7-byte "
