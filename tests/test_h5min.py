@@ -215,3 +215,39 @@ def test_reader_on_a_chunked_table_assembled_by_hand(tmp_path):
 def test_rejects_non_tables(tmp_path):
     with pytest.raises(ValueError):
         h5min.write_table(str(tmp_path / "bad.h5"), "Hits", np.zeros((3, 3)))
+
+
+def test_extents_cover_the_rows_and_the_bounce_path_copies_the_same_bytes(tmp_path, monkeypatch):
+    """TableReader.extents: the raw records of a streamed table as (offset, bytes) runs -- one run when the chunks lie
+    back to back, as TableWriter lays them -- and TableWriter.append_from_file with and without copy_file_range."""
+    a = _hits(5000, seed=3)
+    src = str(tmp_path / "src.h5")
+    h5min.write_table(src, "Hits", a, chunk_rows=512)
+    with h5min.TableReader(src) as r:
+        ext = r.extents("Hits")
+        assert r.dtype_of("Hits") == HITS_DTYPE
+    assert len(ext) == 1 and ext[0][1] == 5000 * 18
+    raw = open(src, "rb").read()
+    assert raw[ext[0][0]:ext[0][0] + ext[0][1]] == a.tobytes()
+    for name, broken in (("kernel.h5", False), ("bounce.h5", True)):
+        if broken:
+            def refuse(*args, **kw):
+                raise OSError(18, "cross-device link")
+            monkeypatch.setattr(os, "copy_file_range", refuse, raising=False)
+        dest = str(tmp_path / name)
+        with h5min.TableWriter(dest, "Hits", HITS_DTYPE, chunk_rows=700) as w:
+            w.append(a[:10])
+            fd = os.open(src, os.O_RDONLY)
+            try:
+                w.append_from_file(fd, ext)
+            finally:
+                os.close(fd)
+            assert w.nrows == 5010
+        assert h5min.read_table(dest, "Hits").tobytes() == np.concatenate([a[:10], a]).tobytes()
+    with h5min.TableWriter(str(tmp_path / "bad.h5"), "Hits", HITS_DTYPE) as w:
+        fd = os.open(src, os.O_RDONLY)
+        try:
+            with pytest.raises(ValueError):
+                w.append_from_file(fd, [(ext[0][0], 19)])            # not a whole number of records
+        finally:
+            os.close(fd)
