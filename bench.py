@@ -443,11 +443,19 @@ def run_gpu(args):
     pipe = ChunkPipeline(sim, chunk, seed=seed)
     host_pipe = ChunkPipeline(sim, chunk, seed=seed, host=True, capacities=pipe.caps, scratch_rows=pipe.rows)
 
+    e2e_shard = {"first": job.first, "chunks": K, "policy": "equal index ranges"}
+
     def run_job(p, to_host):
-        """The timed region: shard prefixes (N>1), then this rank's K chunks."""
-        p.set_bases(*job.bases())
+        """The timed region: shard prefixes (N>1), then this rank's chunks."""
         if to_host:
-            return p.run_to_host(job.first, K)
+            if world > 1:
+                from pytestbeam_b200.distributed import exchange_bases
+                acc, tsum = sim.prefix(e2e_shard["first"], e2e_shard["chunks"] * chunk, seed=seed)
+                p.set_bases(*exchange_bases(acc, tsum, device=sim.device))
+            else:
+                p.set_bases(0, 0)
+            return p.run_to_host(e2e_shard["first"], e2e_shard["chunks"])
+        p.set_bases(*job.bases())
         p.run(job.first, K)
         return None
 
@@ -491,7 +499,24 @@ def run_gpu(args):
     tot = pipe.totals(0)
 
     # end to end through the public API: host buffers, the device->host copy of every chunk's tables inside the timed
-    # region (compressed-row form, include/ptb.h PtbCompactOut; the narrow variant when the set-up fits it)
+    # region (compressed-row form, include/ptb.h PtbCompactOut; the most compressed variant the set-up fits).
+    # N > 1: this pass is bound by what the host takes in over the PCIe links, and the links of one box are not alike
+    # (profiles/README.md), so the same N*K chunks are cut into index-range shards in proportion to the rate every
+    # rank's link reaches while all of them copy (measured here, before the clock starts); the tables do not depend
+    # on where a range is cut (tests/test_gpu_production.py, shard_check)
+    links = link_probe(job) if world > 1 else None
+    if world > 1 and not args.equal_e2e_shards:
+        try:
+            from pytestbeam_b200.pipeline import weighted_shards
+            rates = torch.tensor(links["all_ranks_at_once_GBps"] if rank == 0 else [0.0] * world, dtype=torch.float64,
+                                 device=sim.device)
+            job.dist.broadcast(rates, 0)
+            shards = weighted_shards(K * world, [float(v) for v in rates.cpu()])
+            e2e_shard.update(first=shards[rank][0] * chunk, chunks=shards[rank][1],
+                             policy="index ranges in proportion to the measured link rates",
+                             chunks_per_rank=[k for _, k in shards])
+        except Exception as exc:                      # the probe is a convenience: equal shards remain correct
+            print(f"link-weighted shards unavailable ({exc!r}); equal shards", file=sys.stderr)
     job.sync_all()
     t0 = time.perf_counter()
     e0.record()
@@ -504,7 +529,6 @@ def run_gpu(args):
     hits_per_particle = sum(tot["hits"]) / chunk
 
     check = shard_check(job, args) if not args.no_check else None
-    links = link_probe(job) if world > 1 else None
 
     if rank == 0:
         peaks = {}
@@ -566,10 +590,10 @@ def run_gpu(args):
                 "hits_per_s": value * hits_per_particle,
                 "clocks": clocks,
                 "e2e": {"value": job.total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 0,
-                        "d2h_bytes_per_step": d2h / K, "rows_per_step": rows / K,
-                        "bytes_per_electron": d2h / K / chunk,
+                        "d2h_bytes_per_step": d2h / max(e2e_shard["chunks"], 1), "rows_per_step": rows / max(e2e_shard["chunks"], 1),
+                        "bytes_per_electron": d2h / max(e2e_shard["chunks"], 1) / chunk,
                         "form": {"packed": "PTB_COMPACT_PACKED", "narrow": "PTB_COMPACT_NARROW"}.get(host_pipe.form, "PTB_COMPACT"),
-                        "host_ingest": links,
+                        "host_ingest": links, "shards": {k: v for k, v in e2e_shard.items() if k != "first"},
                         "note": "ChunkPipeline.run_to_host: every chunk's hit tables copied to pinned host memory on a "
                                 "second stream in compressed-row form (PtbCompactOut, include/ptb.h: packed = 6-byte rows "
                                 "in three arrays + 4-bit counts per particle and plane + trigger mask; narrow = 7-byte "
@@ -753,6 +777,8 @@ def main():
     ap.add_argument("--out-dir", default=os.path.join(ROOT, "gpurun_out", "c5"), help="c5: where the HDF5 files go")
     ap.add_argument("--keep-files", action="store_true", help="c5: leave the merged *_dut.h5 files in --out-dir")
     ap.add_argument("--no-check", action="store_true", help="skip the shard check pass")
+    ap.add_argument("--equal-e2e-shards", action="store_true",
+                    help="N > 1: equal index ranges in the end-to-end pass too (default: in proportion to the link rates)")
     ap.add_argument("--check-limit", type=float, default=2.5e10,
                     help="largest job rank 0 repeats alone for the shard check (electrons)")
     ap.add_argument("--no-entry", action="store_true", help="skip the entry-point (files included) measurement")

@@ -314,6 +314,27 @@ def shard_range(n_total: int, rank: int, world: int):
     return lo, hi - lo
 
 
+def weighted_shards(n_units: int, weights) -> list:
+    """Contiguous shards of n_units units, one per rank, sized in proportion to the ranks' weights (largest-remainder
+    rounding, every rank with a positive weight gets at least one unit while units last): [(first unit, units)] in rank
+    order.  Index-range shards keep the reference's row order under rank-order concatenation whatever their sizes; a
+    host that takes rows in faster from some GPUs than from others gives those GPUs more particles."""
+    w = np.asarray(list(weights), dtype=np.float64)
+    if len(w) == 0 or not np.all(np.isfinite(w)) or np.any(w < 0) or w.sum() <= 0:
+        w = np.ones(max(len(w), 1))
+    share = w / w.sum() * n_units
+    n = np.floor(share).astype(np.int64)
+    for i in np.argsort(-(share - n), kind="stable")[:int(n_units - n.sum())]:
+        n[i] += 1
+    for i in np.flatnonzero((n == 0) & (w > 0)):            # nobody idle while another rank has units to spare
+        j = int(np.argmax(n))
+        if n[j] > 1:
+            n[j] -= 1
+            n[i] += 1
+    first = np.concatenate([[0], np.cumsum(n)[:-1]])
+    return [(int(f), int(k)) for f, k in zip(first, n)]
+
+
 def exclusive_prefix(values: np.ndarray, rank: int) -> np.ndarray:
     """Sum of the rows of all lower ranks (values: [world, k])."""
     return values[:rank].sum(axis=0) if rank > 0 else np.zeros(values.shape[1], dtype=values.dtype)

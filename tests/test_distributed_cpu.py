@@ -132,3 +132,16 @@ def test_bench_combines_piecewise_digests_like_one_table():
             lo, hi = cuts[p], cuts[p + 1]
             pieces[p].append(digest([c[lo:hi] for c in cols], mix[lo:hi]))
     assert bench.combine_digests(pieces) == whole
+
+
+def test_weighted_shards_tile_the_units_in_proportion():
+    from pytestbeam_b200.pipeline import weighted_shards
+    s = weighted_shards(80, [11.6] * 4 + [18.1] * 4)
+    assert [k for _, k in s] == [8, 8, 8, 8, 12, 12, 12, 12]
+    assert [f for f, _ in s] == [0, 8, 16, 24, 32, 44, 56, 68]
+    for n, w in ((10, [1, 1, 1]), (7, [0.0, 5.0]), (3, [9, 1, 1, 1]), (100, [57.2, 47.3]), (5, []), (4, [float("nan"), 1])):
+        s = weighted_shards(n, w)
+        assert sum(k for _, k in s) == n and all(k >= 0 for _, k in s)
+        assert [f for f, _ in s] == [sum(k for _, k in s[:i]) for i in range(len(s))]
+    assert weighted_shards(7, [0.0, 5.0]) == [(0, 0), (0, 7)]
+    assert all(k >= 1 for _, k in weighted_shards(4, [100, 1, 1, 1]))
